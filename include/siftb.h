@@ -1,0 +1,154 @@
+/*
+ * siftb.h -- C ABI of libsiftb200.so: the B200 (sm_100a) implementation of the sift_pyocl
+ * keypoint path.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * The reference has no FFI: its boundary is the Python class API (SiftPlan / MatchPlan /
+ * LinearAlign) sitting directly on PyOpenCL enqueue calls.  Each entry point below replaces the
+ * PyOpenCL call sequence cited next to it (paths relative to the reference root); the ctypes
+ * binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (SIFTB_E*); siftb_last_error() gives the
+ *     message of the last failure on the calling thread;
+ *   - images are row-major, dense (stride == width), fp32 unless a dtype code says otherwise;
+ *   - "host" pointers are ordinary CPU memory (pinned memory makes copies asynchronous),
+ *     "dev" pointers are CUDA device memory of the plan's device;
+ *   - a plan owns its device buffers, one CUDA stream and a mutex: calls on one plan serialise
+ *     (reference: threading.Semaphore per plan, plan.py:156,439), different plans run concurrently;
+ *   - keypoint records are the reference's dtype_kp (plan.py:110-115), 144 bytes.
+ */
+#ifndef SIFTB_H
+#define SIFTB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SIFTB_API __attribute__((visibility("default")))
+#else
+#define SIFTB_API
+#endif
+
+#define SIFTB_OK 0
+#define SIFTB_EINVAL (-1)   /* bad argument (reference: RuntimeError / assert, plan.py:151,443,488) */
+#define SIFTB_ECUDA (-2)    /* CUDA runtime error */
+#define SIFTB_ENOMEM (-3)   /* allocation failure (reference: MemoryError, plan.py:365) */
+#define SIFTB_EOVERFLOW (-4) /* keypoint buffer overflow (reference only warns, plan.py:771) */
+
+/* input pixel types accepted by SiftPlan (plan.py:99-106, preprocess.cl:53-223) */
+enum siftb_dtype {
+    SIFTB_F32 = 0, SIFTB_U8 = 1, SIFTB_U16 = 2, SIFTB_U32 = 3, SIFTB_U64 = 4,
+    SIFTB_I32 = 5, SIFTB_I64 = 6, SIFTB_F64 = 7, SIFTB_RGB8 = 8
+};
+
+#define SIFTB_HOST 0
+#define SIFTB_ON_DEVICE 1
+#define SIFTB_IS_F32 2
+
+/* numpy dtype_kp, plan.py:110-115 */
+typedef struct siftb_kp {
+    float x, y, scale, angle;
+    uint8_t desc[128];
+} siftb_kp;
+
+typedef struct siftb_plan siftb_plan;   /* replaces SiftPlan's ctx/queue/buffers, plan.py:117-201 */
+
+SIFTB_API const char *siftb_last_error(void);
+SIFTB_API int siftb_version(void);
+SIFTB_API int siftb_device_count(int *n);                       /* replaces clinit.py:360 select_device */
+
+/* ---- page-locked host memory for asynchronous copies -------------------------------------- */
+SIFTB_API int siftb_host_alloc(void **ptr, uint64_t bytes);
+SIFTB_API int siftb_host_free(void *ptr);
+
+/* ---- SiftPlan ------------------------------------------------------------------------------ */
+/* plan.py:117-201 (__init__: _calc_scales, _calc_memory, _allocate_buffers, _init_gaussian).
+ * octave_max <= 0 means "all octaves" (par.OctaveMax default, param.py:52). */
+SIFTB_API int siftb_plan_create(int height, int width, int dtype, int device, int pix_per_kp, float init_sigma,
+                      int octave_max, siftb_plan **out);
+SIFTB_API int siftb_plan_destroy(siftb_plan *plan);             /* plan.py:203-211 __del__ */
+
+/* read-only facts about a plan: plan.py:213-245 (octave_max, kpsize, scales[o] = (w, h)) */
+SIFTB_API int siftb_plan_octaves(const siftb_plan *plan);
+SIFTB_API int siftb_plan_kpsize(const siftb_plan *plan);
+SIFTB_API int siftb_plan_octave_shape(const siftb_plan *plan, int octave, int *width, int *height);
+SIFTB_API uint64_t siftb_plan_device_bytes(const siftb_plan *plan);   /* plan.py:226 _calc_memory */
+SIFTB_API void *siftb_plan_stream(const siftb_plan *plan);            /* cudaStream_t of the plan's queue */
+SIFTB_API int siftb_plan_set_profile(siftb_plan *plan, int enable);   /* plan.py:185-186 PROFILING_ENABLE */
+
+/* plan.py:432-567 keypoints(): the whole path, blocking.
+ *   image      : height*width pixels of the plan's dtype (RGB8: height*width*3 bytes)
+ *   flags      : SIFTB_HOST (0) = host pointer (copied H->D inside the call);
+ *                SIFTB_ON_DEVICE = device pointer (reference: pyopencl.array.Array input, plan.py:451);
+ *                SIFTB_IS_F32 = the pixels are float32 although the plan was built for another
+ *                dtype (the reference accepts both, plan.py:444,450)
+ *   out/cap    : caller-allocated records; at most cap are written
+ *   n_out      : number of keypoints found (may exceed cap -> SIFTB_EOVERFLOW, out holds cap)
+ *   n_per_octave: optional int[siftb_plan_octaves()] (the "in octave %i found %i kp" log, plan.py:543)
+ *   minmax     : optional float[2] = image min, max (self.buffers["min"], used by alignment.py:345) */
+SIFTB_API int siftb_plan_keypoints(siftb_plan *plan, const void *image, int flags, siftb_kp *out, int cap,
+                         int *n_out, int *n_per_octave, float *minmax);
+
+/* The same path split in two so that callers can overlap the copy of image k+1 with the kernels of
+ * image k: submit() enqueues copy + all kernels on the plan's stream and returns immediately;
+ * collect() waits and copies the records to the host.  One submit may be in flight per plan. */
+SIFTB_API int siftb_plan_submit(siftb_plan *plan, const void *image, int flags);
+SIFTB_API int siftb_plan_collect(siftb_plan *plan, siftb_kp *out, int cap, int *n_out, int *n_per_octave,
+                       float *minmax);
+/* results left on the device (valid until the next submit): records, count */
+SIFTB_API int siftb_plan_result_dev(const siftb_plan *plan, const siftb_kp **dev_records, const int **dev_count);
+
+/* profile=True event list, plan.py:826-847 log_profile: names[i] ran for ms[i] on the device.
+ * Pointers stay valid until the next keypoints()/submit() on the plan. */
+SIFTB_API int siftb_plan_events(siftb_plan *plan, const char *const **names, const float **ms, int *n);
+/* per (octave, scale) stage counters of the last run: int[octaves][3][3] = extrema, after
+ * interpolation, after orientation (what plan.py reads back at :642, :782, :689) */
+SIFTB_API int siftb_plan_stage_counts(siftb_plan *plan, int *counts);
+
+/* ---- stage-level entry points (host pointers; used by the per-kernel parity tests, one per
+ *      reference kernel, mirroring reference test/test_*.py) --------------------------------- */
+/* utils.py:54 kernel_size + plan.py:308-340 _init_gaussian / gaussian.cl:56 */
+SIFTB_API int siftb_gauss_taps(double sigma, float *taps, int cap, int *n);
+/* reductions.cl:62,142 + preprocess.cl:238 normalizes */
+SIFTB_API int siftb_minmax(const float *image, int height, int width, float *minimum, float *maximum);
+SIFTB_API int siftb_normalize(const float *image, int height, int width, float *out);
+/* preprocess.cl *_to_float / rgb_to_float */
+SIFTB_API int siftb_to_float(const void *image, int dtype, int height, int width, float *out);
+/* convolution.cl:16,62 via plan.py:571 _gaussian_convolution (horizontal then vertical) */
+SIFTB_API int siftb_blur(const float *image, int height, int width, const float *taps, int ntaps, float *out);
+/* plan.py:609-625 + :739-745: G[1..5], DoG[0..4] (and G[3][::2, ::2]) of one octave from G[0] */
+SIFTB_API int siftb_pyramid_octave(const float *g0, int height, int width, float init_sigma, float *G5, float *D5,
+                         float *next_base);
+/* image.cl:47 compute_gradient_orientation */
+SIFTB_API int siftb_gradient(const float *image, int height, int width, float *grad, float *ori);
+/* image.cl:119 local_maxmin for scale in {1,2,3} of a 5-plane DoG stack; rows (val,row,col,scale) */
+SIFTB_API int siftb_local_maxmin(const float *dogs5, int height, int width, int scale, int octsize, float *kp4,
+                       int cap, int *n);
+/* image.cl:235 interp_keypoint + algebra.cl:57 compact: in rows (val,row,col,scale), out the
+ * surviving rows (peak,row,col,sigma), compacted */
+SIFTB_API int siftb_interp(const float *dogs5, int height, int width, const float *kp4_in, int n_in, float init_sigma,
+                 float *kp4_out, int *n_out);
+/* orientation_cpu.cl:41: in n rows (peak,row,col,sigma); out n rows (x,y,sigma*oct,angle) followed
+ * by the extra-orientation rows; n_out = total */
+SIFTB_API int siftb_orientation(const float *kp4_in, int n, const float *grad, const float *ori, int height, int width,
+                      int octsize, float *kp4_out, int cap, int *n_out);
+/* keypoints_cpu.cl:36: rows (x,y,sigma*oct,angle) -> uint8[n][128] */
+SIFTB_API int siftb_descriptor(const float *kp4, int n, const float *grad, const float *ori, int height, int width,
+                     int octsize, uint8_t *desc);
+
+/* ---- MatchPlan.match (match.py:200-272, matching_{cpu,gpu}.cl:matching) ---------------------- */
+/* pairs: int[cap][2] = (index in kp1, index in kp2); n = number found (counter, may exceed cap) */
+SIFTB_API int siftb_match_l1(const siftb_kp *kp1, int n1, const siftb_kp *kp2, int n2, float ratio_th, int on_device,
+                   int device, int *pairs, int cap, int *n);
+
+/* ---- LinearAlign's warp (alignment.py:329-349, transform.cl:22 transform) -------------------- */
+SIFTB_API int siftb_transform(const float *image, int height, int width, float *out, int out_height, int out_width,
+                    const float matrix[4], const float offset[2], float fill, int mode, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIFTB_H */

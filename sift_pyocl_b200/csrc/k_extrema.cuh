@@ -1,0 +1,159 @@
+// k_extrema.cuh -- 3x3x3 DoG extrema detection and sub-pixel refinement.
+//
+// k_extrema replaces image.cl:119 local_maxmin (one launch per scale in the reference,
+// plan.py:626-638) plus memset.cl memset_float/_int (plan.py:797): all three scales of an octave in
+// one launch, warp-aggregated append.  k_refine replaces image.cl:235 interp_keypoint AND
+// algebra.cl:57 compact (+ the host round trips of plan.py:642,758-795): rejected candidates are
+// simply not written, so there are no holes to compact.
+#pragma once
+#include "common.cuh"
+
+struct DogStack {
+    const float *d[5];
+    int pitch, w, h;
+};
+
+// image.cl:141-212 for one pixel; returns true when (gid0, gid1, scale) is a keypoint candidate
+__device__ __forceinline__ bool maxmin_pixel(const DogStack &D, int gid0, int gid1, int scale, float peak_thresh,
+                                             float edthresh, float *val_out) {
+    const float *dp = D.d[scale - 1], *dc = D.d[scale], *dn = D.d[scale + 1];
+    const long pos = (long)gid1 * D.pitch + gid0;
+    const float val = dc[pos];
+    *val_out = val;
+    // image.cl:152 -- double comparison (0.8 is a double literal)
+    if (!(fabs((double)val) > (0.8 * (double)peak_thresh))) return false;
+    bool ismax = val > 0.0f, ismin = !ismax;
+#pragma unroll
+    for (int dr = -1; dr <= 1; dr++) {
+#pragma unroll
+        for (int dcx = -1; dcx <= 1; dcx++) {
+            long q = pos + (long)dr * D.pitch + dcx;
+            float a = dp[q], b = dc[q], c = dn[q];
+            if (ismax && (a > val || b > val || c > val)) ismax = false;
+            if (ismin && (a < val || b < val || c < val)) ismin = false;
+        }
+    }
+    if (!(ismax || ismin)) return false;
+    // image.cl:180-186: H00/H11 in double (literal 2.0), H01 float differences then /4.0
+    const long up = pos - D.pitch, dn_ = pos + D.pitch;
+    float H00 = (float)(((double)dc[up] - 2.0 * (double)dc[pos]) + (double)dc[dn_]);
+    float H11 = (float)(((double)dc[pos - 1] - 2.0 * (double)dc[pos]) + (double)dc[pos + 1]);
+    float d1 = dc[dn_ + 1] - dc[dn_ - 1];
+    float d2 = dc[up + 1] - dc[up - 1];
+    float H01 = (float)((double)(d1 - d2) / 4.0);
+    float det = H00 * H11 - H01 * H01, trace = H00 + H11;  // -fmad=false: no contraction
+    float tt = edthresh * trace;
+    tt = tt * trace;
+    if (det < tt) return false;
+    return val != 0.0f;
+}
+
+// grid: (ceil(w/128), h-2*border, 3 scales), block 128 threads along x
+// cand rows: (val, row, col, scale).  counters[0] = total candidates, stage[s-1] = per-scale count.
+__global__ void __launch_bounds__(128) k_extrema(DogStack D, int border, float peak_thresh, float edthresh,
+                                                  float4 *__restrict__ cand, int cap, int *__restrict__ n_cand,
+                                                  int *__restrict__ stage /* [3][3] or null */, int scale_lo) {
+    const int scale = scale_lo + blockIdx.z;
+    const int gid0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gid1 = border + blockIdx.y;
+    bool hit = false;
+    float val = 0.f;
+    if (gid0 >= border && gid0 < D.w - border && gid1 < D.h - border)
+        hit = maxmin_pixel(D, gid0, gid1, scale, peak_thresh, edthresh, &val);
+    unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (m == 0) return;
+    int lane = threadIdx.x & 31, leader = __ffs(m) - 1, base = 0;
+    if (lane == leader) {
+        base = atomicAdd(n_cand, __popc(m));
+        if (stage) atomicAdd(&stage[(scale - 1) * 3 + 0], __popc(m));
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (hit) {
+        int slot = base + __popc(m & lanemask_lt());
+        if (slot < cap) cand[slot] = make_float4(val, (float)gid1, (float)gid0, (float)scale);  // image.cl:202-208
+    }
+}
+
+// image.cl:249-366 for one candidate; returns true if kept, result (peak, row, col, sigma)
+__device__ __forceinline__ bool interp_one(const DogStack &D, float4 k, float peak_thresh, float InitSigma,
+                                           float4 *out) {
+    int r = (int)k.y, c = (int)k.z;
+    const int scale = (int)k.w;
+    const float *Dp = D.d[scale - 1], *Dc = D.d[scale], *Dn = D.d[scale + 1];
+    const int width = D.w, height = D.h, P = D.pitch;
+    float solution0 = 0.f, solution1 = 0.f, solution2 = 0.f, peakval = 0.f;
+    int loop = 1, movesRemain = 5, newr = r, newc = c;
+    while (loop == 1) {
+        r = newr, c = newc;
+        const long pos = (long)newr * P + newc, up = pos - P, dn = pos + P;
+        float g0 = (Dn[pos] - Dp[pos]) / 2.0f;
+        float g1 = (Dc[dn] - Dc[up]) / 2.0f;
+        float g2 = (Dc[pos + 1] - Dc[pos - 1]) / 2.0f;
+        float t2 = 2.0f * Dc[pos];
+        float H00 = (Dp[pos] - t2) + Dn[pos];
+        float H11 = (Dc[up] - t2) + Dc[dn];
+        float H22 = (Dc[pos - 1] - t2) + Dc[pos + 1];
+        float H01 = ((Dn[dn] - Dn[up]) - (Dp[dn] - Dp[up])) / 4.0f;
+        float H02 = ((Dn[pos + 1] - Dn[pos - 1]) - (Dp[pos + 1] - Dp[pos - 1])) / 4.0f;
+        float H12 = ((Dc[dn + 1] - Dc[dn - 1]) - (Dc[up + 1] - Dc[up - 1])) / 4.0f;
+        float H10 = H01, H20 = H02, H21 = H12;
+        // image.cl:300 (left-to-right, no contraction)
+        float t1 = (H02 * H11) * H20, t2b = (H01 * H12) * H20, t3 = (H02 * H10) * H21;
+        float t4 = (H00 * H12) * H21, t5 = (H01 * H10) * H22, t6 = (H00 * H11) * H22;
+        float det = ((((-t1 + t2b) + t3) - t4) - t5) + t6;
+        float K00 = H11 * H22 - H12 * H21;
+        float K01 = H02 * H21 - H01 * H22;
+        float K02 = H01 * H12 - H02 * H11;
+        float K10 = H12 * H20 - H10 * H22;
+        float K11 = H00 * H22 - H02 * H20;
+        float K12 = H02 * H10 - H00 * H12;
+        float K20 = H10 * H21 - H11 * H20;
+        float K21 = H01 * H20 - H00 * H21;
+        float K22 = H00 * H11 - H01 * H10;
+        solution0 = -((g0 * K00 + g1 * K01) + g2 * K02) / det;
+        solution1 = -((g0 * K10 + g1 * K11) + g2 * K12) / det;
+        solution2 = -((g0 * K20 + g1 * K21) + g2 * K22) / det;
+        peakval = Dc[pos] + 0.5f * ((solution0 * g0 + solution1 * g1) + solution2 * g2);
+        if (solution1 > 0.6f && newr < height - 3) newr++;
+        else if (solution1 < -0.6f && newr > 3) newr--;
+        if (solution2 > 0.6f && newc < width - 3) newc++;
+        else if (solution2 < -0.6f && newc > 3) newc--;
+        if (movesRemain > 0 && (newr != r || newc != c)) movesRemain--;
+        else loop = 0;
+    }
+    if (fabsf(solution0) <= 1.5f && fabsf(solution1) <= 1.5f && fabsf(solution2) <= 1.5f &&
+        fabsf(peakval) >= peak_thresh) {
+        out->x = peakval;
+        out->y = (float)r + solution1;
+        out->z = (float)c + solution2;
+        out->w = InitSigma * cr_exp2f((((float)scale) + solution0) / 3.0f);  // pow(2.0f, .), image.cl:355
+        return true;
+    }
+    return false;
+}
+
+// grid-stride over the device-resident candidate count; survivors appended to kp / kp_scale
+__global__ void __launch_bounds__(128) k_refine(DogStack D, const float4 *__restrict__ cand,
+                                                 const int *__restrict__ n_cand, int cap, float peak_thresh,
+                                                 float InitSigma, float4 *__restrict__ kp, int *__restrict__ kp_scale,
+                                                 int *__restrict__ n_kp, int *__restrict__ stage) {
+    const int n = min(*n_cand, cap);
+    const int stride = gridDim.x * blockDim.x;
+    const int rounds = (n + stride - 1) / stride;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int it = 0; it < rounds; it++, i += stride) {
+        bool keep = false;
+        float4 res = make_float4(-1.f, -1.f, -1.f, -1.f);
+        int scale = 0;
+        if (i < n) {
+            float4 k = cand[i];
+            scale = (int)k.w;
+            if ((int)k.y != -1) keep = interp_one(D, k, peak_thresh, InitSigma, &res);
+        }
+        int slot = warp_append(keep, n_kp);
+        if (keep) {
+            if (slot < cap) { kp[slot] = res; kp_scale[slot] = scale; }
+            if (stage) atomicAdd(&stage[(scale - 1) * 3 + 1], 1);
+        }
+    }
+}

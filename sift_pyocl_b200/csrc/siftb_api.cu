@@ -1,0 +1,799 @@
+// siftb_api.cu -- C ABI of libsiftb200.so (see include/siftb.h) and the host-side orchestration
+// that replaces sift-src/plan.py:432-756 (keypoints / _one_octave), match.py:200-272 and the
+// transform launch of alignment.py:329-349.
+//
+// Differences from the reference's control flow (results identical):
+//   * no host round trips inside an image: every count stays on the device and drives the next
+//     kernel through grid-stride loops; one D->H copy of the counters and one of the records at the end;
+//   * the three scales of an octave are processed by single launches (extrema, gradient, orientation,
+//     descriptor), so records of one octave are not grouped by scale (the reference's order inside a
+//     scale group is already nondeterministic: atomic_inc);
+//   * blur + DoG + decimation are one kernel per scale instead of four.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/siftb.h"
+#include "common.cuh"
+#include "k_blur.cuh"
+#include "k_extrema.cuh"
+#include "k_frontend.cuh"
+#include "k_keypoint.cuh"
+#include "k_match.cuh"
+
+#define SIFTB_VERSION 100
+#define MAX_OCT 32
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(e_ == cudaErrorMemoryAllocation ? SIFTB_ENOMEM : SIFTB_ECUDA,                  \
+                        std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" +       \
+                            std::to_string(__LINE__) + ")");                                            \
+    } while (0)
+#define CKL() CK(cudaGetLastError())
+
+// SIFT constants, param.py:52-79
+static const int kScales = 3, kBorderDist = 5;
+static const float kPeakThresh = (float)(255.0 * 0.04 / 3.0), kEdgeThresh = 0.06f, kEdgeThresh1 = 0.08f,
+                   kOriSigma = 1.5f;
+
+static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------
+// taps: utils.py:54-64 kernel_size + plan.py:315-317 numpy formula (identical to the oracle)
+static int kernel_size(double sigma) {
+    int size = (int)ceil(2 * 4 * sigma + 1);
+    if (size % 2 == 0) size += 1;
+    return size;
+}
+static float np_sum_f32(const float *a, int n) {  // numpy pairwise add.reduce, n < 128
+    if (n < 8) {
+        float res = 0.0f;
+        for (int i = 0; i < n; i++) res += a[i];
+        return res;
+    }
+    float r[8];
+    for (int j = 0; j < 8; j++) r[j] = a[j];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8)
+        for (int j = 0; j < 8; j++) r[j] += a[i + j];
+    float res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; i++) res += a[i];
+    return res;
+}
+static void gaussian_taps(double sigma, int size, float *out) {
+    for (int i = 0; i < size; i++) {
+        double x = (double)i - ((double)size - 1.0) / 2.0;
+        double q = x / sigma;
+        out[i] = (float)exp(-(q * q) / 2.0);
+    }
+    float s = np_sum_f32(out, size);
+    for (int i = 0; i < size; i++) out[i] = out[i] / s;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct Event {
+    std::string name;
+    cudaEvent_t a, b;
+};
+
+struct siftb_plan {
+    int device = 0, h = 0, w = 0, dtype = 0, pix_per_kp = 10, n_oct = 0, kpsize = 0;
+    float init_sigma = 1.6f;
+    int ow[MAX_OCT], oh[MAX_OCT], opitch[MAX_OCT];
+    cudaStream_t stream = nullptr;
+    std::mutex mtx;
+    Taps taps[6];
+    int ntaps[6];
+    bool has_init = false;
+    size_t raw_bytes = 0, dev_bytes = 0;
+    void *d_raw = nullptr;     // staging for host input (plan dtype)
+    float *d_img = nullptr;    // dense fp32 plane for converted integer/RGB/f64 input
+    float *G[6] = {}, *D[5] = {}, *grad[3] = {}, *ori[3] = {};
+    float4 *cand = nullptr, *kp = nullptr;
+    int *kp_scale = nullptr;
+    KpRecord *out = nullptr;
+    // device counters: [0]=n_out, [1..]: per octave {n_cand, n_kp, n_extra, n_out_oct}; then stage[n_oct][3][3]; then mm[2]
+    int *d_cnt = nullptr;
+    int *h_cnt = nullptr;  // pinned mirror
+    int cnt_ints = 0;
+    bool in_flight = false, profile = false;
+    std::vector<Event> events;
+    std::vector<const char *> ev_names;
+    std::vector<float> ev_ms;
+
+    int *c_nout() const { return d_cnt; }
+    int *c_oct(int o) const { return d_cnt + 1 + 4 * o; }
+    int *c_stage(int o) const { return d_cnt + 1 + 4 * n_oct + 9 * o; }
+    unsigned *c_mm() const { return reinterpret_cast<unsigned *>(d_cnt + 1 + 13 * n_oct); }
+};
+
+template <typename T>
+static int dalloc(siftb_plan *p, T **ptr, size_t bytes) {
+    CK(cudaMalloc((void **)ptr, bytes));
+    p->dev_bytes += bytes;
+    return 0;
+}
+
+static size_t dtype_bytes(int dtype) {
+    switch (dtype) {
+    case SIFTB_F32: case SIFTB_U32: case SIFTB_I32: return 4;
+    case SIFTB_U8: return 1;
+    case SIFTB_U16: return 2;
+    case SIFTB_U64: case SIFTB_I64: case SIFTB_F64: return 8;
+    case SIFTB_RGB8: return 3;
+    }
+    return 0;
+}
+
+extern "C" const char *siftb_last_error(void) { return g_err.c_str(); }
+extern "C" int siftb_version(void) { return SIFTB_VERSION; }
+extern "C" int siftb_device_count(int *n) {
+    if (!n) return fail(SIFTB_EINVAL, "n is null");
+    CK(cudaGetDeviceCount(n));
+    return 0;
+}
+extern "C" int siftb_host_alloc(void **ptr, uint64_t bytes) {
+    if (!ptr) return fail(SIFTB_EINVAL, "ptr is null");
+    CK(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable));
+    return 0;
+}
+extern "C" int siftb_host_free(void *ptr) {
+    CK(cudaFreeHost(ptr));
+    return 0;
+}
+
+extern "C" int siftb_plan_destroy(siftb_plan *p) {
+    if (!p) return 0;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    cudaFree(p->d_raw); cudaFree(p->d_img);
+    for (auto q : p->G) cudaFree(q);
+    for (auto q : p->D) cudaFree(q);
+    for (auto q : p->grad) cudaFree(q);
+    for (auto q : p->ori) cudaFree(q);
+    cudaFree(p->cand); cudaFree(p->kp); cudaFree(p->kp_scale); cudaFree(p->out); cudaFree(p->d_cnt);
+    if (p->h_cnt) cudaFreeHost(p->h_cnt);
+    for (auto &e : p->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+    return 0;
+}
+
+static int plan_create_impl(siftb_plan *p) {
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    // plan.py:213-224 _calc_scales
+    {
+        int h = p->h, w = p->w, n = 0;
+        const int min_size = 2 * kBorderDist + 2;
+        p->ow[n] = w; p->oh[n] = h; n++;
+        while ((h < w ? h : w) > min_size && n < MAX_OCT) {
+            h /= 2; w /= 2;
+            p->ow[n] = w; p->oh[n] = h; n++;
+        }
+        n--;
+        p->n_oct = n;
+    }
+    if (p->n_oct < 1) return fail(SIFTB_EINVAL, "image too small: min(shape) must exceed 12 (plan.py:216)");
+    for (int o = 0; o < p->n_oct; o++) p->opitch[o] = align_up(p->ow[o], 32);
+    const size_t N = (size_t)p->h * p->w;
+    p->kpsize = (int)(N / p->pix_per_kp);  // plan.py:243
+    // plan.py:297-306 gaussian kernels
+    const double sigmaRatio = pow(2.0, 1.0 / kScales);
+    const double curSigma = 0.5;
+    if ((double)p->init_sigma > curSigma) {
+        double s = sqrt((double)p->init_sigma * (double)p->init_sigma - curSigma * curSigma);
+        p->ntaps[5] = kernel_size(s);
+        if (p->ntaps[5] > SIFTB_MAX_TAPS) return fail(SIFTB_EINVAL, "init_sigma too large");
+        gaussian_taps(s, p->ntaps[5], p->taps[5].f);
+        p->has_init = true;
+    } else {
+        p->ntaps[5] = 1;
+        p->taps[5].f[0] = 1.0f;  // identity "blur": fmaf(x, 1, 0) == x
+    }
+    double prevSigma = (double)p->init_sigma;
+    for (int i = 0; i < kScales + 2; i++) {
+        double increase = prevSigma * sqrt(sigmaRatio * sigmaRatio - 1.0);
+        p->ntaps[i] = kernel_size(increase);
+        if (p->ntaps[i] > SIFTB_MAX_TAPS) return fail(SIFTB_EINVAL, "init_sigma too large");
+        gaussian_taps(increase, p->ntaps[i], p->taps[i].f);
+        prevSigma *= sigmaRatio;
+    }
+    // buffers (plan.py:268-295), planes pitched to 128 B
+    const size_t plane = (size_t)p->opitch[0] * p->oh[0] * sizeof(float);
+    p->raw_bytes = N * (dtype_bytes(p->dtype) > 4 ? dtype_bytes(p->dtype) : 4);  // fp32 input is always accepted
+    int rc;
+    if ((rc = dalloc(p, &p->d_raw, p->raw_bytes))) return rc;
+    if (p->dtype != SIFTB_F32 && (rc = dalloc(p, &p->d_img, N * sizeof(float)))) return rc;
+    for (int i = 0; i < 6; i++) if ((rc = dalloc(p, &p->G[i], plane))) return rc;
+    for (int i = 0; i < 5; i++) if ((rc = dalloc(p, &p->D[i], plane))) return rc;
+    for (int i = 0; i < 3; i++) {
+        if ((rc = dalloc(p, &p->grad[i], plane))) return rc;
+        if ((rc = dalloc(p, &p->ori[i], plane))) return rc;
+    }
+    if ((rc = dalloc(p, &p->cand, (size_t)p->kpsize * sizeof(float4)))) return rc;
+    if ((rc = dalloc(p, &p->kp, (size_t)p->kpsize * sizeof(float4)))) return rc;
+    if ((rc = dalloc(p, &p->kp_scale, (size_t)p->kpsize * sizeof(int)))) return rc;
+    if ((rc = dalloc(p, &p->out, (size_t)p->kpsize * sizeof(KpRecord)))) return rc;
+    p->cnt_ints = 1 + 13 * p->n_oct + 2;
+    if ((rc = dalloc(p, &p->d_cnt, p->cnt_ints * sizeof(int)))) return rc;
+    CK(cudaHostAlloc((void **)&p->h_cnt, p->cnt_ints * sizeof(int), cudaHostAllocDefault));
+    memset(p->h_cnt, 0, p->cnt_ints * sizeof(int));
+    CK(cudaFuncSetAttribute(k_blur_generic, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)blur_generic_smem(SIFTB_MAX_TAPS - 1)));
+    return 0;
+}
+
+extern "C" int siftb_plan_create(int height, int width, int dtype, int device, int pix_per_kp, float init_sigma,
+                                 int octave_max, siftb_plan **out) {
+    if (!out) return fail(SIFTB_EINVAL, "out is null");
+    *out = nullptr;
+    if (height <= 0 || width <= 0) return fail(SIFTB_EINVAL, "bad shape");
+    if (dtype_bytes(dtype) == 0) return fail(SIFTB_EINVAL, "invalid input format error (plan.py:488)");
+    if (pix_per_kp <= 0) pix_per_kp = 10;
+    if (!(init_sigma > 0.f)) init_sigma = 1.6f;
+    siftb_plan *p = new siftb_plan();
+    p->device = device; p->h = height; p->w = width; p->dtype = dtype;
+    p->pix_per_kp = pix_per_kp; p->init_sigma = init_sigma;
+    int rc = plan_create_impl(p);
+    if (rc) {
+        std::string keep = g_err;
+        siftb_plan_destroy(p);
+        g_err = keep;
+        return rc;
+    }
+    if (octave_max > 0 && octave_max < p->n_oct) p->n_oct = octave_max;  // par.OctaveMax
+    *out = p;
+    return 0;
+}
+
+extern "C" int siftb_plan_octaves(const siftb_plan *p) { return p ? p->n_oct : SIFTB_EINVAL; }
+extern "C" int siftb_plan_kpsize(const siftb_plan *p) { return p ? p->kpsize : SIFTB_EINVAL; }
+extern "C" int siftb_plan_octave_shape(const siftb_plan *p, int o, int *w, int *h) {
+    if (!p || o < 0 || o >= p->n_oct) return fail(SIFTB_EINVAL, "bad octave");
+    if (w) *w = p->ow[o];
+    if (h) *h = p->oh[o];
+    return 0;
+}
+extern "C" uint64_t siftb_plan_device_bytes(const siftb_plan *p) { return p ? p->dev_bytes : 0; }
+extern "C" void *siftb_plan_stream(const siftb_plan *p) { return p ? (void *)p->stream : nullptr; }
+extern "C" int siftb_plan_set_profile(siftb_plan *p, int enable) {
+    if (!p) return fail(SIFTB_EINVAL, "plan is null");
+    p->profile = enable != 0;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch helpers (shared by the pipeline and the stage hooks)
+static int launch_blur(cudaStream_t st, const float *in, int in_pitch, int w, int h, float *outG, int out_pitch,
+                       float *outD, float *outHalf, int half_pitch, const Taps &taps, int ntaps,
+                       const unsigned *norm_mm) {
+    BlurArgs a;
+    a.in = in; a.in_pitch = in_pitch; a.outG = outG; a.out_pitch = out_pitch; a.outD = outD;
+    a.outHalf = outHalf; a.half_pitch = half_pitch; a.half_w = w / 2; a.half_h = h / 2;
+    a.w = w; a.h = h; a.ntaps = ntaps; a.norm_mm = norm_mm;
+    dim3 grid((w + BLUR_TW - 1) / BLUR_TW, (h + BLUR_TH - 1) / BLUR_TH);
+    k_blur_generic<<<grid, BLUR_THREADS, blur_generic_smem(ntaps), st>>>(a, taps);
+    CKL();
+    return 0;
+}
+
+static int launch_minmax_f32(cudaStream_t st, const float *img, long n, unsigned *mm) {
+    k_minmax_reset<<<1, 1, 0, st>>>(mm);
+    int vec4 = (n % 4 == 0) && (((uintptr_t)img & 15) == 0);
+    long work = vec4 ? n / 4 : n;
+    int blocks = (int)((work + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    k_minmax_f32<<<blocks, 256, 0, st>>>(img, n, vec4, mm);
+    CKL();
+    return 0;
+}
+
+static int launch_convert(cudaStream_t st, const void *raw, int dtype, long n, float *out, unsigned *mm) {
+    k_minmax_reset<<<1, 1, 0, st>>>(mm);
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    switch (dtype) {
+    case SIFTB_F32: k_convert_minmax<float, false><<<blocks, 256, 0, st>>>((const float *)raw, out, n, mm); break;
+    case SIFTB_U8: k_convert_minmax<uint8_t, false><<<blocks, 256, 0, st>>>((const uint8_t *)raw, out, n, mm); break;
+    case SIFTB_U16: k_convert_minmax<uint16_t, false><<<blocks, 256, 0, st>>>((const uint16_t *)raw, out, n, mm); break;
+    case SIFTB_U32: k_convert_minmax<uint32_t, false><<<blocks, 256, 0, st>>>((const uint32_t *)raw, out, n, mm); break;
+    case SIFTB_U64: k_convert_minmax<unsigned long long, false><<<blocks, 256, 0, st>>>((const unsigned long long *)raw, out, n, mm); break;
+    case SIFTB_I32: k_convert_minmax<int32_t, false><<<blocks, 256, 0, st>>>((const int32_t *)raw, out, n, mm); break;
+    case SIFTB_I64: k_convert_minmax<long long, false><<<blocks, 256, 0, st>>>((const long long *)raw, out, n, mm); break;
+    case SIFTB_F64: k_convert_minmax<double, false><<<blocks, 256, 0, st>>>((const double *)raw, out, n, mm); break;
+    case SIFTB_RGB8: k_convert_minmax<uint8_t, true><<<blocks, 256, 0, st>>>((const uint8_t *)raw, out, n, mm); break;
+    default: return fail(SIFTB_EINVAL, "invalid input format error (plan.py:488)");
+    }
+    CKL();
+    return 0;
+}
+
+static DogStack make_dogstack(float *const D[5], int pitch, int w, int h) {
+    DogStack s;
+    for (int i = 0; i < 5; i++) s.d[i] = D[i];
+    s.pitch = pitch; s.w = w; s.h = h;
+    return s;
+}
+
+struct ProfScope {
+    siftb_plan *p;
+    int idx = -1;
+    ProfScope(siftb_plan *p_, const char *name, int o = -1) : p(p_) {
+        if (!p->profile) return;
+        Event e;
+        e.name = name;
+        if (o >= 0) e.name += " octave " + std::to_string(o);
+        cudaEventCreate(&e.a);
+        cudaEventCreate(&e.b);
+        cudaEventRecord(e.a, p->stream);
+        p->events.push_back(e);
+        idx = (int)p->events.size() - 1;
+    }
+    ~ProfScope() {
+        if (idx >= 0) cudaEventRecord(p->events[idx].b, p->stream);
+    }
+};
+
+// plan.py:432-543 + :596-756, everything enqueued on the plan's stream
+static int submit_impl(siftb_plan *p, const void *image, int flags) {
+    const int on_device = flags & SIFTB_ON_DEVICE;
+    const int dtype = (flags & SIFTB_IS_F32) ? SIFTB_F32 : p->dtype;
+    CK(cudaSetDevice(p->device));
+    cudaStream_t st = p->stream;
+    for (auto &e : p->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    p->events.clear();
+    const long N = (long)p->h * p->w;
+    const void *src = image;
+    if (!on_device) {
+        ProfScope ps(p, "copy H->D");
+        CK(cudaMemcpyAsync(p->d_raw, image, (size_t)N * dtype_bytes(dtype), cudaMemcpyHostToDevice, st));
+        src = p->d_raw;
+    }
+    CK(cudaMemsetAsync(p->d_cnt, 0, p->cnt_ints * sizeof(int), st));
+    unsigned *mm = p->c_mm();
+    const float *img;
+    int rc;
+    {
+        ProfScope ps(p, dtype == SIFTB_F32 ? "max_min" : "convert -> float + max_min");
+        if (dtype == SIFTB_F32) {
+            if ((rc = launch_minmax_f32(st, (const float *)src, N, mm))) return rc;
+            img = (const float *)src;
+        } else {
+            if ((rc = launch_convert(st, src, dtype, N, p->d_img, mm))) return rc;
+            img = p->d_img;
+        }
+    }
+    {   // normalize fused into the initial blur (sigma = sqrt(init^2 - 0.5^2)), plan.py:525-539
+        ProfScope ps(p, "normalize + init blur");
+        if ((rc = launch_blur(st, img, p->w, p->w, p->h, p->G[0], p->opitch[0], nullptr, nullptr, 0, p->taps[5],
+                              p->ntaps[5], mm)))
+            return rc;
+    }
+    for (int o = 0; o < p->n_oct; o++) {
+        const int w = p->ow[o], h = p->oh[o], pitch = p->opitch[o];
+        const int octsize = 1 << o;
+        int *c = p->c_oct(o);
+        int *stage = p->c_stage(o);
+        {
+            ProfScope ps(p, "blur + DoG", o);
+            for (int s = 0; s < kScales + 2; s++) {
+                float *half = nullptr;
+                int hp = 0;
+                if (s == kScales - 1 && o + 1 < p->n_oct) { half = p->G[0]; hp = p->opitch[o + 1]; }
+                if ((rc = launch_blur(st, p->G[s], pitch, w, h, p->G[s + 1], pitch, p->D[s], half, hp, p->taps[s],
+                                      p->ntaps[s], nullptr)))
+                    return rc;
+            }
+        }
+        DogStack ds = make_dogstack(p->D, pitch, w, h);
+        if (w > 2 * kBorderDist && h > 2 * kBorderDist) {
+            ProfScope ps(p, "local_maxmin", o);
+            dim3 grid((w + 127) / 128, h - 2 * kBorderDist, kScales);
+            k_extrema<<<grid, 128, 0, st>>>(ds, kBorderDist, kPeakThresh, octsize <= 1 ? kEdgeThresh1 : kEdgeThresh,
+                                            p->cand, p->kpsize, c + 0, stage, 1);
+            CKL();
+        }
+        {
+            ProfScope ps(p, "interp_keypoint + compact", o);
+            k_refine<<<148 * 4, 128, 0, st>>>(ds, p->cand, c + 0, p->kpsize, kPeakThresh, p->init_sigma, p->kp,
+                                              p->kp_scale, c + 1, stage);
+            CKL();
+        }
+        GradPlanes gp;
+        for (int i = 0; i < 3; i++) { gp.grad[i] = p->grad[i]; gp.ori[i] = p->ori[i]; }
+        gp.pitch = pitch; gp.w = w; gp.h = h;
+        {
+            ProfScope ps(p, "compute_gradient_orientation", o);
+            GradArgs ga;
+            for (int i = 0; i < 3; i++) { ga.g[i] = p->G[i + 1]; ga.grad[i] = p->grad[i]; ga.ori[i] = p->ori[i]; }
+            ga.pitch = pitch; ga.w = w; ga.h = h;
+            dim3 grid((w + 255) / 256, h, 3);
+            k_gradient<<<grid, 256, 0, st>>>(ga);
+            CKL();
+        }
+        {
+            ProfScope ps(p, "orientation_assignment", o);
+            k_orient<<<148 * 4, 256, 0, st>>>(gp, p->kp, p->kp_scale, c + 1, c + 2, p->kpsize, octsize, kOriSigma,
+                                              stage);
+            CKL();
+        }
+        {
+            ProfScope ps(p, "descriptors", o);
+            k_describe<<<148 * 16, 64, 0, st>>>(gp, p->kp, p->kp_scale, c + 1, c + 2, p->kpsize, octsize, p->out,
+                                                p->kpsize, p->c_nout(), c + 3);
+            CKL();
+        }
+    }
+    CK(cudaMemcpyAsync(p->h_cnt, p->d_cnt, p->cnt_ints * sizeof(int), cudaMemcpyDeviceToHost, st));
+    p->in_flight = true;
+    return 0;
+}
+
+static int collect_impl(siftb_plan *p, siftb_kp *out, int cap, int *n_out, int *n_per_octave, float *minmax) {
+    if (!p->in_flight) return fail(SIFTB_EINVAL, "collect without submit");
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->stream));
+    p->in_flight = false;
+    const int n = p->h_cnt[0];
+    int rc = 0;
+    int ncopy = n;
+    if (ncopy > p->kpsize) { ncopy = p->kpsize; rc = SIFTB_EOVERFLOW; }
+    if (ncopy > cap) { ncopy = cap; rc = SIFTB_EOVERFLOW; }
+    for (int o = 0; o < p->n_oct; o++) {
+        const int *c = p->h_cnt + 1 + 4 * o;
+        if (c[0] > p->kpsize || c[1] + c[2] > p->kpsize) rc = SIFTB_EOVERFLOW;
+        if (n_per_octave) n_per_octave[o] = c[3];
+    }
+    if (minmax) {
+        const unsigned *mm = reinterpret_cast<const unsigned *>(p->h_cnt + 1 + 13 * p->n_oct);
+        unsigned u0 = mm[0], u1 = mm[1];
+        uint32_t a = (u0 & 0x80000000u) ? (u0 & 0x7fffffffu) : ~u0, b = (u1 & 0x80000000u) ? (u1 & 0x7fffffffu) : ~u1;
+        memcpy(&minmax[0], &a, 4);
+        memcpy(&minmax[1], &b, 4);
+    }
+    if (out && ncopy > 0) {
+        CK(cudaMemcpyAsync(out, p->out, (size_t)ncopy * sizeof(siftb_kp), cudaMemcpyDeviceToHost, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+    }
+    if (n_out) *n_out = n;
+    if (rc == SIFTB_EOVERFLOW) return fail(rc, "keypoint buffer overflow (reference: plan.py:771 warning)");
+    return 0;
+}
+
+extern "C" int siftb_plan_submit(siftb_plan *p, const void *image, int flags) {
+    if (!p || !image) return fail(SIFTB_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(p->mtx);
+    if (p->in_flight) return fail(SIFTB_EINVAL, "a submit is already in flight on this plan");
+    return submit_impl(p, image, flags);
+}
+extern "C" int siftb_plan_collect(siftb_plan *p, siftb_kp *out, int cap, int *n_out, int *n_per_octave,
+                                  float *minmax) {
+    if (!p) return fail(SIFTB_EINVAL, "null plan");
+    std::lock_guard<std::mutex> lk(p->mtx);
+    return collect_impl(p, out, cap, n_out, n_per_octave, minmax);
+}
+extern "C" int siftb_plan_keypoints(siftb_plan *p, const void *image, int flags, siftb_kp *out, int cap,
+                                    int *n_out, int *n_per_octave, float *minmax) {
+    if (!p || !image) return fail(SIFTB_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(p->mtx);
+    if (p->in_flight) return fail(SIFTB_EINVAL, "a submit is already in flight on this plan");
+    int rc = submit_impl(p, image, flags);
+    if (rc) return rc;
+    return collect_impl(p, out, cap, n_out, n_per_octave, minmax);
+}
+extern "C" int siftb_plan_result_dev(const siftb_plan *p, const siftb_kp **recs, const int **count) {
+    if (!p) return fail(SIFTB_EINVAL, "null plan");
+    if (recs) *recs = reinterpret_cast<const siftb_kp *>(p->out);
+    if (count) *count = p->d_cnt;
+    return 0;
+}
+extern "C" int siftb_plan_events(siftb_plan *p, const char *const **names, const float **ms, int *n) {
+    if (!p) return fail(SIFTB_EINVAL, "null plan");
+    std::lock_guard<std::mutex> lk(p->mtx);
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->stream));
+    p->ev_names.clear();
+    p->ev_ms.clear();
+    for (auto &e : p->events) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, e.a, e.b);
+        p->ev_names.push_back(e.name.c_str());
+        p->ev_ms.push_back(t);
+    }
+    if (names) *names = p->ev_names.data();
+    if (ms) *ms = p->ev_ms.data();
+    if (n) *n = (int)p->events.size();
+    return 0;
+}
+extern "C" int siftb_plan_stage_counts(siftb_plan *p, int *counts) {
+    if (!p || !counts) return fail(SIFTB_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(p->mtx);
+    memcpy(counts, p->h_cnt + 1 + 4 * p->n_oct, sizeof(int) * 9 * p->n_oct);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage-level hooks: host in, host out, temporaries on the current device, default stream
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <typename T> T *as() { return (T *)p; }
+};
+#define DALLOC(buf, bytes) CK((buf).alloc(bytes))
+
+extern "C" int siftb_gauss_taps(double sigma, float *taps, int cap, int *n) {
+    if (!taps || !n || !(sigma > 0)) return fail(SIFTB_EINVAL, "bad argument");
+    int size = kernel_size(sigma);
+    if (size > cap) return fail(SIFTB_EINVAL, "taps buffer too small");
+    gaussian_taps(sigma, size, taps);
+    *n = size;
+    return 0;
+}
+
+extern "C" int siftb_minmax(const float *image, int height, int width, float *minimum, float *maximum) {
+    if (!image || height <= 0 || width <= 0) return fail(SIFTB_EINVAL, "bad argument");
+    const long n = (long)height * width;
+    DevBuf d, mm;
+    DALLOC(d, n * 4); DALLOC(mm, 8);
+    CK(cudaMemcpy(d.p, image, n * 4, cudaMemcpyHostToDevice));
+    int rc = launch_minmax_f32(0, d.as<float>(), n, mm.as<unsigned>());
+    if (rc) return rc;
+    unsigned h[2];
+    CK(cudaMemcpy(h, mm.p, 8, cudaMemcpyDeviceToHost));
+    uint32_t a = (h[0] & 0x80000000u) ? (h[0] & 0x7fffffffu) : ~h[0], b = (h[1] & 0x80000000u) ? (h[1] & 0x7fffffffu) : ~h[1];
+    if (minimum) memcpy(minimum, &a, 4);
+    if (maximum) memcpy(maximum, &b, 4);
+    return 0;
+}
+
+extern "C" int siftb_normalize(const float *image, int height, int width, float *out) {
+    if (!image || !out || height <= 0 || width <= 0) return fail(SIFTB_EINVAL, "bad argument");
+    const long n = (long)height * width;
+    DevBuf d, o, mm;
+    DALLOC(d, n * 4); DALLOC(o, n * 4); DALLOC(mm, 8);
+    CK(cudaMemcpy(d.p, image, n * 4, cudaMemcpyHostToDevice));
+    int rc = launch_minmax_f32(0, d.as<float>(), n, mm.as<unsigned>());
+    if (rc) return rc;
+    k_normalize<<<148 * 8, 256>>>(d.as<float>(), o.as<float>(), n, mm.as<unsigned>());
+    CKL();
+    CK(cudaMemcpy(out, o.p, n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int siftb_to_float(const void *image, int dtype, int height, int width, float *out) {
+    if (!image || !out || height <= 0 || width <= 0 || !dtype_bytes(dtype)) return fail(SIFTB_EINVAL, "bad argument");
+    const long n = (long)height * width;
+    DevBuf d, o, mm;
+    DALLOC(d, n * dtype_bytes(dtype)); DALLOC(o, n * 4); DALLOC(mm, 8);
+    CK(cudaMemcpy(d.p, image, n * dtype_bytes(dtype), cudaMemcpyHostToDevice));
+    int rc = launch_convert(0, d.p, dtype, n, o.as<float>(), mm.as<unsigned>());
+    if (rc) return rc;
+    CK(cudaMemcpy(out, o.p, n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+static int ensure_blur_attr() {
+    CK(cudaFuncSetAttribute(k_blur_generic, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)blur_generic_smem(SIFTB_MAX_TAPS - 1)));
+    return 0;
+}
+
+extern "C" int siftb_blur(const float *image, int height, int width, const float *taps, int ntaps, float *out) {
+    if (!image || !out || !taps || height <= 0 || width <= 0) return fail(SIFTB_EINVAL, "bad argument");
+    if (ntaps < 1 || ntaps > SIFTB_MAX_TAPS || !(ntaps & 1)) return fail(SIFTB_EINVAL, "ntaps must be odd and <= 63");
+    if (ntaps / 2 > (height < width ? height : width)) return fail(SIFTB_EINVAL, "kernel wider than the image");
+    int rc = ensure_blur_attr();
+    if (rc) return rc;
+    const long n = (long)height * width;
+    DevBuf d, o;
+    DALLOC(d, n * 4); DALLOC(o, n * 4);
+    CK(cudaMemcpy(d.p, image, n * 4, cudaMemcpyHostToDevice));
+    Taps t;
+    memset(&t, 0, sizeof(t));
+    memcpy(t.f, taps, ntaps * sizeof(float));
+    rc = launch_blur(0, d.as<float>(), width, width, height, o.as<float>(), width, nullptr, nullptr, 0, t, ntaps, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(out, o.p, n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int siftb_pyramid_octave(const float *g0, int height, int width, float init_sigma, float *G5, float *D5,
+                                    float *next_base) {
+    if (!g0 || height <= 0 || width <= 0) return fail(SIFTB_EINVAL, "bad argument");
+    int rc = ensure_blur_attr();
+    if (rc) return rc;
+    const long n = (long)height * width;
+    const int hw = width / 2, hh = height / 2;
+    DevBuf G, D, half;
+    DALLOC(G, 6 * n * 4); DALLOC(D, 5 * n * 4); DALLOC(half, (size_t)hw * hh * 4);
+    CK(cudaMemcpy(G.p, g0, n * 4, cudaMemcpyHostToDevice));
+    const double sigmaRatio = pow(2.0, 1.0 / kScales);
+    double prevSigma = (double)init_sigma;
+    for (int s = 0; s < kScales + 2; s++) {
+        double increase = prevSigma * sqrt(sigmaRatio * sigmaRatio - 1.0);
+        Taps t;
+        memset(&t, 0, sizeof(t));
+        int nt = kernel_size(increase);
+        if (nt > SIFTB_MAX_TAPS) return fail(SIFTB_EINVAL, "init_sigma too large");
+        gaussian_taps(increase, nt, t.f);
+        prevSigma *= sigmaRatio;
+        rc = launch_blur(0, G.as<float>() + s * n, width, width, height, G.as<float>() + (s + 1) * n, width,
+                         D.as<float>() + s * n, (s == kScales - 1 && hw > 0 && hh > 0) ? half.as<float>() : nullptr, hw,
+                         t, nt, nullptr);
+        if (rc) return rc;
+    }
+    if (G5) CK(cudaMemcpy(G5, G.as<float>() + n, 5 * n * 4, cudaMemcpyDeviceToHost));
+    if (D5) CK(cudaMemcpy(D5, D.p, 5 * n * 4, cudaMemcpyDeviceToHost));
+    if (next_base && hw > 0 && hh > 0) CK(cudaMemcpy(next_base, half.p, (size_t)hw * hh * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int siftb_gradient(const float *image, int height, int width, float *grad, float *ori) {
+    if (!image || !grad || !ori || height < 2 || width < 2) return fail(SIFTB_EINVAL, "bad argument");
+    const long n = (long)height * width;
+    DevBuf d, g, o;
+    DALLOC(d, n * 4); DALLOC(g, n * 4); DALLOC(o, n * 4);
+    CK(cudaMemcpy(d.p, image, n * 4, cudaMemcpyHostToDevice));
+    GradArgs ga;
+    for (int i = 0; i < 3; i++) { ga.g[i] = d.as<float>(); ga.grad[i] = g.as<float>(); ga.ori[i] = o.as<float>(); }
+    ga.pitch = width; ga.w = width; ga.h = height;
+    dim3 grid((width + 255) / 256, height, 1);
+    k_gradient<<<grid, 256>>>(ga);
+    CKL();
+    CK(cudaMemcpy(grad, g.p, n * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ori, o.p, n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int siftb_local_maxmin(const float *dogs5, int height, int width, int scale, int octsize, float *kp4,
+                                  int cap, int *n) {
+    if (!dogs5 || !kp4 || !n || scale < 1 || scale > 3 || cap < 0) return fail(SIFTB_EINVAL, "bad argument");
+    const long np = (long)height * width;
+    DevBuf D, K, C;
+    DALLOC(D, 5 * np * 4); DALLOC(K, (size_t)cap * 16); DALLOC(C, 4);
+    CK(cudaMemcpy(D.p, dogs5, 5 * np * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemset(C.p, 0, 4));
+    CK(cudaMemset(K.p, 0, (size_t)cap * 16));
+    if (width > 2 * kBorderDist && height > 2 * kBorderDist) {
+        float *Dp[5];
+        for (int i = 0; i < 5; i++) Dp[i] = D.as<float>() + i * np;
+        DogStack ds = make_dogstack(Dp, width, width, height);
+        dim3 grid((width + 127) / 128, height - 2 * kBorderDist, 1);
+        k_extrema<<<grid, 128>>>(ds, kBorderDist, kPeakThresh, octsize <= 1 ? kEdgeThresh1 : kEdgeThresh,
+                                 K.as<float4>(), cap, C.as<int>(), nullptr, scale);
+        CKL();
+    }
+    CK(cudaMemcpy(n, C.p, 4, cudaMemcpyDeviceToHost));
+    int m = *n < cap ? *n : cap;
+    if (m > 0) CK(cudaMemcpy(kp4, K.p, (size_t)m * 16, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int siftb_interp(const float *dogs5, int height, int width, const float *kp4_in, int n_in, float init_sigma,
+                            float *kp4_out, int *n_out) {
+    if (!dogs5 || !kp4_in || !kp4_out || !n_out || n_in < 0) return fail(SIFTB_EINVAL, "bad argument");
+    const long np = (long)height * width;
+    DevBuf D, Kin, Kout, S, C;
+    DALLOC(D, 5 * np * 4); DALLOC(Kin, (size_t)n_in * 16); DALLOC(Kout, (size_t)n_in * 16); DALLOC(S, (size_t)n_in * 4);
+    DALLOC(C, 8);
+    CK(cudaMemcpy(D.p, dogs5, 5 * np * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(Kin.p, kp4_in, (size_t)n_in * 16, cudaMemcpyHostToDevice));
+    int cnt[2] = {n_in, 0};
+    CK(cudaMemcpy(C.p, cnt, 8, cudaMemcpyHostToDevice));
+    float *Dp[5];
+    for (int i = 0; i < 5; i++) Dp[i] = D.as<float>() + i * np;
+    DogStack ds = make_dogstack(Dp, width, width, height);
+    k_refine<<<148 * 4, 128>>>(ds, Kin.as<float4>(), C.as<int>(), n_in, kPeakThresh, init_sigma, Kout.as<float4>(),
+                               S.as<int>(), C.as<int>() + 1, nullptr);
+    CKL();
+    CK(cudaMemcpy(cnt, C.p, 8, cudaMemcpyDeviceToHost));
+    *n_out = cnt[1];
+    if (cnt[1] > 0) CK(cudaMemcpy(kp4_out, Kout.p, (size_t)cnt[1] * 16, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int siftb_orientation(const float *kp4_in, int n, const float *grad, const float *ori, int height, int width,
+                                 int octsize, float *kp4_out, int cap, int *n_out) {
+    if (!kp4_in || !grad || !ori || !kp4_out || !n_out || n < 0 || cap < n) return fail(SIFTB_EINVAL, "bad argument");
+    const long np = (long)height * width;
+    DevBuf Gd, Od, K, S, C;
+    DALLOC(Gd, np * 4); DALLOC(Od, np * 4); DALLOC(K, (size_t)cap * 16); DALLOC(S, (size_t)cap * 4); DALLOC(C, 8);
+    CK(cudaMemcpy(Gd.p, grad, np * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(Od.p, ori, np * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(K.p, kp4_in, (size_t)n * 16, cudaMemcpyHostToDevice));
+    std::vector<int> ones(cap > 0 ? cap : 1, 1);
+    CK(cudaMemcpy(S.p, ones.data(), (size_t)cap * 4, cudaMemcpyHostToDevice));
+    int cnt[2] = {n, 0};
+    CK(cudaMemcpy(C.p, cnt, 8, cudaMemcpyHostToDevice));
+    GradPlanes gp;
+    for (int i = 0; i < 3; i++) { gp.grad[i] = Gd.as<float>(); gp.ori[i] = Od.as<float>(); }
+    gp.pitch = width; gp.w = width; gp.h = height;
+    k_orient<<<148 * 4, 256>>>(gp, K.as<float4>(), S.as<int>(), C.as<int>(), C.as<int>() + 1, cap, octsize, kOriSigma,
+                               nullptr);
+    CKL();
+    CK(cudaMemcpy(cnt, C.p, 8, cudaMemcpyDeviceToHost));
+    int total = n + cnt[1];
+    *n_out = total;
+    if (total > cap) total = cap;
+    if (total > 0) CK(cudaMemcpy(kp4_out, K.p, (size_t)total * 16, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int siftb_descriptor(const float *kp4, int n, const float *grad, const float *ori, int height, int width,
+                                int octsize, uint8_t *desc) {
+    if (!kp4 || !grad || !ori || !desc || n < 0) return fail(SIFTB_EINVAL, "bad argument");
+    const long np = (long)height * width;
+    DevBuf Gd, Od, K, Dd;
+    DALLOC(Gd, np * 4); DALLOC(Od, np * 4); DALLOC(K, (size_t)n * 16); DALLOC(Dd, (size_t)n * 128);
+    CK(cudaMemcpy(Gd.p, grad, np * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(Od.p, ori, np * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(K.p, kp4, (size_t)n * 16, cudaMemcpyHostToDevice));
+    CK(cudaMemset(Dd.p, 0, (size_t)n * 128));
+    if (n > 0) {
+        k_describe_rows<<<(n + 63) / 64, 64>>>(Gd.as<float>(), Od.as<float>(), width, width, height, K.as<float4>(), n,
+                                               octsize, Dd.as<uint8_t>());
+        CKL();
+        CK(cudaMemcpy(desc, Dd.p, (size_t)n * 128, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+extern "C" int siftb_match_l1(const siftb_kp *kp1, int n1, const siftb_kp *kp2, int n2, float ratio_th, int on_device,
+                              int device, int *pairs, int cap, int *n) {
+    if (!n || n1 < 0 || n2 < 0 || cap < 0 || (n1 && !kp1) || (n2 && !kp2)) return fail(SIFTB_EINVAL, "bad argument");
+    *n = 0;
+    if (n1 == 0) return 0;
+    CK(cudaSetDevice(device));
+    DevBuf R1, R2, D1, D2, P, C;
+    const uint8_t *r1 = (const uint8_t *)kp1, *r2 = (const uint8_t *)kp2;
+    if (!on_device) {
+        DALLOC(R1, (size_t)n1 * 144); DALLOC(R2, (size_t)n2 * 144);
+        CK(cudaMemcpy(R1.p, kp1, (size_t)n1 * 144, cudaMemcpyHostToDevice));
+        if (n2) CK(cudaMemcpy(R2.p, kp2, (size_t)n2 * 144, cudaMemcpyHostToDevice));
+        r1 = R1.as<uint8_t>(); r2 = R2.as<uint8_t>();
+    }
+    DALLOC(D1, (size_t)n1 * 128); DALLOC(D2, (size_t)n2 * 128); DALLOC(P, (size_t)cap * 8); DALLOC(C, 4);
+    CK(cudaMemset(C.p, 0, 4));
+    k_extract_desc<<<(int)(((long)n1 * 32 + 255) / 256), 256>>>(r1, n1, D1.as<uint32_t>());
+    if (n2) k_extract_desc<<<(int)(((long)n2 * 32 + 255) / 256), 256>>>(r2, n2, D2.as<uint32_t>());
+    CKL();
+    k_match_l1<<<(n1 + 127) / 128, 128>>>(D1.as<uint32_t>(), n1, D2.as<uint32_t>(), n2, ratio_th, P.as<int2>(), cap,
+                                          C.as<int>());
+    CKL();
+    CK(cudaMemcpy(n, C.p, 4, cudaMemcpyDeviceToHost));
+    int m = *n < cap ? *n : cap;
+    if (m > 0 && pairs) CK(cudaMemcpy(pairs, P.p, (size_t)m * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int siftb_transform(const float *image, int height, int width, float *out, int out_height, int out_width,
+                               const float matrix[4], const float offset[2], float fill, int mode, int device) {
+    if (!image || !out || !matrix || !offset || height <= 0 || width <= 0 || out_height <= 0 || out_width <= 0)
+        return fail(SIFTB_EINVAL, "bad argument");
+    CK(cudaSetDevice(device));
+    DevBuf I, O;
+    DALLOC(I, (size_t)height * width * 4); DALLOC(O, (size_t)out_height * out_width * 4);
+    CK(cudaMemcpy(I.p, image, (size_t)height * width * 4, cudaMemcpyHostToDevice));
+    dim3 grid((out_width + 255) / 256, out_height);
+    k_transform<<<grid, 256>>>(I.as<float>(), O.as<float>(), matrix[0], matrix[1], matrix[2], matrix[3], offset[0],
+                               offset[1], width, height, out_width, out_height, fill, mode);
+    CKL();
+    CK(cudaMemcpy(out, O.p, (size_t)out_height * out_width * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}

@@ -1,0 +1,290 @@
+"""SiftPlan: keypoints of an image -- same public surface as the reference's sift-src/plan.py.
+
+    import sift_pyocl_b200 as sift
+    plan = sift.SiftPlan(template=img)           # or shape=..., dtype=...
+    kp = plan.keypoints(img)                      # numpy.recarray of dtype_kp (x, y, scale, angle, desc)
+
+Everything under the class boundary is new: the host stays Python and calls hand-written sm_100a
+CUDA through the C ABI of include/siftb.h (ctypes).  There is no PyOpenCL and no CPU fallback.
+"""
+import ctypes
+import logging
+import threading
+import time
+
+import numpy
+
+from . import _lib
+from .param import par
+from .utils import kernel_size
+
+logger = logging.getLogger("sift.plan")
+
+
+class _DeviceScalar(object):
+    """Stand-in for the reference's ``plan.buffers["min"]`` pyopencl array (alignment.py:345 calls
+    ``.get()[0]`` on it)."""
+
+    def __init__(self):
+        self.value = numpy.zeros(1, numpy.float32)
+
+    def get(self):
+        return self.value.copy()
+
+
+class SiftPlan(object):
+    """How to calculate a set of SIFT keypoints on an image (reference plan.py:70-119).
+
+    Keyword arguments keep the reference's names and meaning.  ``devicetype``,
+    ``max_workgroup_size`` and ``context`` (OpenCL notions) are accepted and ignored; ``device``
+    selects the CUDA device: an integer ordinal, or the reference's (platform, device) 2-tuple of
+    which the second entry is used.
+    """
+    converter = {numpy.dtype(numpy.uint8): "u8_to_float",
+                 numpy.dtype(numpy.uint16): "u16_to_float",
+                 numpy.dtype(numpy.uint32): "u32_to_float",
+                 numpy.dtype(numpy.uint64): "u64_to_float",
+                 numpy.dtype(numpy.int32): "s32_to_float",
+                 numpy.dtype(numpy.int64): "s64_to_float"}
+    sigmaRatio = 2.0 ** (1.0 / par.Scales)
+    PIX_PER_KP = 10  # pre-allocate one keypoint slot per 10 pixels (reference plan.py:109)
+    dtype_kp = _lib.dtype_kp
+
+    def __init__(self, shape=None, dtype=None, devicetype="CPU", template=None,
+                 profile=False, device=None, PIX_PER_KP=None,
+                 max_workgroup_size=None, context=None, init_sigma=None):
+        if init_sigma is None:
+            init_sigma = par.InitSigma
+        self._init_sigma = float(init_sigma)
+        self.buffers = {"min": _DeviceScalar(), "max": _DeviceScalar()}
+        self.programs = {}
+        self._plan = None
+        if template is not None:
+            self.shape = tuple(template.shape)
+            self.dtype = _np_dtype(template.dtype)
+        else:
+            self.shape = tuple(shape)
+            self.dtype = numpy.dtype(dtype)
+        if len(self.shape) == 3:
+            self.RGB = True
+            self.shape = self.shape[:2]
+        elif len(self.shape) == 2:
+            self.RGB = False
+        else:
+            raise RuntimeError("Unable to process image of shape %s" % (tuple(self.shape,)))
+        if PIX_PER_KP:
+            self.PIX_PER_KP = int(PIX_PER_KP)
+        self.profile = bool(profile)
+        self.events = []
+        self._sem = threading.Semaphore()
+        self.devicetype = "GPU"
+        self.max_workgroup_size = max_workgroup_size
+        self.ctx = context
+        self.queue = None
+        if device is None:
+            self.device = 0
+        elif "__len__" in dir(device):
+            self.device = int(device[-1])
+        else:
+            self.device = int(device)
+        if self.RGB:
+            if self.dtype != numpy.uint8:
+                raise RuntimeError("invalid input format error (%s)" % (str(self.dtype)))
+            code = _lib.RGB_CODE
+        elif self.dtype in _lib.DTYPE_CODES:
+            code = _lib.DTYPE_CODES[self.dtype]
+        else:
+            raise RuntimeError("invalid input format error (%s)" % (str(self.dtype)))
+        self._code = code
+        lib = _lib.load()
+        handle = ctypes.c_void_p()
+        octave_limit = int(par.OctaveMax) if par.OctaveMax < 64 else 0
+        _lib.check(lib.siftb_plan_create(int(self.shape[0]), int(self.shape[1]), code, self.device,
+                                         int(self.PIX_PER_KP), self._init_sigma, octave_limit, ctypes.byref(handle)),
+                   RuntimeError)
+        self._plan = handle
+        self.kpsize = lib.siftb_plan_kpsize(handle)
+        self.octave_max = lib.siftb_plan_octaves(handle)
+        self.scales = []  # in XY order, like the reference (plan.py:215)
+        for o in range(self.octave_max):
+            w, h = ctypes.c_int(), ctypes.c_int()
+            lib.siftb_plan_octave_shape(handle, o, ctypes.byref(w), ctypes.byref(h))
+            self.scales.append((numpy.int32(w.value), numpy.int32(h.value)))
+        self.memory = int(lib.siftb_plan_device_bytes(handle))
+        self.queue = lib.siftb_plan_stream(handle)
+        if self.profile:
+            lib.siftb_plan_set_profile(handle, 1)
+        self.last_counts = numpy.zeros(self.octave_max, numpy.int32)
+        self._out = None  # host record buffer, allocated on first use
+        self._pending = False
+        logger.info("SiftPlan %s %s on CUDA device %d: %d octaves, kpsize %d, %.1f MB", self.shape, self.dtype,
+                    self.device, self.octave_max, self.kpsize, self.memory / 1e6)
+
+    def __del__(self):
+        """Destructor: release all buffers (reference plan.py:203-211)."""
+        plan, self._plan = getattr(self, "_plan", None), None
+        if plan:
+            try:
+                _lib.load().siftb_plan_destroy(plan)
+            except Exception:  # interpreter shutdown
+                pass
+
+    # ------------------------------------------------------------------------------------------
+    def _image_args(self, image):
+        """Validate like the reference (plan.py:443-448) and return (pointer, flags, keepalive)."""
+        assert tuple(image.shape[:2]) == self.shape
+        dt = _np_dtype(image.dtype)
+        assert dt in [self.dtype, numpy.dtype(numpy.float32)]
+        is_f32 = dt == numpy.float32 and not (self.RGB and len(image.shape) == 3)
+        if self.RGB and not is_f32:
+            assert len(image.shape) == 3 and image.shape[2] == 3
+        flags = 0
+        if is_f32 and self._code != 0:
+            flags |= 2  # SIFTB_IS_F32
+        dptr = _lib.device_pointer(image)
+        if dptr is not None:
+            if hasattr(image, "is_contiguous") and not image.is_contiguous():
+                image = image.contiguous()
+                dptr = _lib.device_pointer(image)
+            return ctypes.c_void_p(dptr), flags | 1, image
+        if not image.flags["C_CONTIGUOUS"]:
+            image = numpy.ascontiguousarray(image)
+        return _lib.ptr(image), flags, image
+
+    def _records(self):
+        if self._out is None:
+            self._out = numpy.empty(self.kpsize, dtype=self.dtype_kp)
+        return self._out
+
+    def keypoints(self, image):
+        """Calculates the keypoints of the image (reference plan.py:432-567).
+
+        :param image: 2-D array (3-D if RGB); numpy array, or a CUDA-resident array
+                      (torch tensor / ``__cuda_array_interface__``) in place of a pyopencl Array
+        :return: vector of keypoints, ``numpy.recarray`` of ``dtype_kp``
+        """
+        self.reset_timer()
+        with self._sem:
+            t0 = time.time()
+            pointer, flags, keep = self._image_args(image)
+            lib = _lib.load()
+            out = self._records()
+            n = ctypes.c_int()
+            mm = numpy.zeros(2, numpy.float32)
+            rc = lib.siftb_plan_keypoints(self._plan, pointer, flags, _lib.ptr(out), self.kpsize, ctypes.byref(n),
+                                          self.last_counts.ctypes.data_as(_lib.c_int_p),
+                                          mm.ctypes.data_as(_lib.c_float_p))
+            del keep
+            output = self._finish(rc, n.value, mm)
+            logger.info("Execution time: %.3fms" % (1000 * (time.time() - t0)))
+        return output
+
+    __call__ = keypoints
+
+    def _finish(self, rc, n, mm):
+        if rc == _lib.SIFTB_EOVERFLOW:
+            logger.warning("Keypoint counter overflow risk: counted %s / %s" % (n, self.kpsize))  # plan.py:771
+        else:
+            _lib.check(rc)
+        self.buffers["min"].value[0], self.buffers["max"].value[0] = mm[0], mm[1]
+        for octave, cnt in enumerate(self.last_counts):
+            logger.info("in octave %i found %i kp" % (octave, cnt))  # plan.py:543
+        n = min(n, self.kpsize)
+        if self.profile:
+            self._fetch_events()
+        return self._out[:n].copy().view(numpy.recarray)
+
+    # -- split form, for callers that overlap copies with compute (no reference equivalent) -----
+    def submit(self, image):
+        """Enqueue copy + all kernels for ``image`` and return immediately; pair with collect()."""
+        self._sem.acquire()
+        try:
+            pointer, flags, keep = self._image_args(image)
+            _lib.check(_lib.load().siftb_plan_submit(self._plan, pointer, flags))
+            self._keep = keep
+            self._pending = True
+        except Exception:
+            self._sem.release()
+            raise
+
+    def collect(self):
+        """Wait for the submitted image and return its keypoints."""
+        assert self._pending, "collect() without submit()"
+        try:
+            lib = _lib.load()
+            out = self._records()
+            n = ctypes.c_int()
+            mm = numpy.zeros(2, numpy.float32)
+            rc = lib.siftb_plan_collect(self._plan, _lib.ptr(out), self.kpsize, ctypes.byref(n),
+                                        self.last_counts.ctypes.data_as(_lib.c_int_p),
+                                        mm.ctypes.data_as(_lib.c_float_p))
+            return self._finish(rc, n.value, mm)
+        finally:
+            self._pending = False
+            self._keep = None
+            self._sem.release()
+
+    # ------------------------------------------------------------------------------------------
+    def stage_counts(self):
+        """int[octave, scale-1, 3]: extrema found, kept after interpolation, after orientation
+        assignment -- the counters the reference reads back at plan.py:642, 782 and 689."""
+        c = numpy.zeros((self.octave_max, 3, 3), numpy.int32)
+        _lib.check(_lib.load().siftb_plan_stage_counts(self._plan, c.ctypes.data_as(_lib.c_int_p)))
+        return c
+
+    def _fetch_events(self):
+        lib = _lib.load()
+        names = ctypes.POINTER(ctypes.c_char_p)()
+        ms = _lib.c_float_p()
+        n = ctypes.c_int()
+        _lib.check(lib.siftb_plan_events(self._plan, ctypes.byref(names), ctypes.byref(ms), ctypes.byref(n)))
+        self.events = [(names[i].decode(), float(ms[i])) for i in range(n.value)]
+
+    def count_kp(self, output):
+        """Print the number of keypoint per octave (reference plan.py:811-821)."""
+        kpt = 0
+        for octave, ksum in enumerate(self.last_counts):
+            kpt += ksum
+            print("octave %i kp count %i/%i size %s ratio:%s" % (octave, ksum, self.kpsize, self.scales[octave],
+                                                                 1000.0 * ksum / self.scales[octave][1] / self.scales[octave][0]))
+        print("Found total %i guess %s pixels per keypoint" % (kpt, self.shape[0] * self.shape[1] / max(kpt, 1)))
+
+    def log_profile(self):
+        """If profiling is on, print the device time of every stage (reference plan.py:826-847)."""
+        t = orient = descr = 0.0
+        if self.profile:
+            for name, et in self.events:
+                print("%50s:\t%.3fms" % (name, et))
+                t += et
+                if "orient" in name:
+                    orient += et
+                if "descriptors" in name:
+                    descr += et
+        print("_" * 80)
+        print("%50s:\t%.3fms" % ("Total execution time", t))
+        print("%50s:\t%.3fms" % ("Total Orientation assignment", orient))
+        print("%50s:\t%.3fms" % ("Total Descriptors", descr))
+
+    def reset_timer(self):
+        """Resets the profiling timers (reference plan.py:849-854)."""
+        with self._sem:
+            self.events = []
+
+
+def _np_dtype(dt):
+    """numpy dtype of a numpy / torch / cupy dtype object."""
+    try:
+        return numpy.dtype(dt)
+    except TypeError:
+        name = str(dt).split(".")[-1]  # torch.float32 -> float32
+        return numpy.dtype(name)
+
+
+def gaussian_taps(sigma):
+    """Normalised Gaussian taps the plan uses for ``sigma`` (reference plan.py:308-340)."""
+    lib = _lib.load()
+    taps = numpy.zeros(64, numpy.float32)
+    n = ctypes.c_int()
+    _lib.check(lib.siftb_gauss_taps(float(sigma), taps.ctypes.data_as(_lib.c_float_p), 64, ctypes.byref(n)))
+    assert n.value == kernel_size(sigma, True)
+    return taps[:n.value].copy()

@@ -1,0 +1,69 @@
+"""Host-side helpers (reference sift-src/utils.py).  No device code, no oracle."""
+from math import ceil
+
+import numpy
+
+
+def calc_size(shape, blocksize):
+    """Round ``shape`` up to a multiple of ``blocksize`` (reference utils.py:44-51; kept for API parity)."""
+    if "__len__" in dir(blocksize):
+        return tuple((int(i) + int(j) - 1) & ~(int(j) - 1) for i, j in zip(shape, blocksize))
+    return tuple((int(i) + int(blocksize) - 1) & ~(int(blocksize) - 1) for i in shape)
+
+
+def kernel_size(sigma, odd=False, cutoff=4):
+    """Size of the Gaussian kernel for ``sigma`` (reference utils.py:54-64)."""
+    size = int(ceil(2 * cutoff * sigma + 1))
+    if odd and size % 2 == 0:
+        size += 1
+    return size
+
+
+def sizeof(shape, dtype="uint8"):
+    """Number of bytes of an array of ``shape`` and ``dtype`` (reference utils.py:76-83)."""
+    itemsize = numpy.dtype(dtype).itemsize
+    cnt = 1
+    if "__len__" in dir(shape):
+        for dim in shape:
+            cnt *= dim
+    else:
+        cnt = int(shape)
+    return cnt * itemsize
+
+
+def matching_correction(matching):
+    """Least-squares affine transform mapping keypoints[:, 0] onto keypoints[:, 1].
+
+    Reference utils.py:156-189 builds the design matrix for ``x' = a x + b y + c ; y' = d x + e y + f``
+    but the snapshot lost the solve and the return; they are completed with ``pinv(X) . y`` as in the
+    reference's own test (test/test_transform.py:118-133).  Returns the flat vector (a, b, c, d, e, f).
+    """
+    N = matching.shape[0]
+    X = numpy.zeros((2 * N, 6))
+    X[::2, 2:] = 1, 0, 0, 0
+    X[::2, 0] = matching.x[:, 0]
+    X[::2, 1] = matching.y[:, 0]
+    X[1::2, 0:3] = 0, 0, 0
+    X[1::2, 3] = matching.x[:, 0]
+    X[1::2, 4] = matching.y[:, 0]
+    X[1::2, 5] = 1
+    y = numpy.zeros((2 * N, 1))
+    y[::2, 0] = matching.x[:, 1]
+    y[1::2, 0] = matching.y[:, 1]
+    sol = numpy.dot(numpy.linalg.pinv(X), y)
+    return sol.ravel()
+
+
+def multiscale_image(n, seed=1234, shape=None):
+    """Seeded synthetic benchmark/test image:
+    ``sum_k sqrt(k) * zoom(rng.random((n/k, n/k)), k, order=1)`` for k in 1,2,4,8,16,32, float32."""
+    from scipy.ndimage import zoom
+    h, w = (n, n) if shape is None else shape
+    rng = numpy.random.default_rng(seed)
+    img = numpy.zeros((h, w), numpy.float32)
+    for k in (1, 2, 4, 8, 16, 32):
+        hk, wk = -(-h // k), -(-w // k)
+        r = rng.random((hk, wk), dtype=numpy.float32)
+        z = r if k == 1 else zoom(r, k, order=1)
+        img += numpy.float32(numpy.sqrt(k)) * z[:h, :w].astype(numpy.float32)
+    return img

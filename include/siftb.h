@@ -67,7 +67,7 @@ SIFTB_API int siftb_host_free(void *ptr);
 /* ---- SiftPlan ------------------------------------------------------------------------------ */
 /* plan.py:117-201 (__init__: _calc_scales, _calc_memory, _allocate_buffers, _init_gaussian).
  * octave_max <= 0 means "all octaves" (par.OctaveMax default, param.py:52). */
-SIFTB_API int siftb_plan_create(int height, int width, int dtype, int device, int pix_per_kp, float init_sigma,
+SIFTB_API int siftb_plan_create(int height, int width, int dtype, int device, int pix_per_kp, double init_sigma,
                       int octave_max, siftb_plan **out);
 SIFTB_API int siftb_plan_destroy(siftb_plan *plan);             /* plan.py:203-211 __del__ */
 
@@ -78,6 +78,8 @@ SIFTB_API int siftb_plan_octave_shape(const siftb_plan *plan, int octave, int *w
 SIFTB_API uint64_t siftb_plan_device_bytes(const siftb_plan *plan);   /* plan.py:226 _calc_memory */
 SIFTB_API void *siftb_plan_stream(const siftb_plan *plan);            /* cudaStream_t of the plan's queue */
 SIFTB_API int siftb_plan_set_profile(siftb_plan *plan, int enable);   /* plan.py:185-186 PROFILING_ENABLE */
+/* number of CUDA kernels this plan has launched since it was created (bench.py's gpu_launches) */
+SIFTB_API uint64_t siftb_plan_launches(const siftb_plan *plan);
 
 /* plan.py:432-567 keypoints(): the whole path, blocking.
  *   image      : height*width pixels of the plan's dtype (RGB8: height*width*3 bytes)
@@ -97,7 +99,7 @@ SIFTB_API int siftb_plan_keypoints(siftb_plan *plan, const void *image, int flag
  * collect() waits and copies the records to the host.  One submit may be in flight per plan. */
 SIFTB_API int siftb_plan_submit(siftb_plan *plan, const void *image, int flags);
 SIFTB_API int siftb_plan_collect(siftb_plan *plan, siftb_kp *out, int cap, int *n_out, int *n_per_octave,
-                       float *minmax);
+                       float *minmax);   /* out == NULL: wait and return the counts only (records stay on the device) */
 /* results left on the device (valid until the next submit): records, count */
 SIFTB_API int siftb_plan_result_dev(const siftb_plan *plan, const siftb_kp **dev_records, const int **dev_count);
 
@@ -120,7 +122,7 @@ SIFTB_API int siftb_to_float(const void *image, int dtype, int height, int width
 /* convolution.cl:16,62 via plan.py:571 _gaussian_convolution (horizontal then vertical) */
 SIFTB_API int siftb_blur(const float *image, int height, int width, const float *taps, int ntaps, float *out);
 /* plan.py:609-625 + :739-745: G[1..5], DoG[0..4] (and G[3][::2, ::2]) of one octave from G[0] */
-SIFTB_API int siftb_pyramid_octave(const float *g0, int height, int width, float init_sigma, float *G5, float *D5,
+SIFTB_API int siftb_pyramid_octave(const float *g0, int height, int width, double init_sigma, float *G5, float *D5,
                          float *next_base);
 /* image.cl:47 compute_gradient_orientation */
 SIFTB_API int siftb_gradient(const float *image, int height, int width, float *grad, float *ori);

@@ -648,7 +648,7 @@ API void siftref_descriptor(const float *keypoints, uint8_t *descriptors, const 
 /* ------------------------------------------------------------------------------------------ */
 /* plan.py:432-567 keypoints() + :596-756 _one_octave : the whole path                          */
 /* stage_counts (optional, may be NULL): int[octaves][3 scales][3] = {extrema, after interp, after orientation} */
-API int siftref_keypoints(const float *image, int height, int width, float init_sigma, int octave_limit,
+API int siftref_keypoints(const float *image, int height, int width, double init_sigma, int octave_limit,
                           int pix_per_kp, siftref_kp *out, int out_cap, int *n_per_octave, float *minmax,
                           int *stage_counts) {
     const int Scales = 3, BorderDist = 5;
@@ -669,14 +669,14 @@ API int siftref_keypoints(const float *image, int height, int width, float init_
     /* plan.py:297-306 */
     double curSigma = 0.5;
     int has_init = 0;
-    if ((double)init_sigma > curSigma) {
-        double s = sqrt((double)init_sigma * (double)init_sigma - curSigma * curSigma);
+    if (init_sigma > curSigma) {
+        double s = sqrt(init_sigma * init_sigma - curSigma * curSigma);
         ntaps[5] = siftref_kernel_size(s, 1);
         siftref_gaussian_taps(s, ntaps[5], taps[5]);
         has_init = 1;
     }
     {
-        double prevSigma = (double)init_sigma;
+        double prevSigma = init_sigma;  /* python double, plan.py:123-126 */
         for (int i = 0; i < Scales + 2; i++) {
             double increase = prevSigma * sqrt(sigmaRatio * sigmaRatio - 1.0);
             ntaps[i] = siftref_kernel_size(increase, 1);
@@ -706,7 +706,7 @@ API int siftref_keypoints(const float *image, int height, int width, float init_
                                  w, h);
             if (cnt > kpsize) cnt = kpsize; /* reference would run past the buffer; clamp */
             int n_ext = cnt - last_start;
-            siftref_interp_keypoint(DoGs, Kp, last_start, cnt, PeakThresh, init_sigma, w, h);
+            siftref_interp_keypoint(DoGs, Kp, last_start, cnt, PeakThresh, (float)init_sigma, w, h); /* numpy.float32(self._init_sigma), plan.py:650 */
             int newcnt = siftref_compact(Kp, last_start, cnt, kpsize);
             int n_int = newcnt - last_start;
             cnt = newcnt;

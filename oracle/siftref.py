@@ -229,7 +229,7 @@ def keypoints(img, init_sigma=1.6, octave_max=0, pix_per_kp=10, return_all=False
     n_per_oct = np.zeros(noct, np.int32)
     stage = np.zeros((noct, 3, 3), np.int32)
     mm = np.zeros(2, np.float32)
-    n = lib().siftref_keypoints(_fp(img), h, w, ctypes.c_float(init_sigma), int(octave_max), int(pix_per_kp),
+    n = lib().siftref_keypoints(_fp(img), h, w, ctypes.c_double(init_sigma), int(octave_max), int(pix_per_kp),
                                 out.ctypes.data_as(ctypes.c_void_p), cap, n_per_oct.ctypes.data_as(_c_int_p), _fp(mm),
                                 stage.ctypes.data_as(_c_int_p))
     res = out[:min(n, cap)].view(np.recarray)

@@ -37,7 +37,7 @@ SIGNATURES = {
     "siftb_device_count": (c_int, [c_int_p]),
     "siftb_host_alloc": (c_int, [ctypes.POINTER(c_void_p), c_u64]),
     "siftb_host_free": (c_int, [c_void_p]),
-    "siftb_plan_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, c_int, ctypes.POINTER(c_void_p)]),
+    "siftb_plan_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_double, c_int, ctypes.POINTER(c_void_p)]),
     "siftb_plan_destroy": (c_int, [c_void_p]),
     "siftb_plan_octaves": (c_int, [c_void_p]),
     "siftb_plan_kpsize": (c_int, [c_void_p]),
@@ -45,6 +45,7 @@ SIGNATURES = {
     "siftb_plan_device_bytes": (c_u64, [c_void_p]),
     "siftb_plan_stream": (c_void_p, [c_void_p]),
     "siftb_plan_set_profile": (c_int, [c_void_p, c_int]),
+    "siftb_plan_launches": (c_u64, [c_void_p]),
     "siftb_plan_keypoints": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int_p, c_int_p, c_float_p]),
     "siftb_plan_submit": (c_int, [c_void_p, c_void_p, c_int]),
     "siftb_plan_collect": (c_int, [c_void_p, c_void_p, c_int, c_int_p, c_int_p, c_float_p]),
@@ -57,7 +58,7 @@ SIGNATURES = {
     "siftb_normalize": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "siftb_to_float": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
     "siftb_blur": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
-    "siftb_pyramid_octave": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "siftb_pyramid_octave": (c_int, [c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p]),
     "siftb_gradient": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "siftb_local_maxmin": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int_p]),
     "siftb_interp": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_float, c_void_p, c_int_p]),

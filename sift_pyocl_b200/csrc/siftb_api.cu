@@ -91,7 +91,7 @@ struct Event {
 
 struct siftb_plan {
     int device = 0, h = 0, w = 0, dtype = 0, pix_per_kp = 10, n_oct = 0, kpsize = 0;
-    float init_sigma = 1.6f;
+    double init_sigma = 1.6;  // python double in the reference (plan.py:123-126); fp32 only as a kernel argument
     int ow[MAX_OCT], oh[MAX_OCT], opitch[MAX_OCT];
     cudaStream_t stream = nullptr;
     std::mutex mtx;
@@ -110,6 +110,7 @@ struct siftb_plan {
     int *h_cnt = nullptr;  // pinned mirror
     int cnt_ints = 0;
     bool in_flight = false, profile = false;
+    uint64_t launches = 0;
     std::vector<Event> events;
     std::vector<const char *> ev_names;
     std::vector<float> ev_ms;
@@ -194,8 +195,8 @@ static int plan_create_impl(siftb_plan *p) {
     // plan.py:297-306 gaussian kernels
     const double sigmaRatio = pow(2.0, 1.0 / kScales);
     const double curSigma = 0.5;
-    if ((double)p->init_sigma > curSigma) {
-        double s = sqrt((double)p->init_sigma * (double)p->init_sigma - curSigma * curSigma);
+    if (p->init_sigma > curSigma) {
+        double s = sqrt(p->init_sigma * p->init_sigma - curSigma * curSigma);
         p->ntaps[5] = kernel_size(s);
         if (p->ntaps[5] > SIFTB_MAX_TAPS) return fail(SIFTB_EINVAL, "init_sigma too large");
         gaussian_taps(s, p->ntaps[5], p->taps[5].f);
@@ -204,7 +205,7 @@ static int plan_create_impl(siftb_plan *p) {
         p->ntaps[5] = 1;
         p->taps[5].f[0] = 1.0f;  // identity "blur": fmaf(x, 1, 0) == x
     }
-    double prevSigma = (double)p->init_sigma;
+    double prevSigma = p->init_sigma;
     for (int i = 0; i < kScales + 2; i++) {
         double increase = prevSigma * sqrt(sigmaRatio * sigmaRatio - 1.0);
         p->ntaps[i] = kernel_size(increase);
@@ -237,14 +238,14 @@ static int plan_create_impl(siftb_plan *p) {
     return 0;
 }
 
-extern "C" int siftb_plan_create(int height, int width, int dtype, int device, int pix_per_kp, float init_sigma,
+extern "C" int siftb_plan_create(int height, int width, int dtype, int device, int pix_per_kp, double init_sigma,
                                  int octave_max, siftb_plan **out) {
     if (!out) return fail(SIFTB_EINVAL, "out is null");
     *out = nullptr;
     if (height <= 0 || width <= 0) return fail(SIFTB_EINVAL, "bad shape");
     if (dtype_bytes(dtype) == 0) return fail(SIFTB_EINVAL, "invalid input format error (plan.py:488)");
     if (pix_per_kp <= 0) pix_per_kp = 10;
-    if (!(init_sigma > 0.f)) init_sigma = 1.6f;
+    if (!(init_sigma > 0.)) init_sigma = 1.6;
     siftb_plan *p = new siftb_plan();
     p->device = device; p->h = height; p->w = width; p->dtype = dtype;
     p->pix_per_kp = pix_per_kp; p->init_sigma = init_sigma;
@@ -270,6 +271,7 @@ extern "C" int siftb_plan_octave_shape(const siftb_plan *p, int o, int *w, int *
 }
 extern "C" uint64_t siftb_plan_device_bytes(const siftb_plan *p) { return p ? p->dev_bytes : 0; }
 extern "C" void *siftb_plan_stream(const siftb_plan *p) { return p ? (void *)p->stream : nullptr; }
+extern "C" uint64_t siftb_plan_launches(const siftb_plan *p) { return p ? p->launches : 0; }
 extern "C" int siftb_plan_set_profile(siftb_plan *p, int enable) {
     if (!p) return fail(SIFTB_EINVAL, "plan is null");
     p->profile = enable != 0;
@@ -372,9 +374,11 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
         ProfScope ps(p, dtype == SIFTB_F32 ? "max_min" : "convert -> float + max_min");
         if (dtype == SIFTB_F32) {
             if ((rc = launch_minmax_f32(st, (const float *)src, N, mm))) return rc;
+            p->launches += 2;
             img = (const float *)src;
         } else {
             if ((rc = launch_convert(st, src, dtype, N, p->d_img, mm))) return rc;
+            p->launches += 2;
             img = p->d_img;
         }
     }
@@ -383,6 +387,7 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
         if ((rc = launch_blur(st, img, p->w, p->w, p->h, p->G[0], p->opitch[0], nullptr, nullptr, 0, p->taps[5],
                               p->ntaps[5], mm)))
             return rc;
+        p->launches += 1;
     }
     for (int o = 0; o < p->n_oct; o++) {
         const int w = p->ow[o], h = p->oh[o], pitch = p->opitch[o];
@@ -398,6 +403,7 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
                 if ((rc = launch_blur(st, p->G[s], pitch, w, h, p->G[s + 1], pitch, p->D[s], half, hp, p->taps[s],
                                       p->ntaps[s], nullptr)))
                     return rc;
+                p->launches += 1;
             }
         }
         DogStack ds = make_dogstack(p->D, pitch, w, h);
@@ -407,12 +413,14 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
             k_extrema<<<grid, 128, 0, st>>>(ds, kBorderDist, kPeakThresh, octsize <= 1 ? kEdgeThresh1 : kEdgeThresh,
                                             p->cand, p->kpsize, c + 0, stage, 1);
             CKL();
+            p->launches += 1;
         }
         {
             ProfScope ps(p, "interp_keypoint + compact", o);
-            k_refine<<<148 * 4, 128, 0, st>>>(ds, p->cand, c + 0, p->kpsize, kPeakThresh, p->init_sigma, p->kp,
+            k_refine<<<148 * 4, 128, 0, st>>>(ds, p->cand, c + 0, p->kpsize, kPeakThresh, (float)p->init_sigma, p->kp,
                                               p->kp_scale, c + 1, stage);
             CKL();
+            p->launches += 1;
         }
         GradPlanes gp;
         for (int i = 0; i < 3; i++) { gp.grad[i] = p->grad[i]; gp.ori[i] = p->ori[i]; }
@@ -425,18 +433,21 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
             dim3 grid((w + 255) / 256, h, 3);
             k_gradient<<<grid, 256, 0, st>>>(ga);
             CKL();
+            p->launches += 1;
         }
         {
             ProfScope ps(p, "orientation_assignment", o);
             k_orient<<<148 * 4, 256, 0, st>>>(gp, p->kp, p->kp_scale, c + 1, c + 2, p->kpsize, octsize, kOriSigma,
                                               stage);
             CKL();
+            p->launches += 1;
         }
         {
             ProfScope ps(p, "descriptors", o);
             k_describe<<<148 * 16, 64, 0, st>>>(gp, p->kp, p->kp_scale, c + 1, c + 2, p->kpsize, octsize, p->out,
                                                 p->kpsize, p->c_nout(), c + 3);
             CKL();
+            p->launches += 1;
         }
     }
     CK(cudaMemcpyAsync(p->h_cnt, p->d_cnt, p->cnt_ints * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -453,7 +464,7 @@ static int collect_impl(siftb_plan *p, siftb_kp *out, int cap, int *n_out, int *
     int rc = 0;
     int ncopy = n;
     if (ncopy > p->kpsize) { ncopy = p->kpsize; rc = SIFTB_EOVERFLOW; }
-    if (ncopy > cap) { ncopy = cap; rc = SIFTB_EOVERFLOW; }
+    if (out && ncopy > cap) { ncopy = cap; rc = SIFTB_EOVERFLOW; }
     for (int o = 0; o < p->n_oct; o++) {
         const int *c = p->h_cnt + 1 + 4 * o;
         if (c[0] > p->kpsize || c[1] + c[2] > p->kpsize) rc = SIFTB_EOVERFLOW;
@@ -613,7 +624,7 @@ extern "C" int siftb_blur(const float *image, int height, int width, const float
     return 0;
 }
 
-extern "C" int siftb_pyramid_octave(const float *g0, int height, int width, float init_sigma, float *G5, float *D5,
+extern "C" int siftb_pyramid_octave(const float *g0, int height, int width, double init_sigma, float *G5, float *D5,
                                     float *next_base) {
     if (!g0 || height <= 0 || width <= 0) return fail(SIFTB_EINVAL, "bad argument");
     int rc = ensure_blur_attr();
@@ -624,7 +635,7 @@ extern "C" int siftb_pyramid_octave(const float *g0, int height, int width, floa
     DALLOC(G, 6 * n * 4); DALLOC(D, 5 * n * 4); DALLOC(half, (size_t)hw * hh * 4);
     CK(cudaMemcpy(G.p, g0, n * 4, cudaMemcpyHostToDevice));
     const double sigmaRatio = pow(2.0, 1.0 / kScales);
-    double prevSigma = (double)init_sigma;
+    double prevSigma = init_sigma;
     for (int s = 0; s < kScales + 2; s++) {
         double increase = prevSigma * sqrt(sigmaRatio * sigmaRatio - 1.0);
         Taps t;

@@ -207,22 +207,49 @@ class SiftPlan(object):
             self._sem.release()
             raise
 
-    def collect(self):
-        """Wait for the submitted image and return its keypoints."""
+    def collect(self, records=True):
+        """Wait for the submitted image and return its keypoints.  With ``records=False`` the records
+        stay on the device (see device_records()) and only their number is returned."""
         assert self._pending, "collect() without submit()"
         try:
             lib = _lib.load()
-            out = self._records()
             n = ctypes.c_int()
             mm = numpy.zeros(2, numpy.float32)
-            rc = lib.siftb_plan_collect(self._plan, _lib.ptr(out), self.kpsize, ctypes.byref(n),
+            out = _lib.ptr(self._records()) if records else None
+            rc = lib.siftb_plan_collect(self._plan, out, self.kpsize, ctypes.byref(n),
                                         self.last_counts.ctypes.data_as(_lib.c_int_p),
                                         mm.ctypes.data_as(_lib.c_float_p))
+            if not records:
+                if rc != _lib.SIFTB_EOVERFLOW:
+                    _lib.check(rc)
+                self.buffers["min"].value[0], self.buffers["max"].value[0] = mm[0], mm[1]
+                return min(n.value, self.kpsize)
             return self._finish(rc, n.value, mm)
         finally:
             self._pending = False
             self._keep = None
             self._sem.release()
+
+    def device_records(self):
+        """(device pointer of the record array, device pointer of the int32 record count) of the last
+        run; valid until the next submit()/keypoints() on this plan."""
+        recs, cnt = ctypes.c_void_p(), ctypes.c_void_p()
+        _lib.check(_lib.load().siftb_plan_result_dev(self._plan, ctypes.byref(recs), ctypes.byref(cnt)))
+        return recs.value, cnt.value
+
+    @property
+    def launches(self):
+        """CUDA kernels launched by this plan so far."""
+        return int(_lib.load().siftb_plan_launches(self._plan))
+
+    def set_profile(self, enable):
+        self.profile = bool(enable)
+        _lib.load().siftb_plan_set_profile(self._plan, int(self.profile))
+
+    def fetch_events(self):
+        """[(stage name, device milliseconds)] of the last run when profiling is on."""
+        self._fetch_events()
+        return self.events
 
     # ------------------------------------------------------------------------------------------
     def stage_counts(self):

@@ -73,7 +73,8 @@ SIFTB_API int siftb_plan_destroy(siftb_plan *plan);             /* plan.py:203-2
 
 /* read-only facts about a plan: plan.py:213-245 (octave_max, kpsize, scales[o] = (w, h)) */
 SIFTB_API int siftb_plan_octaves(const siftb_plan *plan);
-SIFTB_API int siftb_plan_kpsize(const siftb_plan *plan);
+SIFTB_API int siftb_plan_kpsize(const siftb_plan *plan);      /* per-octave keypoint slots, plan.py:243 */
+SIFTB_API int siftb_plan_capacity(const siftb_plan *plan);    /* records the plan can return for one image (all octaves) */
 SIFTB_API int siftb_plan_octave_shape(const siftb_plan *plan, int octave, int *width, int *height);
 SIFTB_API uint64_t siftb_plan_device_bytes(const siftb_plan *plan);   /* plan.py:226 _calc_memory */
 SIFTB_API void *siftb_plan_stream(const siftb_plan *plan);            /* cudaStream_t of the plan's queue */

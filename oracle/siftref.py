@@ -223,7 +223,7 @@ def keypoints(img, init_sigma=1.6, octave_max=0, pix_per_kp=10, return_all=False
     """Whole path (plan.py:432-567) on a 2-D float32 image.  Returns recarray[dtype_kp] (and details)."""
     img = _f32(img)
     h, w = img.shape
-    cap = h * w // pix_per_kp
+    cap = 2 * (h * w // pix_per_kp)  # kpsize is a per-octave limit in the reference (plan.py:243,748-752)
     out = np.zeros(cap, dtype_kp)
     noct = num_octaves(h, w)
     n_per_oct = np.zeros(noct, np.int32)

@@ -41,6 +41,7 @@ SIGNATURES = {
     "siftb_plan_destroy": (c_int, [c_void_p]),
     "siftb_plan_octaves": (c_int, [c_void_p]),
     "siftb_plan_kpsize": (c_int, [c_void_p]),
+    "siftb_plan_capacity": (c_int, [c_void_p]),
     "siftb_plan_octave_shape": (c_int, [c_void_p, c_int, c_int_p, c_int_p]),
     "siftb_plan_device_bytes": (c_u64, [c_void_p]),
     "siftb_plan_stream": (c_void_p, [c_void_p]),

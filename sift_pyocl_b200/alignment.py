@@ -47,7 +47,7 @@ class LinearAlign(object):
         elif len(self.shape) == 2:
             self.RGB = False
         else:
-            raise RuntimeError("Unable to process image of shape %s" % (tuple(self.shape,)))
+            raise RuntimeError("Unable to process image of shape %s" % (tuple(self.shape),))
         if "__len__" not in dir(extra):
             self.extra = (int(extra), int(extra))
         else:

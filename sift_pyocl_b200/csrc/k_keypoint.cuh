@@ -5,8 +5,7 @@
 //             App. A.7): one warp per keypoint; every lane owns histogram bins and the samples are
 //             committed in the reference's row-major order, so the fp32 sums are bit-identical to
 //             the sequential kernel.
-// k_describe  replaces keypoints_cpu.cl:36 descriptor (CPU-variant semantics, App. A.8) and the
-//             host-side NaN filtering / record assembly of plan.py:546-565.
+// (the descriptor kernel lives in k_describe.cuh)
 #pragma once
 #include "common.cuh"
 
@@ -159,115 +158,7 @@ __global__ void __launch_bounds__(256) k_orient(GradPlanes G, float4 *__restrict
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// keypoints_cpu.cl:49-160 for one keypoint (x, y, sigma*oct, angle) -> 128 bytes.
-// v1: one thread per keypoint, literal restatement (histogram in local memory).
-__device__ void describe_one(const float4 k, const float *__restrict__ grad, const float *__restrict__ orim,
-                             int pitch, int grad_width, int grad_height, int octsize, uint8_t *out) {
-    float tmp_descriptors[128];
-    for (int i = 0; i < 128; i++) tmp_descriptors[i] = 0.0f;
-    const float row = k.y / (float)octsize, col = k.x / (float)octsize, angle = k.w;
-    const int irow = (int)(row + 0.5f), icol = (int)(col + 0.5f);
-    const float sine = cr_sinf(angle), cosine = cr_cosf(angle);
-    const float spacing = k.z / (float)octsize * 3.0f;
-    const int iradius = (int)(((1.414f * spacing) * 2.5f) + 0.5f);
-    const float drow = row - (float)irow, dcol = col - (float)icol;
-    for (int i = -iradius; i <= iradius; i++) {
-        for (int j = -iradius; j <= iradius; j++) {
-            const float rx = ((cosine * (float)i - sine * (float)j) - drow) / spacing + 1.5f;
-            const float cx = ((sine * (float)i + cosine * (float)j) - dcol) / spacing + 1.5f;
-            if ((rx > -1.0f && rx < 4.0f && cx > -1.0f && cx < 4.0f && (irow + i) >= 0 && (irow + i) < grad_height &&
-                 (icol + j) >= 0 && (icol + j) < grad_width)) {
-                const long q = (long)(irow + i) * pitch + (icol + j);
-                const float er = rx - 1.5f, ec = cx - 1.5f;
-                const float mag = grad[q] * cr_expf(-0.125f * (er * er + ec * ec));
-                float ori = orim[q] - angle;
-                while (ori > 2.0f * SIFTB_M_PI_F) ori -= 2.0f * SIFTB_M_PI_F;
-                while (ori < 0.0f) ori += 2.0f * SIFTB_M_PI_F;
-                const float oval = (4.0f * ori) * SIFTB_M_1_PI_F;
-                const int ri = (int)((rx >= 0.0f) ? rx : rx - 1.0f), ci = (int)((cx >= 0.0f) ? cx : cx - 1.0f),
-                          oi = (int)((oval >= 0.0f) ? oval : oval - 1.0f);
-                const float rfrac = rx - (float)ri, cfrac = cx - (float)ci, ofrac = oval - (float)oi;
-                if ((ri >= -1 && ri < 4 && oi >= 0 && oi <= 8 && rfrac >= 0.0f && rfrac <= 1.0f)) {
-                    for (int r = 0; r < 2; r++) {
-                        const int rindex = ri + r;
-                        if ((rindex >= 0 && rindex < 4)) {
-                            const float rweight = mag * ((r == 0) ? 1.0f - rfrac : rfrac);
-                            for (int c = 0; c < 2; c++) {
-                                const int cindex = ci + c;
-                                if ((cindex >= 0 && cindex < 4)) {
-                                    const float cweight = rweight * ((c == 0) ? 1.0f - cfrac : cfrac);
-                                    for (int orr = 0; orr < 2; orr++) {
-                                        int oindex = oi + orr;
-                                        if (oindex >= 8) oindex = 0;
-                                        tmp_descriptors[(rindex * 4 + cindex) * 8 + oindex] +=
-                                            cweight * ((orr == 0) ? 1.0f - ofrac : ofrac);
-                                    }
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-        }
-    }
-    float norm = 0.0f;
-    for (int i = 0; i < 128; i++) norm += tmp_descriptors[i] * tmp_descriptors[i];
-    norm = cr_rsqrtf(norm);
-    for (int i = 0; i < 128; i++) tmp_descriptors[i] *= norm;
-    bool changed = false;
-    norm = 0.0f;
-    for (int i = 0; i < 128; i++) {
-        if (tmp_descriptors[i] > 0.2f) { tmp_descriptors[i] = 0.2f; changed = true; }
-        norm += tmp_descriptors[i] * tmp_descriptors[i];
-    }
-    if (changed) {
-        norm = cr_rsqrtf(norm);
-        for (int i = 0; i < 128; i++) tmp_descriptors[i] *= norm;
-    }
-    for (int i = 0; i < 128; i++) {
-        const float v = 512.0f * tmp_descriptors[i];  // 512.0 * v in double is exact, == fp32 product
-        const int intval = (v != v) ? 0 : (int)v;
-        out[i] = (uint8_t)min(255, intval);
-    }
-}
-
 struct KpRecord {  // == siftb_kp
     float x, y, scale, angle;
     uint8_t desc[128];
 };
-
-// Pipeline form: thread per keypoint over [0, n_base + n_extra); rows with a NaN coordinate are dropped
-// (plan.py:546-550) and the survivors are appended to the final record array.
-__global__ void __launch_bounds__(64) k_describe(GradPlanes G, const float4 *__restrict__ kp,
-                                                  const int *__restrict__ kp_scale, const int *__restrict__ n_base_p,
-                                                  const int *__restrict__ n_extra_p, int cap, int octsize,
-                                                  KpRecord *__restrict__ out, int out_cap, int *__restrict__ n_out,
-                                                  int *__restrict__ n_out_oct) {
-    const int n = min(min(*n_base_p, cap) + *n_extra_p, cap);
-    const int stride = gridDim.x * blockDim.x;
-    for (int gid0 = blockIdx.x * blockDim.x + threadIdx.x; gid0 < n; gid0 += stride) {
-        const float4 k = kp[gid0];
-        if (!(k.y >= 0.0f)) continue;
-        const float s = ((k.x + k.y) + k.z) + k.w;
-        if (s != s) continue;
-        const int slot = atomicAdd(n_out, 1);
-        atomicAdd(n_out_oct, 1);
-        if (slot >= out_cap) continue;
-        const int sc = kp_scale[gid0];
-        KpRecord *o = out + slot;
-        o->x = k.x; o->y = k.y; o->scale = k.z; o->angle = k.w;
-        describe_one(k, G.grad[sc - 1], G.ori[sc - 1], G.pitch, G.w, G.h, octsize, o->desc);
-    }
-}
-
-// Stage-hook form: desc[i] for every input row (no filtering), single gradient plane
-__global__ void __launch_bounds__(64) k_describe_rows(const float *__restrict__ grad, const float *__restrict__ ori,
-                                                       int pitch, int w, int h, const float4 *__restrict__ kp, int n,
-                                                       int octsize, uint8_t *__restrict__ desc) {
-    const int gid0 = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid0 >= n) return;
-    const float4 k = kp[gid0];
-    if (!(k.y >= 0.0f)) return;
-    describe_one(k, grad, ori, pitch, w, h, octsize, desc + 128L * gid0);
-}

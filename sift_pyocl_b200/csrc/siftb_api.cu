@@ -24,6 +24,7 @@
 #include "k_extrema.cuh"
 #include "k_frontend.cuh"
 #include "k_keypoint.cuh"
+#include "k_describe.cuh"
 #include "k_match.cuh"
 
 #define SIFTB_VERSION 100
@@ -91,6 +92,7 @@ struct Event {
 
 struct siftb_plan {
     int device = 0, h = 0, w = 0, dtype = 0, pix_per_kp = 10, n_oct = 0, kpsize = 0;
+    int out_cap = 0;  // records of ALL octaves: the reference's limit (kpsize) is per octave (plan.py:243,748-752)
     double init_sigma = 1.6;  // python double in the reference (plan.py:123-126); fp32 only as a kernel argument
     int ow[MAX_OCT], oh[MAX_OCT], opitch[MAX_OCT];
     cudaStream_t stream = nullptr;
@@ -228,7 +230,8 @@ static int plan_create_impl(siftb_plan *p) {
     if ((rc = dalloc(p, &p->cand, (size_t)p->kpsize * sizeof(float4)))) return rc;
     if ((rc = dalloc(p, &p->kp, (size_t)p->kpsize * sizeof(float4)))) return rc;
     if ((rc = dalloc(p, &p->kp_scale, (size_t)p->kpsize * sizeof(int)))) return rc;
-    if ((rc = dalloc(p, &p->out, (size_t)p->kpsize * sizeof(KpRecord)))) return rc;
+    p->out_cap = 2 * p->kpsize;
+    if ((rc = dalloc(p, &p->out, (size_t)p->out_cap * sizeof(KpRecord)))) return rc;
     p->cnt_ints = 1 + 13 * p->n_oct + 2;
     if ((rc = dalloc(p, &p->d_cnt, p->cnt_ints * sizeof(int)))) return rc;
     CK(cudaHostAlloc((void **)&p->h_cnt, p->cnt_ints * sizeof(int), cudaHostAllocDefault));
@@ -263,6 +266,7 @@ extern "C" int siftb_plan_create(int height, int width, int dtype, int device, i
 
 extern "C" int siftb_plan_octaves(const siftb_plan *p) { return p ? p->n_oct : SIFTB_EINVAL; }
 extern "C" int siftb_plan_kpsize(const siftb_plan *p) { return p ? p->kpsize : SIFTB_EINVAL; }
+extern "C" int siftb_plan_capacity(const siftb_plan *p) { return p ? p->out_cap : SIFTB_EINVAL; }
 extern "C" int siftb_plan_octave_shape(const siftb_plan *p, int o, int *w, int *h) {
     if (!p || o < 0 || o >= p->n_oct) return fail(SIFTB_EINVAL, "bad octave");
     if (w) *w = p->ow[o];
@@ -444,8 +448,8 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
         }
         {
             ProfScope ps(p, "descriptors", o);
-            k_describe<<<148 * 16, 64, 0, st>>>(gp, p->kp, p->kp_scale, c + 1, c + 2, p->kpsize, octsize, p->out,
-                                                p->kpsize, p->c_nout(), c + 3);
+            k_describe<<<148 * 8, DESC_WARPS * 32, 0, st>>>(gp, p->kp, p->kp_scale, c + 1, c + 2, p->kpsize, octsize, p->out,
+                                                p->out_cap, p->c_nout(), c + 3);
             CKL();
             p->launches += 1;
         }
@@ -463,7 +467,7 @@ static int collect_impl(siftb_plan *p, siftb_kp *out, int cap, int *n_out, int *
     const int n = p->h_cnt[0];
     int rc = 0;
     int ncopy = n;
-    if (ncopy > p->kpsize) { ncopy = p->kpsize; rc = SIFTB_EOVERFLOW; }
+    if (ncopy > p->out_cap) { ncopy = p->out_cap; rc = SIFTB_EOVERFLOW; }
     if (out && ncopy > cap) { ncopy = cap; rc = SIFTB_EOVERFLOW; }
     for (int o = 0; o < p->n_oct; o++) {
         const int *c = p->h_cnt + 1 + 4 * o;
@@ -757,7 +761,7 @@ extern "C" int siftb_descriptor(const float *kp4, int n, const float *grad, cons
     CK(cudaMemcpy(K.p, kp4, (size_t)n * 16, cudaMemcpyHostToDevice));
     CK(cudaMemset(Dd.p, 0, (size_t)n * 128));
     if (n > 0) {
-        k_describe_rows<<<(n + 63) / 64, 64>>>(Gd.as<float>(), Od.as<float>(), width, width, height, K.as<float4>(), n,
+        k_describe_rows<<<(n + DESC_WARPS - 1) / DESC_WARPS, DESC_WARPS * 32>>>(Gd.as<float>(), Od.as<float>(), width, width, height, K.as<float4>(), n,
                                                octsize, Dd.as<uint8_t>());
         CKL();
         CK(cudaMemcpy(desc, Dd.p, (size_t)n * 128, cudaMemcpyDeviceToHost));

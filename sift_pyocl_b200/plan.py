@@ -71,7 +71,7 @@ class SiftPlan(object):
         elif len(self.shape) == 2:
             self.RGB = False
         else:
-            raise RuntimeError("Unable to process image of shape %s" % (tuple(self.shape,)))
+            raise RuntimeError("Unable to process image of shape %s" % (tuple(self.shape),))
         if PIX_PER_KP:
             self.PIX_PER_KP = int(PIX_PER_KP)
         self.profile = bool(profile)
@@ -104,6 +104,7 @@ class SiftPlan(object):
                    RuntimeError)
         self._plan = handle
         self.kpsize = lib.siftb_plan_kpsize(handle)
+        self._capacity = lib.siftb_plan_capacity(handle)
         self.octave_max = lib.siftb_plan_octaves(handle)
         self.scales = []  # in XY order, like the reference (plan.py:215)
         for o in range(self.octave_max):
@@ -153,7 +154,7 @@ class SiftPlan(object):
 
     def _records(self):
         if self._out is None:
-            self._out = numpy.empty(self.kpsize, dtype=self.dtype_kp)
+            self._out = numpy.empty(self._capacity, dtype=self.dtype_kp)
         return self._out
 
     def keypoints(self, image):
@@ -171,7 +172,7 @@ class SiftPlan(object):
             out = self._records()
             n = ctypes.c_int()
             mm = numpy.zeros(2, numpy.float32)
-            rc = lib.siftb_plan_keypoints(self._plan, pointer, flags, _lib.ptr(out), self.kpsize, ctypes.byref(n),
+            rc = lib.siftb_plan_keypoints(self._plan, pointer, flags, _lib.ptr(out), self._capacity, ctypes.byref(n),
                                           self.last_counts.ctypes.data_as(_lib.c_int_p),
                                           mm.ctypes.data_as(_lib.c_float_p))
             del keep
@@ -189,7 +190,7 @@ class SiftPlan(object):
         self.buffers["min"].value[0], self.buffers["max"].value[0] = mm[0], mm[1]
         for octave, cnt in enumerate(self.last_counts):
             logger.info("in octave %i found %i kp" % (octave, cnt))  # plan.py:543
-        n = min(n, self.kpsize)
+        n = min(n, self._capacity)
         if self.profile:
             self._fetch_events()
         return self._out[:n].copy().view(numpy.recarray)
@@ -216,14 +217,14 @@ class SiftPlan(object):
             n = ctypes.c_int()
             mm = numpy.zeros(2, numpy.float32)
             out = _lib.ptr(self._records()) if records else None
-            rc = lib.siftb_plan_collect(self._plan, out, self.kpsize, ctypes.byref(n),
+            rc = lib.siftb_plan_collect(self._plan, out, self._capacity, ctypes.byref(n),
                                         self.last_counts.ctypes.data_as(_lib.c_int_p),
                                         mm.ctypes.data_as(_lib.c_float_p))
             if not records:
                 if rc != _lib.SIFTB_EOVERFLOW:
                     _lib.check(rc)
                 self.buffers["min"].value[0], self.buffers["max"].value[0] = mm[0], mm[1]
-                return min(n.value, self.kpsize)
+                return min(n.value, self._capacity)
             return self._finish(rc, n.value, mm)
         finally:
             self._pending = False

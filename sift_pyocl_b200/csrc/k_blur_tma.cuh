@@ -1,0 +1,253 @@
+// k_blur_tma.cuh -- the roofline kernel: fused separable Gaussian blur + DoG (+ decimation /
+// + normalisation) with a TMA-staged shared-memory tile and register-tiled FMA chains.
+//
+// One CTA (256 threads, 2 CTAs/SM) produces a 128 x 64 tile of G[s+1]:
+//   1. one thread issues a single cp.async.bulk.tensor.2d (TMA) for the (64+2C) x (128+2C) input box
+//      at (x0-C, y0-C); out-of-image parts are zero-filled by the TMA unit and then patched with
+//      the reference's mirror rule (convolution.cl:41-50) from the in-tile pixels (border tiles only);
+//   2. horizontal pass: each thread owns one tile row and RH consecutive outputs; the RH+2C inputs
+//      are read with conflict-free LDS.128 (row pitch = 4*odd words), every output is one
+//      sequential chain sum = fmaf(in, tap, sum), taps coming straight from the constant bank
+//      (kernel parameter), results go to a second shared buffer;
+//   3. vertical pass: each thread owns 2 adjacent columns x 16 rows (32 independent FMA chains),
+//      streaming the 16+2C rows it needs with LDS.64;
+//   4. epilogue from registers: G[s+1] (STG.64), DoG[s] = G[s] - G[s+1] with G[s] taken from the
+//      staged tile, and for s == 2 the decimated next-octave base G[3][::2, ::2].
+// The per-pixel arithmetic (tap order, fused multiply-add, fp32 rounding after each pass) is
+// identical to k_blur_generic and to the oracle, so results are bit-identical.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "k_blur.cuh"
+
+#define TB_TW 128
+#define TB_TH 64
+#define TB_THREADS 256
+#define TB_HP 132  // hbuf pitch (words): 4*33 -> conflict-free STS.128 / LDS.64
+
+__host__ __device__ constexpr int tb_box_w(int C) {
+    // smallest multiple of 4 >= TB_TW + 2C whose quarter is odd (conflict-free LDS.128 across rows)
+    int w = (TB_TW + 2 * C + 3) / 4 * 4;
+    return ((w / 4) & 1) ? w : w + 4;
+}
+__host__ __device__ constexpr int tb_box_h(int C) { return TB_TH + 2 * C; }
+__host__ __device__ constexpr size_t tb_smem_bytes(int C) {
+    return (size_t)(tb_box_h(C) * tb_box_w(C) + tb_box_h(C) * TB_HP) * sizeof(float) + 16;
+}
+
+enum { TB_DOG = 0, TB_DOG_HALF = 1, TB_NORM = 2 };
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int C, int MODE>
+__global__ void __launch_bounds__(TB_THREADS, 2)
+k_blur_tma(const __grid_constant__ CUtensorMap tmap, BlurArgs a, Taps taps) {
+    constexpr int N = 2 * C + 1;
+    constexpr int BW = tb_box_w(C), BH = tb_box_h(C);
+    constexpr int RH = 16;                 // outputs per thread in the horizontal pass
+    constexpr int NSEG = TB_TW / RH;       // 8 segments per row
+    constexpr int WIN = RH + 2 * C;        // inputs per horizontal task
+    constexpr int WIN4 = (WIN + 3) / 4;
+    constexpr int RV = 16;                 // rows per thread in the vertical pass
+    extern __shared__ __align__(128) float smem[];
+    float *tile = smem;                    // BH x BW
+    float *hbuf = smem + BH * BW;          // BH x TB_HP
+    uint64_t *bar = reinterpret_cast<uint64_t *>(hbuf + BH * TB_HP);
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * TB_TW, y0 = blockIdx.y * TB_TH;
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                     "r"((uint32_t)(BW * BH * sizeof(float)))
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+            ::"r"(smem_u32(tile)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(x0 - C), "r"(y0 - C), "r"(smem_u32(bar))
+            : "memory");
+    }
+    {   // wait for the tile (phase 0)
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+                : "=r"(done)
+                : "r"(smem_u32(bar))
+                : "memory");
+        }
+    }
+    if (MODE == TB_NORM) {  // preprocess.cl:250 on the staged pixels
+        const float mn = ordered_to_float(a.norm_mm[0]);
+        const float den = ordered_to_float(a.norm_mm[1]) - mn;
+        for (int i = tid; i < BH * BW; i += TB_THREADS) tile[i] = (255.0f * (tile[i] - mn)) / den;
+        __syncthreads();
+    }
+    const bool border = (x0 - C < 0) || (x0 + TB_TW + C > a.w) || (y0 - C < 0) || (y0 + TB_TH + C > a.h);
+    if (border) {  // block-uniform: mirror rule of convolution.cl:41-50, columns then rows
+        for (int i = tid; i < BH * BW; i += TB_THREADS) {
+            const int ty = i / BW, tx = i - ty * BW;
+            const int gy = y0 - C + ty, gx = x0 - C + tx;
+            if (gy >= 0 && gy < a.h && (gx < 0 || gx >= a.w)) {
+                const int mx = (gx < 0) ? -gx - 1 : 2 * a.w - 1 - gx;
+                const int sx = mx - x0 + C;
+                if (mx >= 0 && mx < a.w && sx >= 0 && sx < BW) tile[ty * BW + tx] = tile[ty * BW + sx];
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < BH * BW; i += TB_THREADS) {
+            const int ty = i / BW, tx = i - ty * BW;
+            const int gy = y0 - C + ty;
+            if (gy < 0 || gy >= a.h) {
+                const int my = (gy < 0) ? -gy - 1 : 2 * a.h - 1 - gy;
+                const int sy = my - y0 + C;
+                if (my >= 0 && my < a.h && sy >= 0 && sy < BH) tile[ty * BW + tx] = tile[sy * BW + tx];
+            }
+        }
+        __syncthreads();
+    }
+    // ---- horizontal pass: task q -> (row = q % BH, segment = q / BH) ----------------------------------
+    for (int q = tid; q < BH * NSEG; q += TB_THREADS) {
+        const int seg = q / BH, row = q - seg * BH;
+        const float4 *src = reinterpret_cast<const float4 *>(tile + row * BW + seg * RH);
+        float in[WIN4 * 4];
+#pragma unroll
+        for (int i = 0; i < WIN4; i++) {
+            const float4 v = src[i];
+            in[4 * i] = v.x; in[4 * i + 1] = v.y; in[4 * i + 2] = v.z; in[4 * i + 3] = v.w;
+        }
+        float acc[RH];
+#pragma unroll
+        for (int o = 0; o < RH; o++) acc[o] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+#pragma unroll
+            for (int o = 0; o < RH; o++) acc[o] = __fmaf_rn(in[o + j], taps.f[N - 1 - j], acc[o]);
+        }
+        float4 *dst = reinterpret_cast<float4 *>(hbuf + row * TB_HP + seg * RH);
+#pragma unroll
+        for (int i = 0; i < RH / 4; i++) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+    }
+    __syncthreads();
+    // ---- vertical pass: thread -> column pair cp, rows [r0, r0 + 16) -----------------------------------
+    const int cp = tid & 63, r0 = (tid >> 6) * RV;
+    float2 acc[RV];
+#pragma unroll
+    for (int o = 0; o < RV; o++) acc[o] = make_float2(0.0f, 0.0f);
+    const float *col = hbuf + r0 * TB_HP + 2 * cp;
+#pragma unroll
+    for (int k = 0; k < RV + 2 * C; k++) {
+        const float2 v = *reinterpret_cast<const float2 *>(col + k * TB_HP);
+#pragma unroll
+        for (int o = 0; o < RV; o++) {
+            const int j = k - o;  // tap index of row k for output o: ascending in k, as the reference
+            if (j >= 0 && j < N) {
+                acc[o].x = __fmaf_rn(v.x, taps.f[N - 1 - j], acc[o].x);
+                acc[o].y = __fmaf_rn(v.y, taps.f[N - 1 - j], acc[o].y);
+            }
+        }
+    }
+    // ---- epilogue ------------------------------------------------------------------------------------------
+    const int gx = x0 + 2 * cp;
+    if (gx < a.w) {
+        const bool pair = gx + 1 < a.w;
+#pragma unroll
+        for (int o = 0; o < RV; o++) {
+            const int gy = y0 + r0 + o;
+            if (gy < a.h) {
+                const long p = (long)gy * a.out_pitch + gx;
+                if (pair) *reinterpret_cast<float2 *>(a.outG + p) = acc[o];
+                else a.outG[p] = acc[o].x;
+                if (MODE != TB_NORM) {
+                    const float *ctr = tile + (r0 + o + C) * BW + C + 2 * cp;
+                    const float dx = ctr[0] - acc[o].x;
+                    if (pair) *reinterpret_cast<float2 *>(a.outD + p) = make_float2(dx, ctr[1] - acc[o].y);
+                    else a.outD[p] = dx;
+                }
+                if (MODE == TB_DOG_HALF) {
+                    if (!(o & 1) && (gy >> 1) < a.half_h && (gx >> 1) < a.half_w)
+                        a.outHalf[(long)(gy >> 1) * a.half_pitch + (gx >> 1)] = acc[o].x;
+                }
+            }
+        }
+    }
+}
+
+// ---- host side: tensor-map encoding through the driver entry point (no link-time libcuda dependency) ----
+typedef CUresult (*tb_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static tb_encode_fn tb_get_encode() {
+    static tb_encode_fn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (tb_encode_fn)p;
+    }
+    return fn;
+}
+
+// source plane usable by the TMA path: 16-B aligned base, row stride multiple of 16 B
+static inline bool tb_source_ok(const float *base, int pitch) {
+    return (((uintptr_t)base & 15) == 0) && (pitch % 4 == 0);
+}
+
+// true when a specialised instantiation exists for this half width / mode
+static inline bool tb_supported(int ntaps, int mode) {
+    const int C = ntaps >> 1;
+    if (!(ntaps & 1)) return false;
+    if (mode == TB_DOG) return C == 5 || C == 7 || C == 8 || C == 10 || C == 13;
+    if (mode == TB_DOG_HALF) return C == 8;
+    if (mode == TB_NORM) return C == 7;
+    return false;
+}
+
+static int tb_encode(CUtensorMap *map, const float *base, int w, int h, int pitch, int C) {
+    tb_encode_fn enc = tb_get_encode();
+    if (!enc) return -1;
+    cuuint64_t gdim[2] = {(cuuint64_t)w, (cuuint64_t)h};
+    cuuint64_t gstride[1] = {(cuuint64_t)pitch * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)tb_box_w(C), (cuuint32_t)tb_box_h(C)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -1;
+}
+
+template <int C, int MODE>
+static cudaError_t tb_launch_one(cudaStream_t st, const CUtensorMap &map, const BlurArgs &a, const Taps &taps) {
+    static bool attr_done[64] = {};  // per device: the attribute belongs to the function on the current device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_done[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(k_blur_tma<C, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)tb_smem_bytes(C));
+        if (e != cudaSuccess) return e;
+        attr_done[dev & 63] = true;
+    }
+    dim3 grid((a.w + TB_TW - 1) / TB_TW, (a.h + TB_TH - 1) / TB_TH);
+    k_blur_tma<C, MODE><<<grid, TB_THREADS, tb_smem_bytes(C), st>>>(map, a, taps);
+    return cudaGetLastError();
+}
+
+static cudaError_t tb_launch(cudaStream_t st, const CUtensorMap &map, const BlurArgs &a, const Taps &taps, int mode) {
+    const int C = a.ntaps >> 1;
+    if (mode == TB_DOG_HALF) return tb_launch_one<8, TB_DOG_HALF>(st, map, a, taps);
+    if (mode == TB_NORM) return tb_launch_one<7, TB_NORM>(st, map, a, taps);
+    switch (C) {
+    case 5: return tb_launch_one<5, TB_DOG>(st, map, a, taps);
+    case 7: return tb_launch_one<7, TB_DOG>(st, map, a, taps);
+    case 8: return tb_launch_one<8, TB_DOG>(st, map, a, taps);
+    case 10: return tb_launch_one<10, TB_DOG>(st, map, a, taps);
+    case 13: return tb_launch_one<13, TB_DOG>(st, map, a, taps);
+    }
+    return cudaErrorInvalidValue;
+}

@@ -21,6 +21,7 @@
 #include "../../include/siftb.h"
 #include "common.cuh"
 #include "k_blur.cuh"
+#include "k_blur_tma.cuh"
 #include "k_extrema.cuh"
 #include "k_frontend.cuh"
 #include "k_keypoint.cuh"
@@ -51,6 +52,11 @@ static const float kPeakThresh = (float)(255.0 * 0.04 / 3.0), kEdgeThresh = 0.06
                    kOriSigma = 1.5f;
 
 static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+// SIFTB_FORCE_GENERIC=1 routes every blur through the generic kernel (A/B testing of the TMA kernel)
+static int env_force_generic() {
+    const char *e = getenv("SIFTB_FORCE_GENERIC");
+    return e && e[0] == '1';
+}
 
 // ---------------------------------------------------------------------------------------------
 // taps: utils.py:54-64 kernel_size + plan.py:315-317 numpy formula (identical to the oracle)
@@ -113,6 +119,11 @@ struct siftb_plan {
     int cnt_ints = 0;
     bool in_flight = false, profile = false;
     uint64_t launches = 0;
+    CUtensorMap tmaps[MAX_OCT][5];  // source G[s] of octave o, box for taps[s]
+    bool tmaps_ok[MAX_OCT][5] = {};
+    CUtensorMap tmap_raw, tmap_img;  // first blur: from the host-staging buffer / the converted fp32 plane
+    bool tmap_raw_ok = false, tmap_img_ok = false;
+    int force_generic = 0;
     std::vector<Event> events;
     std::vector<const char *> ev_names;
     std::vector<float> ev_ms;
@@ -232,6 +243,16 @@ static int plan_create_impl(siftb_plan *p) {
     if ((rc = dalloc(p, &p->kp_scale, (size_t)p->kpsize * sizeof(int)))) return rc;
     p->out_cap = 2 * p->kpsize;
     if ((rc = dalloc(p, &p->out, (size_t)p->out_cap * sizeof(KpRecord)))) return rc;
+    if (tb_get_encode()) {
+        for (int o = 0; o < p->n_oct; o++)
+            for (int s = 0; s < 5; s++)
+                if (tb_supported(p->ntaps[s], s == kScales - 1 && o + 1 < p->n_oct ? TB_DOG_HALF : TB_DOG))
+                    p->tmaps_ok[o][s] = tb_encode(&p->tmaps[o][s], p->G[s], p->ow[o], p->oh[o], p->opitch[o], p->ntaps[s] >> 1) == 0;
+        if (tb_supported(p->ntaps[5], TB_NORM) && p->w % 4 == 0) {
+            p->tmap_raw_ok = tb_encode(&p->tmap_raw, (const float *)p->d_raw, p->w, p->h, p->w, p->ntaps[5] >> 1) == 0;
+            if (p->d_img) p->tmap_img_ok = tb_encode(&p->tmap_img, p->d_img, p->w, p->h, p->w, p->ntaps[5] >> 1) == 0;
+        }
+    }
     p->cnt_ints = 1 + 13 * p->n_oct + 2;
     if ((rc = dalloc(p, &p->d_cnt, p->cnt_ints * sizeof(int)))) return rc;
     CK(cudaHostAlloc((void **)&p->h_cnt, p->cnt_ints * sizeof(int), cudaHostAllocDefault));
@@ -252,6 +273,7 @@ extern "C" int siftb_plan_create(int height, int width, int dtype, int device, i
     siftb_plan *p = new siftb_plan();
     p->device = device; p->h = height; p->w = width; p->dtype = dtype;
     p->pix_per_kp = pix_per_kp; p->init_sigma = init_sigma;
+    p->force_generic = env_force_generic();
     int rc = plan_create_impl(p);
     if (rc) {
         std::string keep = g_err;
@@ -284,13 +306,31 @@ extern "C" int siftb_plan_set_profile(siftb_plan *p, int enable) {
 
 // ---------------------------------------------------------------------------------------------
 // launch helpers (shared by the pipeline and the stage hooks)
+// Chooses the TMA-staged specialised kernel when one exists for this tap count and the planes meet the
+// alignment rules of TMA / float2 stores; otherwise the generic kernel (identical results).
+// premap: tensor map already encoded for (in, w, h, in_pitch, C) or null (encoded here).
 static int launch_blur(cudaStream_t st, const float *in, int in_pitch, int w, int h, float *outG, int out_pitch,
                        float *outD, float *outHalf, int half_pitch, const Taps &taps, int ntaps,
-                       const unsigned *norm_mm) {
+                       const unsigned *norm_mm, const CUtensorMap *premap = nullptr, int force_generic = 0) {
     BlurArgs a;
     a.in = in; a.in_pitch = in_pitch; a.outG = outG; a.out_pitch = out_pitch; a.outD = outD;
     a.outHalf = outHalf; a.half_pitch = half_pitch; a.half_w = w / 2; a.half_h = h / 2;
     a.w = w; a.h = h; a.ntaps = ntaps; a.norm_mm = norm_mm;
+    int mode = -1;
+    if (norm_mm && !outD && !outHalf) mode = TB_NORM;
+    else if (!norm_mm && outD && outHalf) mode = TB_DOG_HALF;
+    else if (!norm_mm && outD && !outHalf) mode = TB_DOG;
+    const bool out_ok = (out_pitch % 2 == 0) && (((uintptr_t)outG & 7) == 0) && (!outD || ((uintptr_t)outD & 7) == 0);
+    if (!force_generic && mode >= 0 && tb_supported(ntaps, mode) && tb_source_ok(in, in_pitch) && out_ok &&
+        tb_get_encode()) {
+        CUtensorMap local;
+        if (!premap) {
+            if (tb_encode(&local, in, w, h, in_pitch, ntaps >> 1)) return fail(SIFTB_ECUDA, "cuTensorMapEncodeTiled failed");
+            premap = &local;
+        }
+        CK(tb_launch(st, *premap, a, taps, mode));
+        return 0;
+    }
     dim3 grid((w + BLUR_TW - 1) / BLUR_TW, (h + BLUR_TH - 1) / BLUR_TH);
     k_blur_generic<<<grid, BLUR_THREADS, blur_generic_smem(ntaps), st>>>(a, taps);
     CKL();
@@ -388,8 +428,11 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
     }
     {   // normalize fused into the initial blur (sigma = sqrt(init^2 - 0.5^2)), plan.py:525-539
         ProfScope ps(p, "normalize + init blur");
+        const CUtensorMap *pm = nullptr;
+        if (img == (const float *)p->d_raw && p->tmap_raw_ok) pm = &p->tmap_raw;
+        else if (img == p->d_img && p->tmap_img_ok) pm = &p->tmap_img;
         if ((rc = launch_blur(st, img, p->w, p->w, p->h, p->G[0], p->opitch[0], nullptr, nullptr, 0, p->taps[5],
-                              p->ntaps[5], mm)))
+                              p->ntaps[5], mm, pm, p->force_generic)))
             return rc;
         p->launches += 1;
     }
@@ -405,7 +448,8 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
                 int hp = 0;
                 if (s == kScales - 1 && o + 1 < p->n_oct) { half = p->G[0]; hp = p->opitch[o + 1]; }
                 if ((rc = launch_blur(st, p->G[s], pitch, w, h, p->G[s + 1], pitch, p->D[s], half, hp, p->taps[s],
-                                      p->ntaps[s], nullptr)))
+                                      p->ntaps[s], nullptr, p->tmaps_ok[o][s] ? &p->tmaps[o][s] : nullptr,
+                                      p->force_generic)))
                     return rc;
                 p->launches += 1;
             }
@@ -615,16 +659,18 @@ extern "C" int siftb_blur(const float *image, int height, int width, const float
     if (ntaps / 2 > (height < width ? height : width)) return fail(SIFTB_EINVAL, "kernel wider than the image");
     int rc = ensure_blur_attr();
     if (rc) return rc;
-    const long n = (long)height * width;
-    DevBuf d, o;
-    DALLOC(d, n * 4); DALLOC(o, n * 4);
-    CK(cudaMemcpy(d.p, image, n * 4, cudaMemcpyHostToDevice));
+    const int pitch = align_up(width, 32);  // same plane layout as the plan's buffers
+    const size_t pb = (size_t)pitch * height * 4, rb = (size_t)width * 4;
+    DevBuf d, o, dd;
+    DALLOC(d, pb); DALLOC(o, pb); DALLOC(dd, pb);
+    CK(cudaMemcpy2D(d.p, (size_t)pitch * 4, image, rb, rb, height, cudaMemcpyHostToDevice));
     Taps t;
     memset(&t, 0, sizeof(t));
     memcpy(t.f, taps, ntaps * sizeof(float));
-    rc = launch_blur(0, d.as<float>(), width, width, height, o.as<float>(), width, nullptr, nullptr, 0, t, ntaps, nullptr);
+    rc = launch_blur(0, d.as<float>(), pitch, width, height, o.as<float>(), pitch, dd.as<float>(), nullptr, 0, t, ntaps,
+                     nullptr, nullptr, env_force_generic());
     if (rc) return rc;
-    CK(cudaMemcpy(out, o.p, n * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy2D(out, rb, o.p, (size_t)pitch * 4, rb, height, cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -633,11 +679,13 @@ extern "C" int siftb_pyramid_octave(const float *g0, int height, int width, doub
     if (!g0 || height <= 0 || width <= 0) return fail(SIFTB_EINVAL, "bad argument");
     int rc = ensure_blur_attr();
     if (rc) return rc;
-    const long n = (long)height * width;
+    const int pitch = align_up(width, 32);
+    const long n = (long)pitch * height;  // pitched planes, as in the plan
+    const size_t rb = (size_t)width * 4, pbytes = (size_t)pitch * 4;
     const int hw = width / 2, hh = height / 2;
     DevBuf G, D, half;
     DALLOC(G, 6 * n * 4); DALLOC(D, 5 * n * 4); DALLOC(half, (size_t)hw * hh * 4);
-    CK(cudaMemcpy(G.p, g0, n * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy2D(G.p, pbytes, g0, rb, rb, height, cudaMemcpyHostToDevice));
     const double sigmaRatio = pow(2.0, 1.0 / kScales);
     double prevSigma = init_sigma;
     for (int s = 0; s < kScales + 2; s++) {
@@ -648,13 +696,13 @@ extern "C" int siftb_pyramid_octave(const float *g0, int height, int width, doub
         if (nt > SIFTB_MAX_TAPS) return fail(SIFTB_EINVAL, "init_sigma too large");
         gaussian_taps(increase, nt, t.f);
         prevSigma *= sigmaRatio;
-        rc = launch_blur(0, G.as<float>() + s * n, width, width, height, G.as<float>() + (s + 1) * n, width,
+        rc = launch_blur(0, G.as<float>() + s * n, pitch, width, height, G.as<float>() + (s + 1) * n, pitch,
                          D.as<float>() + s * n, (s == kScales - 1 && hw > 0 && hh > 0) ? half.as<float>() : nullptr, hw,
-                         t, nt, nullptr);
+                         t, nt, nullptr, nullptr, env_force_generic());
         if (rc) return rc;
     }
-    if (G5) CK(cudaMemcpy(G5, G.as<float>() + n, 5 * n * 4, cudaMemcpyDeviceToHost));
-    if (D5) CK(cudaMemcpy(D5, D.p, 5 * n * 4, cudaMemcpyDeviceToHost));
+    if (G5) CK(cudaMemcpy2D(G5, rb, G.as<float>() + n, pbytes, rb, (size_t)5 * height, cudaMemcpyDeviceToHost));
+    if (D5) CK(cudaMemcpy2D(D5, rb, D.p, pbytes, rb, (size_t)5 * height, cudaMemcpyDeviceToHost));
     if (next_base && hw > 0 && hh > 0) CK(cudaMemcpy(next_base, half.p, (size_t)hw * hh * 4, cudaMemcpyDeviceToHost));
     return 0;
 }

@@ -2,8 +2,8 @@
 // + normalisation) with a TMA-staged shared-memory tile and register-tiled FMA chains.
 //
 // One CTA (256 threads, 2 CTAs/SM) produces a 128 x 64 tile of G[s+1]:
-//   1. one thread issues a single cp.async.bulk.tensor.2d (TMA) for the (64+2C) x (128+2C) input box
-//      at (x0-C, y0-C); out-of-image parts are zero-filled by the TMA unit and then patched with
+//   1. one thread issues a single cp.async.bulk.tensor.2d (TMA) for the (64+2C) x (128+2C+pad) input box
+//      at (x0-C-DELTA, y0-C) (x aligned to 16 B); out-of-image parts are zero-filled by the TMA unit and then patched with
 //      the reference's mirror rule (convolution.cl:41-50) from the in-tile pixels (border tiles only);
 //   2. horizontal pass: each thread owns one tile row and RH consecutive outputs; the RH+2C inputs
 //      are read with conflict-free LDS.128 (row pitch = 4*odd words), every output is one
@@ -26,9 +26,14 @@
 #define TB_THREADS 256
 #define TB_HP 132  // hbuf pitch (words): 4*33 -> conflict-free STS.128 / LDS.64
 
+// TMA needs the innermost box coordinate 16-byte aligned (measured on B200: a misaligned x raises
+// "illegal instruction"), so the box starts DELTA = (-C mod 4) columns left of x0 - C.
+__host__ __device__ constexpr int tb_delta(int C) { return (4 - C % 4) % 4; }
+__host__ __device__ constexpr int tb_win4(int C) { return (16 + 2 * C + tb_delta(C) + 3) / 4; }
 __host__ __device__ constexpr int tb_box_w(int C) {
-    // smallest multiple of 4 >= TB_TW + 2C whose quarter is odd (conflict-free LDS.128 across rows)
-    int w = (TB_TW + 2 * C + 3) / 4 * 4;
+    // widest column touched by the horizontal pass, rounded to a multiple of 4 whose quarter is odd
+    // (conflict-free LDS.128 across consecutive rows)
+    int w = (TB_TW - 16) + 4 * tb_win4(C);
     return ((w / 4) & 1) ? w : w + 4;
 }
 __host__ __device__ constexpr int tb_box_h(int C) { return TB_TH + 2 * C; }
@@ -48,7 +53,9 @@ k_blur_tma(const __grid_constant__ CUtensorMap tmap, BlurArgs a, Taps taps) {
     constexpr int RH = 16;                 // outputs per thread in the horizontal pass
     constexpr int NSEG = TB_TW / RH;       // 8 segments per row
     constexpr int WIN = RH + 2 * C;        // inputs per horizontal task
-    constexpr int WIN4 = (WIN + 3) / 4;
+    constexpr int DELTA = tb_delta(C);     // tile column of global x is x - (x0 - C - DELTA)
+    constexpr int WIN4 = tb_win4(C);
+    static_assert(WIN4 * 4 >= WIN + DELTA, "window");
     constexpr int RV = 16;                 // rows per thread in the vertical pass
     extern __shared__ __align__(128) float smem[];
     float *tile = smem;                    // BH x BW
@@ -68,7 +75,7 @@ k_blur_tma(const __grid_constant__ CUtensorMap tmap, BlurArgs a, Taps taps) {
                      : "memory");
         asm volatile(
             "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-            ::"r"(smem_u32(tile)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(x0 - C), "r"(y0 - C), "r"(smem_u32(bar))
+            ::"r"(smem_u32(tile)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(x0 - C - DELTA), "r"(y0 - C), "r"(smem_u32(bar))
             : "memory");
     }
     {   // wait for the tile (phase 0)
@@ -91,10 +98,10 @@ k_blur_tma(const __grid_constant__ CUtensorMap tmap, BlurArgs a, Taps taps) {
     if (border) {  // block-uniform: mirror rule of convolution.cl:41-50, columns then rows
         for (int i = tid; i < BH * BW; i += TB_THREADS) {
             const int ty = i / BW, tx = i - ty * BW;
-            const int gy = y0 - C + ty, gx = x0 - C + tx;
+            const int gy = y0 - C + ty, gx = x0 - C - DELTA + tx;
             if (gy >= 0 && gy < a.h && (gx < 0 || gx >= a.w)) {
                 const int mx = (gx < 0) ? -gx - 1 : 2 * a.w - 1 - gx;
-                const int sx = mx - x0 + C;
+                const int sx = mx - x0 + C + DELTA;
                 if (mx >= 0 && mx < a.w && sx >= 0 && sx < BW) tile[ty * BW + tx] = tile[ty * BW + sx];
             }
         }
@@ -126,7 +133,7 @@ k_blur_tma(const __grid_constant__ CUtensorMap tmap, BlurArgs a, Taps taps) {
 #pragma unroll
         for (int j = 0; j < N; j++) {
 #pragma unroll
-            for (int o = 0; o < RH; o++) acc[o] = __fmaf_rn(in[o + j], taps.f[N - 1 - j], acc[o]);
+            for (int o = 0; o < RH; o++) acc[o] = __fmaf_rn(in[DELTA + o + j], taps.f[N - 1 - j], acc[o]);
         }
         float4 *dst = reinterpret_cast<float4 *>(hbuf + row * TB_HP + seg * RH);
 #pragma unroll
@@ -163,7 +170,7 @@ k_blur_tma(const __grid_constant__ CUtensorMap tmap, BlurArgs a, Taps taps) {
                 if (pair) *reinterpret_cast<float2 *>(a.outG + p) = acc[o];
                 else a.outG[p] = acc[o].x;
                 if (MODE != TB_NORM) {
-                    const float *ctr = tile + (r0 + o + C) * BW + C + 2 * cp;
+                    const float *ctr = tile + (r0 + o + C) * BW + C + DELTA + 2 * cp;
                     const float dx = ctr[0] - acc[o].x;
                     if (pair) *reinterpret_cast<float2 *>(a.outD + p) = make_float2(dx, ctr[1] - acc[o].y);
                     else a.outD[p] = dx;

@@ -1,0 +1,69 @@
+"""N>1 host logic on CPU: world_size-2 gloo run of the batch sharding + ragged all-gather
+(sift_pyocl_b200/dist.py).  The plan is replaced by a stub so no GPU is needed; on the GPU box the same
+code runs over NCCL (bench.py --gpus N)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+class _StubPlan(object):
+    device = 0
+
+    def keypoints(self, image):
+        from sift_pyocl_b200._lib import dtype_kp
+        seed, n = int(image[0]), int(image[1])
+        rng = np.random.default_rng(seed)
+        kp = np.zeros(n, dtype_kp)
+        kp["x"], kp["y"] = rng.random(n), rng.random(n)
+        kp["desc"] = rng.integers(0, 256, (n, 128))
+        return kp.view(np.recarray)
+
+
+def _worker(rank, world, port, n_images, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sift_pyocl_b200 import dist as sdist
+    images = [np.array([100 + i, (7 * i) % 5 * 3]) for i in range(n_images)]  # some images have 0 keypoints
+    out = sdist.keypoints_batch(_StubPlan(), images)
+    ok = len(out) == n_images
+    for i, kp in enumerate(out):
+        want = _StubPlan().keypoints(images[i])
+        ok = ok and kp.size == want.size and np.array_equal(kp.x, want.x) and np.array_equal(kp.desc, want.desc)
+    mine = sdist.shard_indices(n_images, rank, world)
+    local_only = sdist.keypoints_batch(_StubPlan(), images, gather=False)
+    ok = ok and all((local_only[i] is not None) == (i in mine) for i in range(n_images))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_images", [5, 2, 1])
+def test_sharded_batch_allgather_world2(n_images):
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_images, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert res == [(0, True), (1, True)]
+
+
+def test_shard_indices():
+    from sift_pyocl_b200.dist import shard_indices
+    assert shard_indices(64, 3, 8) == list(range(3, 64, 8))  # BASELINE config 3: 64 images over 8 GPUs
+    assert sorted(sum((shard_indices(10, r, 4) for r in range(4)), [])) == list(range(10))

@@ -11,8 +11,10 @@
 //      (kernel parameter), results go to a second shared buffer;
 //   3. vertical pass: each thread owns 2 adjacent columns x 16 rows (32 independent FMA chains),
 //      streaming the 16+2C rows it needs with LDS.64;
-//   4. epilogue from registers: G[s+1] (STG.64), DoG[s] = G[s] - G[s+1] with G[s] taken from the
-//      staged tile, and for s == 2 the decimated next-octave base G[3][::2, ::2].
+//   4. epilogue from registers: G[s+1] (STG.64), DoG[s] = G[s] - G[s+1] with G[s] re-read from L2
+//      (so the staged tile is dead after the row pass and the next tile's TMA load overlaps the column
+//      pass), and for s == 2 the decimated next-octave base G[3][::2, ::2].
+// CTAs are persistent (grid = min(tiles, 2 x 148)) and walk the tiles with a stride of gridDim.x.
 // The per-pixel arithmetic (tap order, fused multiply-add, fp32 rounding after each pass) is
 // identical to k_blur_generic and to the oracle, so results are bit-identical.
 #pragma once
@@ -47,7 +49,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 
 template <int C, int MODE>
 __global__ void __launch_bounds__(TB_THREADS, 2)
-k_blur_tma(const __grid_constant__ CUtensorMap tmap, BlurArgs a, Taps taps) {
+k_blur_tma(const __grid_constant__ CUtensorMap tmap, BlurArgs a, Taps taps, int ntx, int ntiles) {
     constexpr int N = 2 * C + 1;
     constexpr int BW = tb_box_w(C), BH = tb_box_h(C);
     constexpr int RH = 16;                 // outputs per thread in the horizontal pass
@@ -57,130 +59,199 @@ k_blur_tma(const __grid_constant__ CUtensorMap tmap, BlurArgs a, Taps taps) {
     constexpr int WIN4 = tb_win4(C);
     static_assert(WIN4 * 4 >= WIN + DELTA, "window");
     constexpr int RV = 16;                 // rows per thread in the vertical pass
+    constexpr int LW = C + DELTA;          // left halo width in tile columns
     extern __shared__ __align__(128) float smem[];
     float *tile = smem;                    // BH x BW
     float *hbuf = smem + BH * BW;          // BH x TB_HP
     uint64_t *bar = reinterpret_cast<uint64_t *>(hbuf + BH * TB_HP);
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * TB_TW, y0 = blockIdx.y * TB_TH;
 
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid == 0) {
+    // persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA load of the next tile is issued
+    // as soon as the row pass has consumed the staged tile, so it overlaps the column pass + epilogue.
+    int t = blockIdx.x;
+    if (tid == 0 && t < ntiles) {
+        const int tx0 = (t % ntx) * TB_TW, ty0 = (t / ntx) * TB_TH;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-                     "r"((uint32_t)(BW * BH * sizeof(float)))
-                     : "memory");
+                     "r"((uint32_t)(BW * BH * sizeof(float))) : "memory");
         asm volatile(
             "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-            ::"r"(smem_u32(tile)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(x0 - C - DELTA), "r"(y0 - C), "r"(smem_u32(bar))
-            : "memory");
+            ::"r"(smem_u32(tile)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(tx0 - C - DELTA), "r"(ty0 - C),
+            "r"(smem_u32(bar)) : "memory");
     }
-    {   // wait for the tile (phase 0)
-        uint32_t done = 0;
-        while (!done) {
+    uint32_t phase = 0;
+    for (; t < ntiles; t += gridDim.x) {
+        const int x0 = (t % ntx) * TB_TW, y0 = (t / ntx) * TB_TH;
+        {   // wait for the staged tile
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile(
+                    "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                    : "=r"(done) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+            }
+            phase ^= 1;
+        }
+        if (MODE == TB_NORM) {  // preprocess.cl:250 on the staged pixels
+            const float mn = ordered_to_float(a.norm_mm[0]);
+            const float den = ordered_to_float(a.norm_mm[1]) - mn;
+            float4 *t4 = reinterpret_cast<float4 *>(tile);
+            for (int i = tid; i < BH * BW / 4; i += TB_THREADS) {
+                float4 v = t4[i];
+                v.x = (255.0f * (v.x - mn)) / den; v.y = (255.0f * (v.y - mn)) / den;
+                v.z = (255.0f * (v.z - mn)) / den; v.w = (255.0f * (v.w - mn)) / den;
+                t4[i] = v;
+            }
+            __syncthreads();
+        }
+        const bool left = x0 == 0, right = x0 + TB_TW + C > a.w, top = y0 == 0, bottom = y0 + TB_TH + C > a.h;
+        if (left || right) {  // block-uniform.  Mirror rule of convolution.cl:41-50: columns first ...
+            if (left) {
+                for (int i = tid; i < BH * LW; i += TB_THREADS) {
+                    const int ty = i / LW, tx = i - ty * LW;
+                    const int gx = tx - LW;                 // < 0
+                    const int mx = -gx - 1, sx = mx + LW;   // source column inside the tile
+                    if (mx < a.w && sx < BW) tile[ty * BW + tx] = tile[ty * BW + sx];
+                }
+            }
+            if (right) {
+                const int txr = a.w - x0 + LW;              // first tile column beyond the image
+                const int nr = BW - txr;
+                for (int i = tid; i < BH * nr; i += TB_THREADS) {
+                    const int ty = i / nr, tx = txr + (i - ty * nr);
+                    const int gx = x0 - LW + tx;            // >= w
+                    const int mx = 2 * a.w - 1 - gx, sx = mx - x0 + LW;
+                    if (mx >= 0 && sx >= 0) tile[ty * BW + tx] = tile[ty * BW + sx];
+                }
+            }
+            __syncthreads();
+        }
+        if (top || bottom) {  // ... then whole rows
+            if (top) {
+                for (int i = tid; i < C * BW; i += TB_THREADS) {
+                    const int ty = i / BW, tx = i - ty * BW;
+                    const int my = C - ty - 1, sy = my + C;  // gy = ty - C < 0 -> row -gy-1
+                    if (my < a.h && sy < BH) tile[ty * BW + tx] = tile[sy * BW + tx];
+                }
+            }
+            if (bottom) {
+                const int tyb = a.h - y0 + C;               // first tile row beyond the image
+                const int nb = BH - tyb;
+                for (int i = tid; i < nb * BW; i += TB_THREADS) {
+                    const int r = i / BW, tx = i - r * BW;
+                    const int ty = tyb + r, gy = y0 - C + ty;
+                    const int my = 2 * a.h - 1 - gy, sy = my - y0 + C;
+                    if (my >= 0 && sy >= 0) tile[ty * BW + tx] = tile[sy * BW + tx];
+                }
+            }
+            __syncthreads();
+        }
+        // ---- horizontal pass: task q -> (row = q % BH, segment = q / BH) ------------------------------
+        for (int q = tid; q < BH * NSEG; q += TB_THREADS) {
+            const int seg = q / BH, row = q - seg * BH;
+            const float4 *src = reinterpret_cast<const float4 *>(tile + row * BW + seg * RH);
+            float in[WIN4 * 4];
+#pragma unroll
+            for (int i = 0; i < WIN4; i++) {
+                const float4 v = src[i];
+                in[4 * i] = v.x; in[4 * i + 1] = v.y; in[4 * i + 2] = v.z; in[4 * i + 3] = v.w;
+            }
+            float acc[RH];
+#pragma unroll
+            for (int o = 0; o < RH; o++) acc[o] = 0.0f;
+#pragma unroll
+            for (int j = 0; j < N; j++) {
+#pragma unroll
+                for (int o = 0; o < RH; o++) acc[o] = __fmaf_rn(in[DELTA + o + j], taps.f[N - 1 - j], acc[o]);
+            }
+            float4 *dst = reinterpret_cast<float4 *>(hbuf + row * TB_HP + seg * RH);
+#pragma unroll
+            for (int i = 0; i < RH / 4; i++)
+                dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+        }
+        __syncthreads();
+        // the staged tile is dead (the DoG centre is re-read from global/L2): prefetch the next one
+        if (tid == 0 && t + (int)gridDim.x < ntiles) {
+            const int tn = t + gridDim.x;
+            const int nx0 = (tn % ntx) * TB_TW, ny0 = (tn / ntx) * TB_TH;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic accesses above -> async write
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                         "r"((uint32_t)(BW * BH * sizeof(float))) : "memory");
             asm volatile(
-                "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
-                : "=r"(done)
-                : "r"(smem_u32(bar))
-                : "memory");
+                "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                ::"r"(smem_u32(tile)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(nx0 - C - DELTA), "r"(ny0 - C),
+                "r"(smem_u32(bar)) : "memory");
         }
-    }
-    if (MODE == TB_NORM) {  // preprocess.cl:250 on the staged pixels
-        const float mn = ordered_to_float(a.norm_mm[0]);
-        const float den = ordered_to_float(a.norm_mm[1]) - mn;
-        for (int i = tid; i < BH * BW; i += TB_THREADS) tile[i] = (255.0f * (tile[i] - mn)) / den;
-        __syncthreads();
-    }
-    const bool border = (x0 - C < 0) || (x0 + TB_TW + C > a.w) || (y0 - C < 0) || (y0 + TB_TH + C > a.h);
-    if (border) {  // block-uniform: mirror rule of convolution.cl:41-50, columns then rows
-        for (int i = tid; i < BH * BW; i += TB_THREADS) {
-            const int ty = i / BW, tx = i - ty * BW;
-            const int gy = y0 - C + ty, gx = x0 - C - DELTA + tx;
-            if (gy >= 0 && gy < a.h && (gx < 0 || gx >= a.w)) {
-                const int mx = (gx < 0) ? -gx - 1 : 2 * a.w - 1 - gx;
-                const int sx = mx - x0 + C + DELTA;
-                if (mx >= 0 && mx < a.w && sx >= 0 && sx < BW) tile[ty * BW + tx] = tile[ty * BW + sx];
-            }
-        }
-        __syncthreads();
-        for (int i = tid; i < BH * BW; i += TB_THREADS) {
-            const int ty = i / BW, tx = i - ty * BW;
-            const int gy = y0 - C + ty;
-            if (gy < 0 || gy >= a.h) {
-                const int my = (gy < 0) ? -gy - 1 : 2 * a.h - 1 - gy;
-                const int sy = my - y0 + C;
-                if (my >= 0 && my < a.h && sy >= 0 && sy < BH) tile[ty * BW + tx] = tile[sy * BW + tx];
-            }
-        }
-        __syncthreads();
-    }
-    // ---- horizontal pass: task q -> (row = q % BH, segment = q / BH) ----------------------------------
-    for (int q = tid; q < BH * NSEG; q += TB_THREADS) {
-        const int seg = q / BH, row = q - seg * BH;
-        const float4 *src = reinterpret_cast<const float4 *>(tile + row * BW + seg * RH);
-        float in[WIN4 * 4];
+        // ---- vertical pass: thread -> column pair cp, rows [r0, r0 + 16) -------------------------------
+        const int cp = tid & 63, r0 = (tid >> 6) * RV;
+        float2 acc[RV];
 #pragma unroll
-        for (int i = 0; i < WIN4; i++) {
-            const float4 v = src[i];
-            in[4 * i] = v.x; in[4 * i + 1] = v.y; in[4 * i + 2] = v.z; in[4 * i + 3] = v.w;
-        }
-        float acc[RH];
+        for (int o = 0; o < RV; o++) acc[o] = make_float2(0.0f, 0.0f);
+        const float *col = hbuf + r0 * TB_HP + 2 * cp;
 #pragma unroll
-        for (int o = 0; o < RH; o++) acc[o] = 0.0f;
+        for (int k = 0; k < RV + 2 * C; k++) {
+            const float2 v = *reinterpret_cast<const float2 *>(col + k * TB_HP);
 #pragma unroll
-        for (int j = 0; j < N; j++) {
-#pragma unroll
-            for (int o = 0; o < RH; o++) acc[o] = __fmaf_rn(in[DELTA + o + j], taps.f[N - 1 - j], acc[o]);
-        }
-        float4 *dst = reinterpret_cast<float4 *>(hbuf + row * TB_HP + seg * RH);
-#pragma unroll
-        for (int i = 0; i < RH / 4; i++) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
-    }
-    __syncthreads();
-    // ---- vertical pass: thread -> column pair cp, rows [r0, r0 + 16) -----------------------------------
-    const int cp = tid & 63, r0 = (tid >> 6) * RV;
-    float2 acc[RV];
-#pragma unroll
-    for (int o = 0; o < RV; o++) acc[o] = make_float2(0.0f, 0.0f);
-    const float *col = hbuf + r0 * TB_HP + 2 * cp;
-#pragma unroll
-    for (int k = 0; k < RV + 2 * C; k++) {
-        const float2 v = *reinterpret_cast<const float2 *>(col + k * TB_HP);
-#pragma unroll
-        for (int o = 0; o < RV; o++) {
-            const int j = k - o;  // tap index of row k for output o: ascending in k, as the reference
-            if (j >= 0 && j < N) {
-                acc[o].x = __fmaf_rn(v.x, taps.f[N - 1 - j], acc[o].x);
-                acc[o].y = __fmaf_rn(v.y, taps.f[N - 1 - j], acc[o].y);
-            }
-        }
-    }
-    // ---- epilogue ------------------------------------------------------------------------------------------
-    const int gx = x0 + 2 * cp;
-    if (gx < a.w) {
-        const bool pair = gx + 1 < a.w;
-#pragma unroll
-        for (int o = 0; o < RV; o++) {
-            const int gy = y0 + r0 + o;
-            if (gy < a.h) {
-                const long p = (long)gy * a.out_pitch + gx;
-                if (pair) *reinterpret_cast<float2 *>(a.outG + p) = acc[o];
-                else a.outG[p] = acc[o].x;
-                if (MODE != TB_NORM) {
-                    const float *ctr = tile + (r0 + o + C) * BW + C + DELTA + 2 * cp;
-                    const float dx = ctr[0] - acc[o].x;
-                    if (pair) *reinterpret_cast<float2 *>(a.outD + p) = make_float2(dx, ctr[1] - acc[o].y);
-                    else a.outD[p] = dx;
-                }
-                if (MODE == TB_DOG_HALF) {
-                    if (!(o & 1) && (gy >> 1) < a.half_h && (gx >> 1) < a.half_w)
-                        a.outHalf[(long)(gy >> 1) * a.half_pitch + (gx >> 1)] = acc[o].x;
+            for (int o = 0; o < RV; o++) {
+                const int j = k - o;  // tap index of row k for output o: ascending in k, as the reference
+                if (j >= 0 && j < N) {
+                    acc[o].x = __fmaf_rn(v.x, taps.f[N - 1 - j], acc[o].x);
+                    acc[o].y = __fmaf_rn(v.y, taps.f[N - 1 - j], acc[o].y);
                 }
             }
         }
+        // ---- epilogue ----------------------------------------------------------------------------------
+        const int gx = x0 + 2 * cp, gy0 = y0 + r0;
+        if (x0 + TB_TW <= a.w && y0 + TB_TH <= a.h) {  // full tile: no per-element predicates
+            float *pG = a.outG + (size_t)gy0 * a.out_pitch + gx;
+            if (MODE != TB_NORM) {
+                float *pD = a.outD + (size_t)gy0 * a.out_pitch + gx;
+                const float *pC = a.in + (size_t)gy0 * a.in_pitch + gx;
+                float2 ctr[RV];
+#pragma unroll
+                for (int o = 0; o < RV; o++) ctr[o] = __ldg(reinterpret_cast<const float2 *>(pC + o * a.in_pitch));
+#pragma unroll
+                for (int o = 0; o < RV; o++) {
+                    *reinterpret_cast<float2 *>(pG + o * a.out_pitch) = acc[o];
+                    *reinterpret_cast<float2 *>(pD + o * a.out_pitch) =
+                        make_float2(ctr[o].x - acc[o].x, ctr[o].y - acc[o].y);
+                }
+            } else {
+#pragma unroll
+                for (int o = 0; o < RV; o++) *reinterpret_cast<float2 *>(pG + o * a.out_pitch) = acc[o];
+            }
+            if (MODE == TB_DOG_HALF) {
+                float *pH = a.outHalf + (size_t)(gy0 >> 1) * a.half_pitch + (gx >> 1);
+#pragma unroll
+                for (int o = 0; o < RV; o += 2)
+                    if (((gy0 + o) >> 1) < a.half_h && (gx >> 1) < a.half_w) pH[(o >> 1) * a.half_pitch] = acc[o].x;
+            }
+        } else if (gx < a.w) {
+            const bool pair = gx + 1 < a.w;
+#pragma unroll
+            for (int o = 0; o < RV; o++) {
+                const int gy = gy0 + o;
+                if (gy < a.h) {
+                    const size_t p = (size_t)gy * a.out_pitch + gx;
+                    if (pair) *reinterpret_cast<float2 *>(a.outG + p) = acc[o];
+                    else a.outG[p] = acc[o].x;
+                    if (MODE != TB_NORM) {
+                        const float *ctr = a.in + (size_t)gy * a.in_pitch + gx;
+                        const float dx = ctr[0] - acc[o].x;
+                        if (pair) *reinterpret_cast<float2 *>(a.outD + p) = make_float2(dx, ctr[1] - acc[o].y);
+                        else a.outD[p] = dx;
+                    }
+                    if (MODE == TB_DOG_HALF) {
+                        if (!(o & 1) && (gy >> 1) < a.half_h && (gx >> 1) < a.half_w)
+                            a.outHalf[(size_t)(gy >> 1) * a.half_pitch + (gx >> 1)] = acc[o].x;
+                    }
+                }
+            }
+        }
+        __syncthreads();  // hbuf is reused by the next tile's row pass
     }
 }
 
@@ -240,8 +311,10 @@ static cudaError_t tb_launch_one(cudaStream_t st, const CUtensorMap &map, const 
         if (e != cudaSuccess) return e;
         attr_done[dev & 63] = true;
     }
-    dim3 grid((a.w + TB_TW - 1) / TB_TW, (a.h + TB_TH - 1) / TB_TH);
-    k_blur_tma<C, MODE><<<grid, TB_THREADS, tb_smem_bytes(C), st>>>(map, a, taps);
+    const int ntx = (a.w + TB_TW - 1) / TB_TW, nty = (a.h + TB_TH - 1) / TB_TH;
+    const int ntiles = ntx * nty;
+    const int grid = ntiles < 2 * 148 ? ntiles : 2 * 148;  // persistent: 2 CTAs per SM, 148 SMs
+    k_blur_tma<C, MODE><<<grid, TB_THREADS, tb_smem_bytes(C), st>>>(map, a, taps, ntx, ntiles);
     return cudaGetLastError();
 }
 

@@ -1,16 +1,16 @@
 // k_blur_tma.cuh -- the roofline kernel: fused separable Gaussian blur + DoG (+ decimation /
 // + normalisation) with a TMA-staged shared-memory tile and register-tiled FMA chains.
 //
-// One CTA (256 threads, 2 CTAs/SM) produces a 128 x 64 tile of G[s+1]:
+// One CTA (512 threads, 2 CTAs/SM) produces a 128 x 64 tile of G[s+1] (64 x 64 with 256 threads on small planes):
 //   1. one thread issues a single cp.async.bulk.tensor.2d (TMA) for the (64+2C) x (128+2C+pad) input box
 //      at (x0-C-DELTA, y0-C) (x aligned to 16 B); out-of-image parts are zero-filled by the TMA unit and then patched with
 //      the reference's mirror rule (convolution.cl:41-50) from the in-tile pixels (border tiles only);
-//   2. horizontal pass: each thread owns one tile row and RH consecutive outputs; the RH+2C inputs
+//   2. horizontal pass: each thread owns one tile row and 8 consecutive outputs; the 8+2C inputs
 //      are read with conflict-free LDS.128 (row pitch = 4*odd words), every output is one
 //      sequential chain sum = fmaf(in, tap, sum), taps coming straight from the constant bank
 //      (kernel parameter), results go to a second shared buffer;
-//   3. vertical pass: each thread owns 2 adjacent columns x 16 rows (32 independent FMA chains),
-//      streaming the 16+2C rows it needs with LDS.64;
+//   3. vertical pass: each thread owns 2 adjacent columns x 8 rows (16 independent FMA chains),
+//      streaming the 8+2C rows it needs with LDS.64;
 //   4. epilogue from registers: G[s+1] (STG.64), DoG[s] = G[s] - G[s+1] with G[s] re-read from L2
 //      (so the staged tile is dead after the row pass and the next tile's TMA load overlaps the column
 //      pass), and for s == 2 the decimated next-octave base G[3][::2, ::2].
@@ -23,42 +23,47 @@
 #include "common.cuh"
 #include "k_blur.cuh"
 
-#define TB_TW 128
 #define TB_TH 64
-#define TB_THREADS 256
-#define TB_HP 132  // hbuf pitch (words): 4*33 -> conflict-free STS.128 / LDS.64
+// tile widths: 128 (512 threads) for large planes, 64 (256 threads) when a plane has too few 128-wide tiles
+// to fill the GPU.  hbuf pitch (words) = TW + 4: a multiple of 4 with an odd quarter -> conflict-free
+// STS.128 across rows and LDS.64 along a row.
+#define TB_R 8   // outputs per thread in the row pass and rows per thread in the column pass
 
 // TMA needs the innermost box coordinate 16-byte aligned (measured on B200: a misaligned x raises
 // "illegal instruction"), so the box starts DELTA = (-C mod 4) columns left of x0 - C.
 __host__ __device__ constexpr int tb_delta(int C) { return (4 - C % 4) % 4; }
-__host__ __device__ constexpr int tb_win4(int C) { return (16 + 2 * C + tb_delta(C) + 3) / 4; }
-__host__ __device__ constexpr int tb_box_w(int C) {
+__host__ __device__ constexpr int tb_win4(int C) { return (TB_R + 2 * C + tb_delta(C) + 3) / 4; }
+__host__ __device__ constexpr int tb_box_w(int C, int TW) {
     // widest column touched by the horizontal pass, rounded to a multiple of 4 whose quarter is odd
     // (conflict-free LDS.128 across consecutive rows)
-    int w = (TB_TW - 16) + 4 * tb_win4(C);
+    int w = (TW - TB_R) + 4 * tb_win4(C);
     return ((w / 4) & 1) ? w : w + 4;
 }
 __host__ __device__ constexpr int tb_box_h(int C) { return TB_TH + 2 * C; }
-__host__ __device__ constexpr size_t tb_smem_bytes(int C) {
-    return (size_t)(tb_box_h(C) * tb_box_w(C) + tb_box_h(C) * TB_HP) * sizeof(float) + 16;
+__host__ __device__ constexpr int tb_hp(int TW) { return TW + 4; }
+__host__ __device__ constexpr size_t tb_smem_bytes(int C, int TW) {
+    return (size_t)(tb_box_h(C) * tb_box_w(C, TW) + tb_box_h(C) * tb_hp(TW)) * sizeof(float) + 16;
 }
 
 enum { TB_DOG = 0, TB_DOG_HALF = 1, TB_NORM = 2 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <int C, int MODE>
-__global__ void __launch_bounds__(TB_THREADS, 2)
+template <int C, int MODE, int TB_TW>
+__global__ void __launch_bounds__(TB_TW * 4, 2)
 k_blur_tma(const __grid_constant__ CUtensorMap tmap, BlurArgs a, Taps taps, int ntx, int ntiles) {
     constexpr int N = 2 * C + 1;
-    constexpr int BW = tb_box_w(C), BH = tb_box_h(C);
-    constexpr int RH = 16;                 // outputs per thread in the horizontal pass
-    constexpr int NSEG = TB_TW / RH;       // 8 segments per row
+    constexpr int TB_THREADS = TB_TW * 4;  // column pass: (TW/2 column pairs) x (TH/R row groups) threads
+    constexpr int TB_HP = tb_hp(TB_TW);
+    constexpr int BW = tb_box_w(C, TB_TW), BH = tb_box_h(C);
+    constexpr int RH = TB_R;               // outputs per thread in the horizontal pass
+    constexpr int NSEG = TB_TW / RH;       // segments per row
     constexpr int WIN = RH + 2 * C;        // inputs per horizontal task
     constexpr int DELTA = tb_delta(C);     // tile column of global x is x - (x0 - C - DELTA)
     constexpr int WIN4 = tb_win4(C);
     static_assert(WIN4 * 4 >= WIN + DELTA, "window");
-    constexpr int RV = 16;                 // rows per thread in the vertical pass
+    constexpr int RV = TB_R;               // rows per thread in the vertical pass
+    static_assert((TB_TW / 2) * (TB_TH / RV) == TB_THREADS, "column-pass mapping");
     constexpr int LW = C + DELTA;          // left halo width in tile columns
     extern __shared__ __align__(128) float smem[];
     float *tile = smem;                    // BH x BW
@@ -186,7 +191,7 @@ k_blur_tma(const __grid_constant__ CUtensorMap tmap, BlurArgs a, Taps taps, int 
                 "r"(smem_u32(bar)) : "memory");
         }
         // ---- vertical pass: thread -> column pair cp, rows [r0, r0 + 16) -------------------------------
-        const int cp = tid & 63, r0 = (tid >> 6) * RV;
+        const int cp = tid % (TB_TW / 2), r0 = (tid / (TB_TW / 2)) * RV;
         float2 acc[RV];
 #pragma unroll
         for (int o = 0; o < RV; o++) acc[o] = make_float2(0.0f, 0.0f);
@@ -210,14 +215,11 @@ k_blur_tma(const __grid_constant__ CUtensorMap tmap, BlurArgs a, Taps taps, int 
             if (MODE != TB_NORM) {
                 float *pD = a.outD + (size_t)gy0 * a.out_pitch + gx;
                 const float *pC = a.in + (size_t)gy0 * a.in_pitch + gx;
-                float2 ctr[RV];
-#pragma unroll
-                for (int o = 0; o < RV; o++) ctr[o] = __ldg(reinterpret_cast<const float2 *>(pC + o * a.in_pitch));
 #pragma unroll
                 for (int o = 0; o < RV; o++) {
+                    const float2 ctr = __ldg(reinterpret_cast<const float2 *>(pC + o * a.in_pitch));
                     *reinterpret_cast<float2 *>(pG + o * a.out_pitch) = acc[o];
-                    *reinterpret_cast<float2 *>(pD + o * a.out_pitch) =
-                        make_float2(ctr[o].x - acc[o].x, ctr[o].y - acc[o].y);
+                    *reinterpret_cast<float2 *>(pD + o * a.out_pitch) = make_float2(ctr.x - acc[o].x, ctr.y - acc[o].y);
                 }
             } else {
 #pragma unroll
@@ -287,12 +289,18 @@ static inline bool tb_supported(int ntaps, int mode) {
     return false;
 }
 
+// tile width used for a plane: 128 unless that leaves fewer tiles than resident CTAs (2 per SM)
+static inline int tb_tile_w(int w, int h) {
+    const int n128 = ((w + 127) / 128) * ((h + TB_TH - 1) / TB_TH);
+    return n128 >= 2 * 148 ? 128 : 64;
+}
+
 static int tb_encode(CUtensorMap *map, const float *base, int w, int h, int pitch, int C) {
     tb_encode_fn enc = tb_get_encode();
     if (!enc) return -1;
     cuuint64_t gdim[2] = {(cuuint64_t)w, (cuuint64_t)h};
     cuuint64_t gstride[1] = {(cuuint64_t)pitch * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)tb_box_w(C), (cuuint32_t)tb_box_h(C)};
+    cuuint32_t box[2] = {(cuuint32_t)tb_box_w(C, tb_tile_w(w, h)), (cuuint32_t)tb_box_h(C)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, gdim, gstride, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -300,22 +308,28 @@ static int tb_encode(CUtensorMap *map, const float *base, int w, int h, int pitc
     return r == CUDA_SUCCESS ? 0 : -1;
 }
 
-template <int C, int MODE>
-static cudaError_t tb_launch_one(cudaStream_t st, const CUtensorMap &map, const BlurArgs &a, const Taps &taps) {
+template <int C, int MODE, int TW>
+static cudaError_t tb_launch_tw(cudaStream_t st, const CUtensorMap &map, const BlurArgs &a, const Taps &taps) {
     static bool attr_done[64] = {};  // per device: the attribute belongs to the function on the current device
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_done[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(k_blur_tma<C, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)tb_smem_bytes(C));
+        cudaError_t e = cudaFuncSetAttribute(k_blur_tma<C, MODE, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)tb_smem_bytes(C, TW));
         if (e != cudaSuccess) return e;
         attr_done[dev & 63] = true;
     }
-    const int ntx = (a.w + TB_TW - 1) / TB_TW, nty = (a.h + TB_TH - 1) / TB_TH;
+    const int ntx = (a.w + TW - 1) / TW, nty = (a.h + TB_TH - 1) / TB_TH;
     const int ntiles = ntx * nty;
     const int grid = ntiles < 2 * 148 ? ntiles : 2 * 148;  // persistent: 2 CTAs per SM, 148 SMs
-    k_blur_tma<C, MODE><<<grid, TB_THREADS, tb_smem_bytes(C), st>>>(map, a, taps, ntx, ntiles);
+    k_blur_tma<C, MODE, TW><<<grid, TW * 4, tb_smem_bytes(C, TW), st>>>(map, a, taps, ntx, ntiles);
     return cudaGetLastError();
+}
+
+template <int C, int MODE>
+static cudaError_t tb_launch_one(cudaStream_t st, const CUtensorMap &map, const BlurArgs &a, const Taps &taps) {
+    if (tb_tile_w(a.w, a.h) == 128) return tb_launch_tw<C, MODE, 128>(st, map, a, taps);
+    return tb_launch_tw<C, MODE, 64>(st, map, a, taps);
 }
 
 static cudaError_t tb_launch(cudaStream_t st, const CUtensorMap &map, const BlurArgs &a, const Taps &taps, int mode) {

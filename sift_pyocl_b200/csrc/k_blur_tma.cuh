@@ -1,16 +1,16 @@
 // k_blur_tma.cuh -- the roofline kernel: fused separable Gaussian blur + DoG (+ decimation /
 // + normalisation) with a TMA-staged shared-memory tile and register-tiled FMA chains.
 //
-// One CTA (512 threads, 2 CTAs/SM) produces a 128 x 64 tile of G[s+1] (64 x 64 with 256 threads on small planes):
+// One CTA (256 threads, 2 CTAs/SM) produces a 128 x 64 tile of G[s+1] (64 x 64 on small planes):
 //   1. one thread issues a single cp.async.bulk.tensor.2d (TMA) for the (64+2C) x (128+2C+pad) input box
 //      at (x0-C-DELTA, y0-C) (x aligned to 16 B); out-of-image parts are zero-filled by the TMA unit and then patched with
 //      the reference's mirror rule (convolution.cl:41-50) from the in-tile pixels (border tiles only);
-//   2. horizontal pass: each thread owns one tile row and 8 consecutive outputs; the 8+2C inputs
+//   2. horizontal pass: each thread owns one tile row and 16 consecutive outputs; the 16+2C inputs
 //      are read with conflict-free LDS.128 (row pitch = 4*odd words), every output is one
 //      sequential chain sum = fmaf(in, tap, sum), taps coming straight from the constant bank
 //      (kernel parameter), results go to a second shared buffer;
-//   3. vertical pass: each thread owns 2 adjacent columns x 8 rows (16 independent FMA chains),
-//      streaming the 8+2C rows it needs with LDS.64;
+//   3. vertical pass: each thread owns 2 adjacent columns x 16 rows (32 independent FMA chains),
+//      streaming the 16+2C rows it needs with LDS.64;
 //   4. epilogue from registers: G[s+1] (STG.64), DoG[s] = G[s] - G[s+1] with G[s] re-read from L2
 //      (so the staged tile is dead after the row pass and the next tile's TMA load overlaps the column
 //      pass), and for s == 2 the decimated next-octave base G[3][::2, ::2].
@@ -27,16 +27,17 @@
 // tile widths: 128 (512 threads) for large planes, 64 (256 threads) when a plane has too few 128-wide tiles
 // to fill the GPU.  hbuf pitch (words) = TW + 4: a multiple of 4 with an odd quarter -> conflict-free
 // STS.128 across rows and LDS.64 along a row.
-#define TB_R 8   // outputs per thread in the row pass and rows per thread in the column pass
 
 // TMA needs the innermost box coordinate 16-byte aligned (measured on B200: a misaligned x raises
 // "illegal instruction"), so the box starts DELTA = (-C mod 4) columns left of x0 - C.
 __host__ __device__ constexpr int tb_delta(int C) { return (4 - C % 4) % 4; }
-__host__ __device__ constexpr int tb_win4(int C) { return (TB_R + 2 * C + tb_delta(C) + 3) / 4; }
+// outputs per thread in the row pass and rows per thread in the column pass: 16 on 128-wide tiles, 8 on 64-wide
+__host__ __device__ constexpr int tb_r(int TW) { return TW / 8; }
+__host__ __device__ constexpr int tb_win4(int C, int TW) { return (tb_r(TW) + 2 * C + tb_delta(C) + 3) / 4; }
 __host__ __device__ constexpr int tb_box_w(int C, int TW) {
     // widest column touched by the horizontal pass, rounded to a multiple of 4 whose quarter is odd
     // (conflict-free LDS.128 across consecutive rows)
-    int w = (TW - TB_R) + 4 * tb_win4(C);
+    int w = (TW - tb_r(TW)) + 4 * tb_win4(C, TW);
     return ((w / 4) & 1) ? w : w + 4;
 }
 __host__ __device__ constexpr int tb_box_h(int C) { return TB_TH + 2 * C; }
@@ -50,17 +51,18 @@ enum { TB_DOG = 0, TB_DOG_HALF = 1, TB_NORM = 2 };
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <int C, int MODE, int TB_TW>
-__global__ void __launch_bounds__(TB_TW * 4, 2)
+__global__ void __launch_bounds__(256, 2)
 k_blur_tma(const __grid_constant__ CUtensorMap tmap, BlurArgs a, Taps taps, int ntx, int ntiles) {
     constexpr int N = 2 * C + 1;
-    constexpr int TB_THREADS = TB_TW * 4;  // column pass: (TW/2 column pairs) x (TH/R row groups) threads
+    constexpr int TB_THREADS = 256;        // column pass: (TW/2 column pairs) x (TH/R row groups) threads
+    constexpr int TB_R = tb_r(TB_TW);
     constexpr int TB_HP = tb_hp(TB_TW);
     constexpr int BW = tb_box_w(C, TB_TW), BH = tb_box_h(C);
     constexpr int RH = TB_R;               // outputs per thread in the horizontal pass
     constexpr int NSEG = TB_TW / RH;       // segments per row
     constexpr int WIN = RH + 2 * C;        // inputs per horizontal task
     constexpr int DELTA = tb_delta(C);     // tile column of global x is x - (x0 - C - DELTA)
-    constexpr int WIN4 = tb_win4(C);
+    constexpr int WIN4 = tb_win4(C, TB_TW);
     static_assert(WIN4 * 4 >= WIN + DELTA, "window");
     constexpr int RV = TB_R;               // rows per thread in the vertical pass
     static_assert((TB_TW / 2) * (TB_TH / RV) == TB_THREADS, "column-pass mapping");
@@ -192,6 +194,16 @@ k_blur_tma(const __grid_constant__ CUtensorMap tmap, BlurArgs a, Taps taps, int 
         }
         // ---- vertical pass: thread -> column pair cp, rows [r0, r0 + 16) -------------------------------
         const int cp = tid % (TB_TW / 2), r0 = (tid / (TB_TW / 2)) * RV;
+        const int gx = x0 + 2 * cp, gy0 = y0 + r0;
+        const bool full = x0 + TB_TW <= a.w && y0 + TB_TH <= a.h;
+        // G[s] centre values for the DoG: requested from L2 now, consumed after the column pass, so that
+        // their latency hides behind the FMA chains (ncu: 20 % of the stall samples sat on these loads)
+        float2 ctr[RV];
+        if (MODE != TB_NORM && full) {
+            const float *pC = a.in + (size_t)gy0 * a.in_pitch + gx;
+#pragma unroll
+            for (int o = 0; o < RV; o++) ctr[o] = __ldg(reinterpret_cast<const float2 *>(pC + o * a.in_pitch));
+        }
         float2 acc[RV];
 #pragma unroll
         for (int o = 0; o < RV; o++) acc[o] = make_float2(0.0f, 0.0f);
@@ -209,17 +221,15 @@ k_blur_tma(const __grid_constant__ CUtensorMap tmap, BlurArgs a, Taps taps, int 
             }
         }
         // ---- epilogue ----------------------------------------------------------------------------------
-        const int gx = x0 + 2 * cp, gy0 = y0 + r0;
-        if (x0 + TB_TW <= a.w && y0 + TB_TH <= a.h) {  // full tile: no per-element predicates
+        if (full) {  // full tile: no per-element predicates
             float *pG = a.outG + (size_t)gy0 * a.out_pitch + gx;
             if (MODE != TB_NORM) {
                 float *pD = a.outD + (size_t)gy0 * a.out_pitch + gx;
-                const float *pC = a.in + (size_t)gy0 * a.in_pitch + gx;
 #pragma unroll
                 for (int o = 0; o < RV; o++) {
-                    const float2 ctr = __ldg(reinterpret_cast<const float2 *>(pC + o * a.in_pitch));
                     *reinterpret_cast<float2 *>(pG + o * a.out_pitch) = acc[o];
-                    *reinterpret_cast<float2 *>(pD + o * a.out_pitch) = make_float2(ctr.x - acc[o].x, ctr.y - acc[o].y);
+                    *reinterpret_cast<float2 *>(pD + o * a.out_pitch) =
+                        make_float2(ctr[o].x - acc[o].x, ctr[o].y - acc[o].y);
                 }
             } else {
 #pragma unroll
@@ -322,7 +332,7 @@ static cudaError_t tb_launch_tw(cudaStream_t st, const CUtensorMap &map, const B
     const int ntx = (a.w + TW - 1) / TW, nty = (a.h + TB_TH - 1) / TB_TH;
     const int ntiles = ntx * nty;
     const int grid = ntiles < 2 * 148 ? ntiles : 2 * 148;  // persistent: 2 CTAs per SM, 148 SMs
-    k_blur_tma<C, MODE, TW><<<grid, TW * 4, tb_smem_bytes(C, TW), st>>>(map, a, taps, ntx, ntiles);
+    k_blur_tma<C, MODE, TW><<<grid, 256, tb_smem_bytes(C, TW), st>>>(map, a, taps, ntx, ntiles);
     return cudaGetLastError();
 }
 

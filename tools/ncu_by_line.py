@@ -1,11 +1,12 @@
 #!/usr/bin/env python
 """Aggregate an ncu SASS source page (csv) by CUDA source line using nvdisasm -g line markers.
 
-usage: ncu_by_line.py <report.ncu-rep> <kernel-regex> <mangled-substring> [cubin]
+usage: ncu_by_line.py <report.ncu-rep> <kernel-regex> <mangled-substring> [launch-skip] [cubin]
 """
 import csv, io, re, subprocess, sys, collections
 rep, kre, mangled = sys.argv[1:4]
-cubin = sys.argv[4] if len(sys.argv) > 4 else "/tmp/cub/siftb_api.sm_100a.cubin"
+skip = sys.argv[4] if len(sys.argv) > 4 else "0"
+cubin = sys.argv[5] if len(sys.argv) > 5 else "/tmp/cub/siftb_api.sm_100a.cubin"
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
 # offset -> (file,line) for the function
 line_of, cur, infun = {}, None, False
@@ -22,7 +23,7 @@ for l in dis:
     m = re.match(r'\s*/\*([0-9a-f]{4,})\*/', l)
     if m and cur:
         line_of[int(m.group(1), 16)] = cur
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kre], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kre, "-s", skip, "-c", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hi = next(i for i, r in enumerate(rows) if "Address" in r and "Source" in r)
 hdr = rows[hi]

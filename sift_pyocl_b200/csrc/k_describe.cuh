@@ -1,65 +1,44 @@
-// k_describe.cuh -- 4x4x8 SIFT descriptor, one warp per keypoint, bit-identical to the sequential
-// reference kernel keypoints_cpu.cl:36-160 (CPU-variant semantics).
+// k_describe.cuh -- 4x4x8 SIFT descriptor, bit-identical to the sequential reference kernel
+// keypoints_cpu.cl:36-160 (CPU-variant semantics).
 //
 // The reference accumulates `hist[bin] += w` while scanning the (2R+1)^2 window in row-major order;
 // fp32 addition is not associative, so every bin must see its contributions in exactly that order.
-// Parallel scheme:
-//   phase 1  the 32 lanes evaluate 32 consecutive window samples (row-major), the valid ones are
-//            compacted IN ORDER into a shared-memory record buffer; each record also registers
-//            itself in the ordered list of every cell (r, c) it touches (<= 4 of the 16 cells);
-//   phase 2  lane X < 16 owns cell X = r*4+c and walks its own list, adding the two orientation
-//            contributions of each record into its 8 bins -- lists are in sample order, bins of
-//            different cells are independent, so all 16 lanes run concurrently;
-//   phase 3  L2 normalisation / 0.2 clamp / renormalisation / x512 -> uint8; the two
-//            sum-of-squares are accumulated sequentially by one lane (order matters), the rest is
-//            lane-parallel.
+//
+// Parallel scheme: 8 lanes (an "octet") per keypoint, 4 keypoints per warp.
+//   * evaluation: the 8 lanes evaluate 8 consecutive window samples (row-major);
+//   * commit: the valid samples of the pass are committed ONE AT A TIME in sample order.  A sample
+//     feeds up to 8 bins (2 rows x 2 columns x 2 orientations of the trilinear interpolation) and
+//     those 8 bins always differ in the parities (row&1, col&1, ori&1) -- so lane p of the octet owns
+//     parity class p, computes exactly the one contribution of its class from the broadcast sample and
+//     adds it to shared memory.  All 8 lanes work on every committed sample, bins of one sample
+//     never collide, and each bin receives its contributions in the reference's order.
+//     (The only exception, ori == 2*pi exactly, puts both orientation terms into bin 0; the lane of
+//     the even class then adds both, in order.)
+//   * finish: L2 normalisation / 0.2 clamp / renormalisation / x512 -> uint8; the two
+//     sums of squares are accumulated sequentially by one lane of the octet (order matters).
 // Also performs the host-side NaN filtering and record assembly of plan.py:546-565.
 #pragma once
 #include "common.cuh"
 #include "k_keypoint.cuh"
 
-#define DESC_WARPS 4          // warps per CTA
-#define DESC_BATCH 128        // records buffered between two phase-2 sweeps
+#define DESC_WARPS 4  // warps per CTA -> 16 keypoints per CTA
+#define DESC_HSTRIDE 136  // floats between the histograms of two octets (128 + 8: spreads the banks)
 
-struct DescSmem {
-    float4 rec_f[DESC_BATCH];            // rw0 = mag*(1-rfrac), rw1 = mag*rfrac, cfrac, ofrac
-    uint32_t rec_i[DESC_BATCH];          // (ri+1) | (ci+1)<<8 | o0<<16 | o1<<24
-    uint8_t lists[16][DESC_BATCH];       // per cell: record indices in sample order
-    uint32_t cellmask[16];
-    uint32_t count[16];
-    float hist[128];                     // [o*16 + cell]
+struct DescKp {       // per-octet state, all lanes of the octet hold the same values
+    float row, col, angle, sine, cosine, spacing, drow, dcol;
+    int irow, icol, iradius, side, total;
 };
 
-__device__ __forceinline__ void describe_flush(DescSmem &S, int lane) {
-    // phase 2: lane X < 16 consumes its ordered list
-    if (lane < 16) {
-        const int r = lane >> 2, c = lane & 3;
-        const int n = (int)S.count[lane];
-        for (int e = 0; e < n; e++) {
-            const int idx = S.lists[lane][e];
-            const float4 f = S.rec_f[idx];
-            const uint32_t u = S.rec_i[idx];
-            const int ri = (int)(u & 0xff) - 1, ci = (int)((u >> 8) & 0xff) - 1;
-            const int o0 = (u >> 16) & 0xff, o1 = (u >> 24) & 0xff;
-            const float rweight = (r == ri) ? f.x : f.y;                    // (r == 0) ? 1 - rfrac : rfrac
-            const float cweight = rweight * ((c == ci) ? 1.0f - f.z : f.z);  // (c == 0) ? 1 - cfrac : cfrac
-            float *h0 = &S.hist[o0 * 16 + lane];
-            *h0 += cweight * (1.0f - f.w);
-            float *h1 = &S.hist[o1 * 16 + lane];
-            *h1 += cweight * f.w;
-        }
-        S.count[lane] = 0;
-    }
-    __syncwarp();
-}
-
-// One warp computes the descriptor of keypoint k into out128 (128 bytes, 4-byte aligned).
-__device__ __forceinline__ void describe_warp(DescSmem &S, const float4 k, const float *__restrict__ grad,
-                                              const float *__restrict__ orim, int pitch, int grad_width,
-                                              int grad_height, int octsize, uint8_t *out128) {
-    const int lane = threadIdx.x & 31;
-    for (int i = lane; i < 128; i += 32) S.hist[i] = 0.0f;
-    if (lane < 16) { S.cellmask[lane] = 0; S.count[lane] = 0; }
+// One warp, 4 keypoints (octet g handles kp[g] when act is true for that octet).
+// hist: this octet's 128 floats in shared memory, index (r*4+c)*8 + o (the descriptor order).
+__device__ __forceinline__ void describe_octets(float *hist, bool act, const float4 k,
+                                                const float *__restrict__ grad, const float *__restrict__ orim,
+                                                int pitch, int grad_width, int grad_height, int octsize,
+                                                uint8_t *out128) {
+    const int lane = threadIdx.x & 31, l8 = lane & 7, obase = lane & 24;
+    const unsigned omask = 0xffu << obase;  // lanes of my octet
+    const int pr = (l8 >> 2) & 1, pc = (l8 >> 1) & 1, po = l8 & 1;  // parity class of this lane
+    for (int i = l8; i < 128; i += 8) hist[i] = 0.0f;
     // keypoints_cpu.cl:55-61
     const float row = k.y / (float)octsize, col = k.x / (float)octsize, angle = k.w;
     const int irow = (int)(row + 0.5f), icol = (int)(col + 0.5f);
@@ -68,15 +47,15 @@ __device__ __forceinline__ void describe_warp(DescSmem &S, const float4 k, const
     const int iradius = (int)(((1.414f * spacing) * 2.5f) + 0.5f);
     const float drow = row - (float)irow, dcol = col - (float)icol;
     const int side = 2 * iradius + 1;
-    const int total = (iradius >= 0 && iradius < 16384) ? side * side : 0;
-    int nrec = 0;
+    const int total = (act && iradius >= 0 && iradius < 16384) ? side * side : 0;
     __syncwarp();
-    for (int base = 0; base < total; base += 32) {
-        if (nrec + 32 > DESC_BATCH) { describe_flush(S, lane); nrec = 0; }
-        const int t = base + lane;
+    // warp-uniform trip count: the largest window of the 4 octets
+    const int total_max = __reduce_max_sync(0xffffffffu, total);
+    for (int base = 0; base < total_max; base += 8) {
+        const int t = base + l8;
         bool valid = false;
         float rw0 = 0.f, rw1 = 0.f, cfrac = 0.f, ofrac = 0.f;
-        int ri = 0, ci = 0, o0 = 0, o1 = 0;
+        int packed = 0;
         if (t < total) {
             const int ti = t / side;
             const int i = ti - iradius, j = (t - ti * side) - iradius;
@@ -91,100 +70,103 @@ __device__ __forceinline__ void describe_warp(DescSmem &S, const float4 k, const
                 while (ori > 2.0f * SIFTB_M_PI_F) ori -= 2.0f * SIFTB_M_PI_F;
                 while (ori < 0.0f) ori += 2.0f * SIFTB_M_PI_F;
                 const float oval = (4.0f * ori) * SIFTB_M_1_PI_F;
-                ri = (int)((rx >= 0.0f) ? rx : rx - 1.0f);
-                ci = (int)((cx >= 0.0f) ? cx : cx - 1.0f);
+                const int ri = (int)((rx >= 0.0f) ? rx : rx - 1.0f);
+                const int ci = (int)((cx >= 0.0f) ? cx : cx - 1.0f);
                 const int oi = (int)((oval >= 0.0f) ? oval : oval - 1.0f);
                 const float rfrac = rx - (float)ri;
                 cfrac = cx - (float)ci;
                 ofrac = oval - (float)oi;
                 if ((ri >= -1 && ri < 4 && oi >= 0 && oi <= 8 && rfrac >= 0.0f && rfrac <= 1.0f)) {
                     valid = true;
-                    rw0 = mag * (1.0f - rfrac);
-                    rw1 = mag * rfrac;
-                    o0 = (oi >= 8) ? 0 : oi;          // oindex = oi + orr; if (oindex >= 8) oindex = 0
-                    o1 = (oi + 1 >= 8) ? 0 : oi + 1;
+                    rw0 = mag * (1.0f - rfrac);  // rweight for r == 0
+                    rw1 = mag * rfrac;           // rweight for r == 1
+                    const int o0 = (oi >= 8) ? 0 : oi;  // oindex = oi + orr; if (oindex >= 8) oindex = 0
+                    const int o1 = (oi + 1 >= 8) ? 0 : oi + 1;
+                    packed = (ri + 1) | ((ci + 1) << 8) | (o0 << 16) | (o1 << 24);
                 }
             }
         }
-        const unsigned vm = __ballot_sync(0xffffffffu, valid);
-        if (vm == 0) continue;
-        int idx = 0;
-        if (valid) {
-            idx = nrec + __popc(vm & lanemask_lt());
-            S.rec_f[idx] = make_float4(rw0, rw1, cfrac, ofrac);
-            S.rec_i[idx] = (uint32_t)(ri + 1) | ((uint32_t)(ci + 1) << 8) | ((uint32_t)o0 << 16) | ((uint32_t)o1 << 24);
-#pragma unroll
-            for (int d = 0; d < 4; d++) {
-                const int rr = ri + (d >> 1), cc = ci + (d & 1);
-                if (rr >= 0 && rr < 4 && cc >= 0 && cc < 4) atomicOr(&S.cellmask[rr * 4 + cc], 1u << lane);
-            }
-        }
-        __syncwarp();
-        if (valid) {
-#pragma unroll
-            for (int d = 0; d < 4; d++) {
-                const int rr = ri + (d >> 1), cc = ci + (d & 1);
+        // commit the valid samples of every octet in lane (= sample) order
+        unsigned m = __ballot_sync(0xffffffffu, valid) & omask;
+        while (__any_sync(0xffffffffu, m != 0)) {
+            const bool have = m != 0;
+            const int src = have ? (__ffs(m) - 1) : lane;  // lane of my octet holding the sample
+            m &= m - 1;
+            const int u = __shfl_sync(0xffffffffu, packed, src);
+            const float s_rw0 = __shfl_sync(0xffffffffu, rw0, src);
+            const float s_rw1 = __shfl_sync(0xffffffffu, rw1, src);
+            const float s_cf = __shfl_sync(0xffffffffu, cfrac, src);
+            const float s_of = __shfl_sync(0xffffffffu, ofrac, src);
+            if (have) {
+                const int ri = (u & 0xff) - 1, ci = ((u >> 8) & 0xff) - 1, o0 = (u >> 16) & 0xff, o1 = (u >> 24) & 0xff;
+                const int dr = (pr ^ ri) & 1, dc = (pc ^ ci) & 1;  // the neighbour of my parity
+                const int rr = ri + dr, cc = ci + dc;
                 if (rr >= 0 && rr < 4 && cc >= 0 && cc < 4) {
-                    const int X = rr * 4 + cc;
-                    S.lists[X][S.count[X] + __popc(S.cellmask[X] & lanemask_lt())] = (uint8_t)idx;
+                    const float rweight = dr ? s_rw1 : s_rw0;
+                    const float cweight = rweight * (dc ? s_cf : 1.0f - s_cf);
+                    float *hb = hist + (rr * 4 + cc) * 8;
+                    if (o0 != o1) {
+                        const bool first = (o0 & 1) == po;  // which of the two orientation terms is mine
+                        hb[first ? o0 : o1] += cweight * (first ? 1.0f - s_of : s_of);
+                    } else if (po == (o0 & 1)) {  // ori == 2*pi: both terms land in the same bin, in order
+                        hb[o0] += cweight * (1.0f - s_of);
+                        hb[o0] += cweight * s_of;
+                    }
                 }
             }
         }
-        __syncwarp();
-        if (lane < 16) {
-            S.count[lane] += __popc(S.cellmask[lane]);
-            S.cellmask[lane] = 0;
-        }
-        __syncwarp();
-        nrec += __popc(vm);
-    }
-    describe_flush(S, lane);
-    // phase 3, keypoints_cpu.cl:127-160.  descriptor index i = (r*4+c)*8 + o  <->  hist[o*16 + r*4+c]
-    float v[4];
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const int i = lane * 4 + q;
-        v[q] = S.hist[(i & 7) * 16 + (i >> 3)];
     }
     __syncwarp();
-    float *seq = S.hist;  // reuse as the i-ordered scratch of squares
+    // finish, keypoints_cpu.cl:127-160: each lane of the octet owns 16 consecutive descriptor entries
+    float v[16];
 #pragma unroll
-    for (int q = 0; q < 4; q++) seq[lane * 4 + q] = v[q] * v[q];
+    for (int q = 0; q < 16; q++) v[q] = hist[l8 * 16 + q];
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 16; q++) hist[l8 * 16 + q] = v[q] * v[q];
     __syncwarp();
     float norm = 0.0f;
-    if (lane == 0)
-        for (int i = 0; i < 128; i++) norm += seq[i];
-    norm = cr_rsqrtf(__shfl_sync(0xffffffffu, norm, 0));
+    if (l8 == 0)
+        for (int i = 0; i < 128; i++) norm += hist[i];
+    norm = cr_rsqrtf(__shfl_sync(0xffffffffu, norm, obase));
     bool changed = false;
     __syncwarp();
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
+    for (int q = 0; q < 16; q++) {
         v[q] *= norm;
         if (v[q] > 0.2f) { v[q] = 0.2f; changed = true; }
-        seq[lane * 4 + q] = v[q] * v[q];
+        hist[l8 * 16 + q] = v[q] * v[q];
     }
-    changed = __any_sync(0xffffffffu, changed);
+    changed = (__ballot_sync(0xffffffffu, changed) & omask) != 0;
     __syncwarp();
+    float norm2 = 0.0f;
+    if (l8 == 0 && changed)
+        for (int i = 0; i < 128; i++) norm2 += hist[i];
+    norm2 = cr_rsqrtf(__shfl_sync(0xffffffffu, norm2, obase));
     if (changed) {
-        norm = 0.0f;
-        if (lane == 0)
-            for (int i = 0; i < 128; i++) norm += seq[i];
-        norm = cr_rsqrtf(__shfl_sync(0xffffffffu, norm, 0));
 #pragma unroll
-        for (int q = 0; q < 4; q++) v[q] *= norm;
+        for (int q = 0; q < 16; q++) v[q] *= norm2;
     }
-    uint32_t packed = 0;
+    if (act) {
+        uint32_t w4[4];
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const float x = 512.0f * v[q];
-        const int intval = (x != x) ? 0 : (int)x;
-        packed |= (uint32_t)min(255, intval) << (8 * q);  // intval >= 0 here (hist >= 0)
+        for (int q4 = 0; q4 < 4; q4++) {
+            uint32_t pk = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const float x = 512.0f * v[q4 * 4 + q];
+                const int intval = (x != x) ? 0 : (int)x;
+                pk |= (uint32_t)min(255, intval) << (8 * q);  // intval >= 0 here (hist >= 0)
+            }
+            w4[q4] = pk;
+        }
+        uint32_t *dst = reinterpret_cast<uint32_t *>(out128) + l8 * 4;  // 16-byte records offset: 4-B aligned
+        dst[0] = w4[0]; dst[1] = w4[1]; dst[2] = w4[2]; dst[3] = w4[3];
     }
-    reinterpret_cast<uint32_t *>(out128)[lane] = packed;
     __syncwarp();
 }
 
-// Pipeline form: warps grid-stride over the keypoints of the octave; rows with NaN are dropped
+// Pipeline form: octets grid-stride over the keypoints of the octave; rows with NaN are dropped
 // (plan.py:546-550) and survivors appended to the final record array (plan.py:555-565).
 __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(GradPlanes G, const float4 *__restrict__ kp,
                                                                const int *__restrict__ kp_scale,
@@ -192,27 +174,33 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(GradPlanes G, cons
                                                                const int *__restrict__ n_extra_p, int cap, int octsize,
                                                                KpRecord *__restrict__ out, int out_cap,
                                                                int *__restrict__ n_out, int *__restrict__ n_out_oct) {
-    __shared__ DescSmem smem[DESC_WARPS];
-    DescSmem &S = smem[threadIdx.x >> 5];
-    const int lane = threadIdx.x & 31;
+    __shared__ float s_hist[DESC_WARPS * 4][DESC_HSTRIDE];
+    const int lane = threadIdx.x & 31, l8 = lane & 7, obase = lane & 24;
+    float *hist = s_hist[threadIdx.x >> 3];
     const int n = min(min(*n_base_p, cap) + *n_extra_p, cap);
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int gid0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; gid0 < n; gid0 += nwarps) {
-        const float4 k = kp[gid0];
-        if (!(k.y >= 0.0f)) continue;
-        const float s = ((k.x + k.y) + k.z) + k.w;
-        if (s != s) continue;
+    const int noct = (gridDim.x * blockDim.x) >> 3;
+    const int rounds = (n + noct - 1) / noct;
+    int gid0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    for (int it = 0; it < rounds; it++, gid0 += noct) {  // warp-uniform trip count
+        bool act = gid0 < n;
+        float4 k = make_float4(0.f, 0.f, 1.f, 0.f);
+        int sc = 1;
+        if (act) {
+            k = kp[gid0];
+            sc = kp_scale[gid0];
+            const float s = ((k.x + k.y) + k.z) + k.w;
+            act = (k.y >= 0.0f) && !(s != s);
+        }
         int slot = 0;
-        if (lane == 0) {
+        if (act && l8 == 0) {
             slot = atomicAdd(n_out, 1);
             atomicAdd(n_out_oct, 1);
         }
-        slot = __shfl_sync(0xffffffffu, slot, 0);
-        if (slot >= out_cap) continue;
-        const int sc = kp_scale[gid0];
-        KpRecord *o = out + slot;
-        if (lane == 0) { o->x = k.x; o->y = k.y; o->scale = k.z; o->angle = k.w; }
-        describe_warp(S, k, G.grad[sc - 1], G.ori[sc - 1], G.pitch, G.w, G.h, octsize, o->desc);
+        slot = __shfl_sync(0xffffffffu, slot, obase);
+        if (slot >= out_cap) act = false;
+        KpRecord *o = out + (act ? slot : 0);
+        if (act && l8 == 0) { o->x = k.x; o->y = k.y; o->scale = k.z; o->angle = k.w; }
+        describe_octets(hist, act, k, G.grad[sc - 1], G.ori[sc - 1], G.pitch, G.w, G.h, octsize, o->desc);
     }
 }
 
@@ -221,12 +209,18 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe_rows(const float *
                                                                     const float *__restrict__ ori, int pitch, int w,
                                                                     int h, const float4 *__restrict__ kp, int n,
                                                                     int octsize, uint8_t *__restrict__ desc) {
-    __shared__ DescSmem smem[DESC_WARPS];
-    DescSmem &S = smem[threadIdx.x >> 5];
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int gid0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; gid0 < n; gid0 += nwarps) {
-        const float4 k = kp[gid0];
-        if (!(k.y >= 0.0f)) continue;
-        describe_warp(S, k, grad, ori, pitch, w, h, octsize, desc + 128L * gid0);
+    __shared__ float s_hist[DESC_WARPS * 4][DESC_HSTRIDE];
+    float *hist = s_hist[threadIdx.x >> 3];
+    const int noct = (gridDim.x * blockDim.x) >> 3;
+    const int rounds = (n + noct - 1) / noct;
+    int gid0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    for (int it = 0; it < rounds; it++, gid0 += noct) {
+        bool act = gid0 < n;
+        float4 k = make_float4(0.f, 0.f, 1.f, 0.f);
+        if (act) {
+            k = kp[gid0];
+            act = k.y >= 0.0f;
+        }
+        describe_octets(hist, act, k, grad, ori, pitch, w, h, octsize, desc + 128L * (act ? gid0 : 0));
     }
 }

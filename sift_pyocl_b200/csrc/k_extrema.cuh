@@ -22,18 +22,20 @@ __device__ __forceinline__ bool maxmin_pixel(const DogStack &D, int gid0, int gi
     *val_out = val;
     // image.cl:152 -- double comparison (0.8 is a double literal)
     if (!(fabs((double)val) > (0.8 * (double)peak_thresh))) return false;
-    bool ismax = val > 0.0f, ismin = !ismax;
+    // image.cl:155-170: maximum test for val > 0, minimum test otherwise, strict comparisons (plateaus
+    // fire).  Same result as the reference's flag loops, with an early exit: the in-plane neighbours are
+    // tested first because they reject most pixels after a few (L1-resident) loads.
+    const bool want_max = val > 0.0f;
+    const float sgn = want_max ? 1.0f : -1.0f;  // compare sgn*n > sgn*val : exact (sign flip only)
+    const float sval = sgn * val;
+    for (int plane = 0; plane < 3; plane++) {
+        const float *pl = plane == 0 ? dc : (plane == 1 ? dp : dn);
 #pragma unroll
-    for (int dr = -1; dr <= 1; dr++) {
-#pragma unroll
-        for (int dcx = -1; dcx <= 1; dcx++) {
-            long q = pos + (long)dr * D.pitch + dcx;
-            float a = dp[q], b = dc[q], c = dn[q];
-            if (ismax && (a > val || b > val || c > val)) ismax = false;
-            if (ismin && (a < val || b < val || c < val)) ismin = false;
+        for (int dr = -1; dr <= 1; dr++) {
+            const float *rowp = pl + pos + (long)dr * D.pitch;
+            if (sgn * rowp[-1] > sval || sgn * rowp[0] > sval || sgn * rowp[1] > sval) return false;
         }
     }
-    if (!(ismax || ismin)) return false;
     // image.cl:180-186: H00/H11 in double (literal 2.0), H01 float differences then /4.0
     const long up = pos - D.pitch, dn_ = pos + D.pitch;
     float H00 = (float)(((double)dc[up] - 2.0 * (double)dc[pos]) + (double)dc[dn_]);

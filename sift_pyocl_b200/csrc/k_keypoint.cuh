@@ -65,7 +65,9 @@ __global__ void __launch_bounds__(256) k_orient(GradPlanes G, float4 *__restrict
         const float rad2 = ((float)(radius * radius)) + 0.5f;
         const int ncols = cmax - cmin + 1, nrows = rmax - rmin + 1;
         const int total = (ncols > 0 && nrows > 0) ? ncols * nrows : 0;
-        float h0 = 0.0f, h1 = 0.0f;  // bins lane and lane+32
+        hist[lane] = 0.0f;
+        if (lane < 4) hist[32 + lane] = 0.0f;
+        __syncwarp();
         for (int base = 0; base < total; base += 32) {
             const int idx = base + lane;
             int bin = -1;
@@ -87,20 +89,18 @@ __global__ void __launch_bounds__(256) k_orient(GradPlanes G, float4 *__restrict
                     }
                 }
             }
-            // commit in lane order == the reference's row-major sample order
-            unsigned m = __ballot_sync(0xffffffffu, bin >= 0);
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const int b = __shfl_sync(0xffffffffu, bin, src);
-                const float wv = __shfl_sync(0xffffffffu, w, src);
-                if (b == lane) h0 += wv;
-                if (b == lane + 32) h1 += wv;
+            // commit: bins are independent chains; lanes that hit the same bin add in lane order
+            // (== the reference's row-major sample order), different bins add concurrently
+            if (__any_sync(0xffffffffu, bin >= 0)) {
+                const unsigned peers = __match_any_sync(0xffffffffu, bin);
+                const int rank = __popc(peers & lanemask_lt());
+                const int rounds = __reduce_max_sync(0xffffffffu, bin >= 0 ? rank : 0);
+                for (int r = 0; r <= rounds; r++) {
+                    if (bin >= 0 && rank == r) hist[bin] += w;
+                    __syncwarp();
+                }
             }
         }
-        hist[lane] = h0;
-        if (lane < 4) hist[32 + lane] = h1;
-        __syncwarp();
         // orientation_cpu.cl:100-108 -- six in-place smoothing passes.  In place means: bins 0..34 see
         // the OLD neighbours (prev is carried), bin 35 sees the NEW bin 0.  "/ 3.0" is a double division.
         for (int j = 0; j < 6; j++) {

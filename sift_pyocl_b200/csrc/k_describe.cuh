@@ -5,7 +5,8 @@
 // fp32 addition is not associative, so every bin must see its contributions in exactly that order.
 //
 // Parallel scheme: 8 lanes (an "octet") per keypoint, 4 keypoints per warp.
-//   * evaluation: the 8 lanes evaluate 8 consecutive window samples (row-major);
+//   * evaluation: the 8 lanes evaluate 8 consecutive window samples (row-major); rows are clipped to the
+//     j-interval that can pass the reference's (rx, cx) test, so almost every evaluated sample is valid;
 //   * commit: the valid samples of the pass are committed ONE AT A TIME in sample order.  A sample
 //     feeds up to 8 bins (2 rows x 2 columns x 2 orientations of the trilinear interpolation) and
 //     those 8 bins always differ in the parities (row&1, col&1, ori&1) -- so lane p of the octet owns
@@ -24,14 +25,16 @@
 #define DESC_WARPS 4  // warps per CTA -> 16 keypoints per CTA
 #define DESC_HSTRIDE 136  // floats between the histograms of two octets (128 + 8: spreads the banks)
 
-struct DescKp {       // per-octet state, all lanes of the octet hold the same values
-    float row, col, angle, sine, cosine, spacing, drow, dcol;
-    int irow, icol, iradius, side, total;
+#define DESC_MAXROWS 200  // window rows per keypoint handled by the interval table (iradius <= 99)
+
+struct DescRows {          // per-octet table of the window rows: only the j-interval that can be valid
+    short jlo[DESC_MAXROWS];       // first candidate j of row i = r - iradius
+    short pfx[DESC_MAXROWS + 1];   // exclusive prefix sum of the number of 8-sample passes per row
 };
 
 // One warp, 4 keypoints (octet g handles kp[g] when act is true for that octet).
 // hist: this octet's 128 floats in shared memory, index (r*4+c)*8 + o (the descriptor order).
-__device__ __forceinline__ void describe_octets(float *hist, bool act, const float4 k,
+__device__ __forceinline__ void describe_octets(float *hist, DescRows &rows, bool act, const float4 k,
                                                 const float *__restrict__ grad, const float *__restrict__ orim,
                                                 int pitch, int grad_width, int grad_height, int octsize,
                                                 uint8_t *out128) {
@@ -44,21 +47,77 @@ __device__ __forceinline__ void describe_octets(float *hist, bool act, const flo
     const int irow = (int)(row + 0.5f), icol = (int)(col + 0.5f);
     const float sine = cr_sinf(angle), cosine = cr_cosf(angle);
     const float spacing = k.z / (float)octsize * 3.0f;
-    const int iradius = (int)(((1.414f * spacing) * 2.5f) + 0.5f);
+    int iradius = (int)(((1.414f * spacing) * 2.5f) + 0.5f);
     const float drow = row - (float)irow, dcol = col - (float)icol;
-    const int side = 2 * iradius + 1;
-    const int total = (act && iradius >= 0 && iradius < 16384) ? side * side : 0;
-    __syncwarp();
-    // warp-uniform trip count: the largest window of the 4 octets
-    const int total_max = __reduce_max_sync(0xffffffffu, total);
-    for (int base = 0; base < total_max; base += 8) {
-        const int t = base + l8;
+    if (!(act && iradius >= 0)) iradius = -1;
+    const int nrows = 2 * iradius + 1;  // 0 rows for an inactive octet
+    const bool tabled = nrows <= DESC_MAXROWS;
+    // ---- row table: the reference scans j = -R..R of every row and keeps the samples with rx, cx in (-1, 4)
+    // (keypoints_cpu.cl:66); those form one j-interval per row.  A conservative superset of it is computed
+    // here (real-valued bounds widened by a full sample on each side) so that only candidate samples are
+    // evaluated; every evaluated sample still goes through the reference's exact fp32 test.
+    int my_passes = 0;
+    if (tabled) {
+        const double L = 2.5 * (double)spacing, sn = (double)sine, cs = (double)cosine;
+        for (int r = l8; r < nrows; r += 8) {
+            const int i = r - iradius;
+            double lo = -(double)iradius, hi = (double)iradius;
+            if (irow + i < 0 || irow + i >= grad_height) hi = lo - 1.0;  // row outside the image
+            lo = fmax(lo, -(double)icol);
+            hi = fmin(hi, (double)(grad_width - 1 - icol));
+            const double A = cs * (double)i - (double)drow;  // |A - sn*j| < L
+            if (fabs(sn) > 1e-9) {
+                const double a = (A - L) / sn, b = (A + L) / sn;
+                lo = fmax(lo, fmin(a, b) - 1.0);
+                hi = fmin(hi, fmax(a, b) + 1.0);
+            }
+            const double B = sn * (double)i - (double)dcol;  // |B + cs*j| < L
+            if (fabs(cs) > 1e-9) {
+                const double a = (-L - B) / cs, b = (L - B) / cs;
+                lo = fmax(lo, fmin(a, b) - 1.0);
+                hi = fmin(hi, fmax(a, b) + 1.0);
+            }
+            int jlo = (int)floor(lo), jhi = (int)ceil(hi);
+            jlo = max(jlo, -iradius);
+            jhi = min(jhi, iradius);
+            const int np = jhi >= jlo ? (jhi - jlo + 8) >> 3 : 0;
+            rows.jlo[r] = (short)jlo;
+            rows.pfx[r + 1] = (short)np;  // counts first, scanned below
+        }
+        __syncwarp();
+        if (l8 == 0) {
+            int acc = 0;
+            rows.pfx[0] = 0;
+            for (int r = 0; r < nrows; r++) { acc += rows.pfx[r + 1]; rows.pfx[r + 1] = (short)acc; }
+        }
+        __syncwarp();
+        my_passes = nrows > 0 ? rows.pfx[nrows] : 0;
+    } else {
+        my_passes = (nrows * nrows + 7) >> 3;  // enormous window: plain row-major scan of the whole square
+    }
+    // warp-uniform trip count: the longest of the 4 octets
+    const int passes_max = __reduce_max_sync(0xffffffffu, my_passes);
+    int rcur = 0;
+    for (int p = 0; p < passes_max; p++) {
         bool valid = false;
         float rw0 = 0.f, rw1 = 0.f, cfrac = 0.f, ofrac = 0.f;
         int packed = 0;
-        if (t < total) {
-            const int ti = t / side;
-            const int i = ti - iradius, j = (t - ti * side) - iradius;
+        int i = 0, j = 0;
+        bool in_window = false;
+        if (p < my_passes) {
+            if (tabled) {
+                while (p >= rows.pfx[rcur + 1]) rcur++;
+                i = rcur - iradius;
+                j = rows.jlo[rcur] + ((p - rows.pfx[rcur]) << 3) + l8;
+                in_window = j <= iradius;
+            } else {
+                const int t = p * 8 + l8, ti = t / nrows;
+                i = ti - iradius;
+                j = (t - ti * nrows) - iradius;
+                in_window = t < nrows * nrows;
+            }
+        }
+        if (in_window) {
             const float rx = ((cosine * (float)i - sine * (float)j) - drow) / spacing + 1.5f;
             const float cx = ((sine * (float)i + cosine * (float)j) - dcol) / spacing + 1.5f;
             if ((rx > -1.0f && rx < 4.0f && cx > -1.0f && cx < 4.0f && (irow + i) >= 0 && (irow + i) < grad_height &&
@@ -175,6 +234,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(GradPlanes G, cons
                                                                KpRecord *__restrict__ out, int out_cap,
                                                                int *__restrict__ n_out, int *__restrict__ n_out_oct) {
     __shared__ float s_hist[DESC_WARPS * 4][DESC_HSTRIDE];
+    __shared__ DescRows s_rows[DESC_WARPS * 4];
     const int lane = threadIdx.x & 31, l8 = lane & 7, obase = lane & 24;
     float *hist = s_hist[threadIdx.x >> 3];
     const int n = min(min(*n_base_p, cap) + *n_extra_p, cap);
@@ -200,7 +260,8 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(GradPlanes G, cons
         if (slot >= out_cap) act = false;
         KpRecord *o = out + (act ? slot : 0);
         if (act && l8 == 0) { o->x = k.x; o->y = k.y; o->scale = k.z; o->angle = k.w; }
-        describe_octets(hist, act, k, G.grad[sc - 1], G.ori[sc - 1], G.pitch, G.w, G.h, octsize, o->desc);
+        describe_octets(hist, s_rows[threadIdx.x >> 3], act, k, G.grad[sc - 1], G.ori[sc - 1], G.pitch, G.w, G.h, octsize,
+                        o->desc);
     }
 }
 
@@ -210,6 +271,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe_rows(const float *
                                                                     int h, const float4 *__restrict__ kp, int n,
                                                                     int octsize, uint8_t *__restrict__ desc) {
     __shared__ float s_hist[DESC_WARPS * 4][DESC_HSTRIDE];
+    __shared__ DescRows s_rows[DESC_WARPS * 4];
     float *hist = s_hist[threadIdx.x >> 3];
     const int noct = (gridDim.x * blockDim.x) >> 3;
     const int rounds = (n + noct - 1) / noct;
@@ -221,6 +283,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe_rows(const float *
             k = kp[gid0];
             act = k.y >= 0.0f;
         }
-        describe_octets(hist, act, k, grad, ori, pitch, w, h, octsize, desc + 128L * (act ? gid0 : 0));
+        describe_octets(hist, s_rows[threadIdx.x >> 3], act, k, grad, ori, pitch, w, h, octsize,
+                        desc + 128L * (act ? gid0 : 0));
     }
 }

@@ -25,7 +25,7 @@
 #define DESC_WARPS 4  // warps per CTA -> 16 keypoints per CTA
 #define DESC_HSTRIDE 136  // floats between the histograms of two octets (128 + 8: spreads the banks)
 
-#define DESC_MAXROWS 200  // window rows per keypoint handled by the interval table (iradius <= 99)
+#define DESC_MAXROWS 100  // window rows per keypoint handled by the interval table (iradius <= 49; default sigmas need 97)
 
 struct DescRows {          // per-octet table of the window rows: only the j-interval that can be valid
     short jlo[DESC_MAXROWS];       // first candidate j of row i = r - iradius
@@ -227,7 +227,7 @@ __device__ __forceinline__ void describe_octets(float *hist, DescRows &rows, boo
 
 // Pipeline form: octets grid-stride over the keypoints of the octave; rows with NaN are dropped
 // (plan.py:546-550) and survivors appended to the final record array (plan.py:555-565).
-__global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(GradPlanes G, const float4 *__restrict__ kp,
+__global__ void __launch_bounds__(DESC_WARPS * 32, 8) k_describe(GradPlanes G, const float4 *__restrict__ kp,
                                                                const int *__restrict__ kp_scale,
                                                                const int *__restrict__ n_base_p,
                                                                const int *__restrict__ n_extra_p, int cap, int octsize,
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(GradPlanes G, cons
 }
 
 // Stage-hook form: desc[i] for every input row (no filtering), single gradient plane
-__global__ void __launch_bounds__(DESC_WARPS * 32) k_describe_rows(const float *__restrict__ grad,
+__global__ void __launch_bounds__(DESC_WARPS * 32, 8) k_describe_rows(const float *__restrict__ grad,
                                                                     const float *__restrict__ ori, int pitch, int w,
                                                                     int h, const float4 *__restrict__ kp, int n,
                                                                     int octsize, uint8_t *__restrict__ desc) {

@@ -107,31 +107,38 @@ struct siftb_plan {
     int ntaps[6];
     bool has_init = false;
     size_t raw_bytes = 0, dev_bytes = 0;
-    void *d_raw = nullptr;     // staging for host input (plan dtype)
+    // Two image slots so that submit(k+1) (H->D copy on the copy stream) and collect(k) (D->H of the records)
+    // overlap the kernels of the other image; the planes and keypoint lists are shared (kernels of successive
+    // images are serialised on the compute stream).
+    void *d_raws[2] = {nullptr, nullptr};  // staging for host input (plan dtype)
     float *d_img = nullptr;    // dense fp32 plane for converted integer/RGB/f64 input
     float *G[6] = {}, *D[5] = {}, *grad[3] = {}, *ori[3] = {};
     float4 *cand = nullptr, *kp = nullptr;
     int *kp_scale = nullptr;
-    KpRecord *out = nullptr;
+    KpRecord *outs[2] = {nullptr, nullptr};
     // device counters: [0]=n_out, [1..]: per octave {n_cand, n_kp, n_extra, n_out_oct}; then stage[n_oct][3][3]; then mm[2]
-    int *d_cnt = nullptr;
-    int *h_cnt = nullptr;  // pinned mirror
+    int *d_cnts[2] = {nullptr, nullptr};
+    int *h_cnts[2] = {nullptr, nullptr};  // pinned mirrors
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {}, ev_done[2] = {}, ev_d2h[2] = {};
+    int head = 0, n_flight = 0;  // slots [head, head + n_flight) are submitted and not yet collected
+    int last = 0;                // slot of the most recently collected image
     int cnt_ints = 0;
-    bool in_flight = false, profile = false;
+    bool profile = false;
     uint64_t launches = 0;
     CUtensorMap tmaps[MAX_OCT][5];  // source G[s] of octave o, box for taps[s]
     bool tmaps_ok[MAX_OCT][5] = {};
-    CUtensorMap tmap_raw, tmap_img;  // first blur: from the host-staging buffer / the converted fp32 plane
+    CUtensorMap tmap_raws[2], tmap_img;  // first blur: from the host-staging buffers / the converted fp32 plane
     bool tmap_raw_ok = false, tmap_img_ok = false;
     int force_generic = 0;
     std::vector<Event> events;
     std::vector<const char *> ev_names;
     std::vector<float> ev_ms;
 
-    int *c_nout() const { return d_cnt; }
-    int *c_oct(int o) const { return d_cnt + 1 + 4 * o; }
-    int *c_stage(int o) const { return d_cnt + 1 + 4 * n_oct + 9 * o; }
-    unsigned *c_mm() const { return reinterpret_cast<unsigned *>(d_cnt + 1 + 13 * n_oct); }
+    int *c_nout(int s) const { return d_cnts[s]; }
+    int *c_oct(int s, int o) const { return d_cnts[s] + 1 + 4 * o; }
+    int *c_stage(int s, int o) const { return d_cnts[s] + 1 + 4 * n_oct + 9 * o; }
+    unsigned *c_mm(int s) const { return reinterpret_cast<unsigned *>(d_cnts[s] + 1 + 13 * n_oct); }
 };
 
 template <typename T>
@@ -173,13 +180,21 @@ extern "C" int siftb_plan_destroy(siftb_plan *p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
-    cudaFree(p->d_raw); cudaFree(p->d_img);
+    if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
+    for (int s = 0; s < 2; s++) { cudaFree(p->d_raws[s]); cudaFree(p->outs[s]); cudaFree(p->d_cnts[s]); }
+    cudaFree(p->d_img);
     for (auto q : p->G) cudaFree(q);
     for (auto q : p->D) cudaFree(q);
     for (auto q : p->grad) cudaFree(q);
     for (auto q : p->ori) cudaFree(q);
-    cudaFree(p->cand); cudaFree(p->kp); cudaFree(p->kp_scale); cudaFree(p->out); cudaFree(p->d_cnt);
-    if (p->h_cnt) cudaFreeHost(p->h_cnt);
+    cudaFree(p->cand); cudaFree(p->kp); cudaFree(p->kp_scale);
+    for (int s = 0; s < 2; s++) {
+        if (p->h_cnts[s]) cudaFreeHost(p->h_cnts[s]);
+        if (p->ev_h2d[s]) cudaEventDestroy(p->ev_h2d[s]);
+        if (p->ev_done[s]) cudaEventDestroy(p->ev_done[s]);
+        if (p->ev_d2h[s]) cudaEventDestroy(p->ev_d2h[s]);
+    }
+    if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
     for (auto &e : p->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
@@ -189,6 +204,12 @@ extern "C" int siftb_plan_destroy(siftb_plan *p) {
 static int plan_create_impl(siftb_plan *p) {
     CK(cudaSetDevice(p->device));
     CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+    for (int s = 0; s < 2; s++) {
+        CK(cudaEventCreateWithFlags(&p->ev_h2d[s], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&p->ev_done[s], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&p->ev_d2h[s], cudaEventDisableTiming));
+    }
     // plan.py:213-224 _calc_scales
     {
         int h = p->h, w = p->w, n = 0;
@@ -230,7 +251,7 @@ static int plan_create_impl(siftb_plan *p) {
     const size_t plane = (size_t)p->opitch[0] * p->oh[0] * sizeof(float);
     p->raw_bytes = N * (dtype_bytes(p->dtype) > 4 ? dtype_bytes(p->dtype) : 4);  // fp32 input is always accepted
     int rc;
-    if ((rc = dalloc(p, &p->d_raw, p->raw_bytes))) return rc;
+    for (int s = 0; s < 2; s++) if ((rc = dalloc(p, &p->d_raws[s], p->raw_bytes))) return rc;
     if (p->dtype != SIFTB_F32 && (rc = dalloc(p, &p->d_img, N * sizeof(float)))) return rc;
     for (int i = 0; i < 6; i++) if ((rc = dalloc(p, &p->G[i], plane))) return rc;
     for (int i = 0; i < 5; i++) if ((rc = dalloc(p, &p->D[i], plane))) return rc;
@@ -242,21 +263,24 @@ static int plan_create_impl(siftb_plan *p) {
     if ((rc = dalloc(p, &p->kp, (size_t)p->kpsize * sizeof(float4)))) return rc;
     if ((rc = dalloc(p, &p->kp_scale, (size_t)p->kpsize * sizeof(int)))) return rc;
     p->out_cap = 2 * p->kpsize;
-    if ((rc = dalloc(p, &p->out, (size_t)p->out_cap * sizeof(KpRecord)))) return rc;
+    for (int s = 0; s < 2; s++) if ((rc = dalloc(p, &p->outs[s], (size_t)p->out_cap * sizeof(KpRecord)))) return rc;
     if (tb_get_encode()) {
         for (int o = 0; o < p->n_oct; o++)
             for (int s = 0; s < 5; s++)
                 if (tb_supported(p->ntaps[s], s == kScales - 1 && o + 1 < p->n_oct ? TB_DOG_HALF : TB_DOG))
                     p->tmaps_ok[o][s] = tb_encode(&p->tmaps[o][s], p->G[s], p->ow[o], p->oh[o], p->opitch[o], p->ntaps[s] >> 1) == 0;
         if (tb_supported(p->ntaps[5], TB_NORM) && p->w % 4 == 0) {
-            p->tmap_raw_ok = tb_encode(&p->tmap_raw, (const float *)p->d_raw, p->w, p->h, p->w, p->ntaps[5] >> 1) == 0;
+            p->tmap_raw_ok = tb_encode(&p->tmap_raws[0], (const float *)p->d_raws[0], p->w, p->h, p->w, p->ntaps[5] >> 1) == 0 &&
+                             tb_encode(&p->tmap_raws[1], (const float *)p->d_raws[1], p->w, p->h, p->w, p->ntaps[5] >> 1) == 0;
             if (p->d_img) p->tmap_img_ok = tb_encode(&p->tmap_img, p->d_img, p->w, p->h, p->w, p->ntaps[5] >> 1) == 0;
         }
     }
     p->cnt_ints = 1 + 13 * p->n_oct + 2;
-    if ((rc = dalloc(p, &p->d_cnt, p->cnt_ints * sizeof(int)))) return rc;
-    CK(cudaHostAlloc((void **)&p->h_cnt, p->cnt_ints * sizeof(int), cudaHostAllocDefault));
-    memset(p->h_cnt, 0, p->cnt_ints * sizeof(int));
+    for (int s = 0; s < 2; s++) {
+        if ((rc = dalloc(p, &p->d_cnts[s], p->cnt_ints * sizeof(int)))) return rc;
+        CK(cudaHostAlloc((void **)&p->h_cnts[s], p->cnt_ints * sizeof(int), cudaHostAllocDefault));
+        memset(p->h_cnts[s], 0, p->cnt_ints * sizeof(int));
+    }
     CK(cudaFuncSetAttribute(k_blur_generic, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)blur_generic_smem(SIFTB_MAX_TAPS - 1)));
     return 0;
@@ -405,13 +429,19 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
     p->events.clear();
     const long N = (long)p->h * p->w;
     const void *src = image;
+    const int slot = (p->head + p->n_flight) & 1;
     if (!on_device) {
-        ProfScope ps(p, "copy H->D");
-        CK(cudaMemcpyAsync(p->d_raw, image, (size_t)N * dtype_bytes(dtype), cudaMemcpyHostToDevice, st));
-        src = p->d_raw;
+        // H->D on the copy stream: overlaps the kernels of the previous image (pinned host memory)
+        CK(cudaMemcpyAsync(p->d_raws[slot], image, (size_t)N * dtype_bytes(dtype), cudaMemcpyHostToDevice,
+                           p->copy_stream));
+        CK(cudaEventRecord(p->ev_h2d[slot], p->copy_stream));
+        CK(cudaStreamWaitEvent(st, p->ev_h2d[slot], 0));
+        src = p->d_raws[slot];
     }
-    CK(cudaMemsetAsync(p->d_cnt, 0, p->cnt_ints * sizeof(int), st));
-    unsigned *mm = p->c_mm();
+    // the records of this slot's previous image must have left the device before they are overwritten
+    CK(cudaStreamWaitEvent(st, p->ev_d2h[slot], 0));
+    CK(cudaMemsetAsync(p->d_cnts[slot], 0, p->cnt_ints * sizeof(int), st));
+    unsigned *mm = p->c_mm(slot);
     const float *img;
     int rc;
     {
@@ -429,7 +459,7 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
     {   // normalize fused into the initial blur (sigma = sqrt(init^2 - 0.5^2)), plan.py:525-539
         ProfScope ps(p, "normalize + init blur");
         const CUtensorMap *pm = nullptr;
-        if (img == (const float *)p->d_raw && p->tmap_raw_ok) pm = &p->tmap_raw;
+        if (img == (const float *)p->d_raws[slot] && p->tmap_raw_ok) pm = &p->tmap_raws[slot];
         else if (img == p->d_img && p->tmap_img_ok) pm = &p->tmap_img;
         if ((rc = launch_blur(st, img, p->w, p->w, p->h, p->G[0], p->opitch[0], nullptr, nullptr, 0, p->taps[5],
                               p->ntaps[5], mm, pm, p->force_generic)))
@@ -439,8 +469,8 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
     for (int o = 0; o < p->n_oct; o++) {
         const int w = p->ow[o], h = p->oh[o], pitch = p->opitch[o];
         const int octsize = 1 << o;
-        int *c = p->c_oct(o);
-        int *stage = p->c_stage(o);
+        int *c = p->c_oct(slot, o);
+        int *stage = p->c_stage(slot, o);
         {
             ProfScope ps(p, "blur + DoG", o);
             for (int s = 0; s < kScales + 2; s++) {
@@ -492,42 +522,50 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
         }
         {
             ProfScope ps(p, "descriptors", o);
-            k_describe<<<148 * 8, DESC_WARPS * 32, 0, st>>>(gp, p->kp, p->kp_scale, c + 1, c + 2, p->kpsize, octsize, p->out,
-                                                p->out_cap, p->c_nout(), c + 3);
+            k_describe<<<148 * 8, DESC_WARPS * 32, 0, st>>>(gp, p->kp, p->kp_scale, c + 1, c + 2, p->kpsize, octsize,
+                                                p->outs[slot], p->out_cap, p->c_nout(slot), c + 3);
             CKL();
             p->launches += 1;
         }
     }
-    CK(cudaMemcpyAsync(p->h_cnt, p->d_cnt, p->cnt_ints * sizeof(int), cudaMemcpyDeviceToHost, st));
-    p->in_flight = true;
+    CK(cudaMemcpyAsync(p->h_cnts[slot], p->d_cnts[slot], p->cnt_ints * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(p->ev_done[slot], st));
+    p->n_flight++;
     return 0;
 }
 
 static int collect_impl(siftb_plan *p, siftb_kp *out, int cap, int *n_out, int *n_per_octave, float *minmax) {
-    if (!p->in_flight) return fail(SIFTB_EINVAL, "collect without submit");
+    if (p->n_flight == 0) return fail(SIFTB_EINVAL, "collect without submit");
     CK(cudaSetDevice(p->device));
-    CK(cudaStreamSynchronize(p->stream));
-    p->in_flight = false;
-    const int n = p->h_cnt[0];
+    const int slot = p->head;
+    CK(cudaEventSynchronize(p->ev_done[slot]));
+    p->head ^= 1;
+    p->n_flight--;
+    p->last = slot;
+    const int *h_cnt = p->h_cnts[slot];
+    const int n = h_cnt[0];
     int rc = 0;
     int ncopy = n;
     if (ncopy > p->out_cap) { ncopy = p->out_cap; rc = SIFTB_EOVERFLOW; }
     if (out && ncopy > cap) { ncopy = cap; rc = SIFTB_EOVERFLOW; }
     for (int o = 0; o < p->n_oct; o++) {
-        const int *c = p->h_cnt + 1 + 4 * o;
+        const int *c = h_cnt + 1 + 4 * o;
         if (c[0] > p->kpsize || c[1] + c[2] > p->kpsize) rc = SIFTB_EOVERFLOW;
         if (n_per_octave) n_per_octave[o] = c[3];
     }
     if (minmax) {
-        const unsigned *mm = reinterpret_cast<const unsigned *>(p->h_cnt + 1 + 13 * p->n_oct);
+        const unsigned *mm = reinterpret_cast<const unsigned *>(h_cnt + 1 + 13 * p->n_oct);
         unsigned u0 = mm[0], u1 = mm[1];
         uint32_t a = (u0 & 0x80000000u) ? (u0 & 0x7fffffffu) : ~u0, b = (u1 & 0x80000000u) ? (u1 & 0x7fffffffu) : ~u1;
         memcpy(&minmax[0], &a, 4);
         memcpy(&minmax[1], &b, 4);
     }
     if (out && ncopy > 0) {
-        CK(cudaMemcpyAsync(out, p->out, (size_t)ncopy * sizeof(siftb_kp), cudaMemcpyDeviceToHost, p->stream));
-        CK(cudaStreamSynchronize(p->stream));
+        // D->H on the copy stream: the compute stream may already be running the next image
+        CK(cudaMemcpyAsync(out, p->outs[slot], (size_t)ncopy * sizeof(siftb_kp), cudaMemcpyDeviceToHost,
+                           p->copy_stream));
+        CK(cudaEventRecord(p->ev_d2h[slot], p->copy_stream));
+        CK(cudaStreamSynchronize(p->copy_stream));
     }
     if (n_out) *n_out = n;
     if (rc == SIFTB_EOVERFLOW) return fail(rc, "keypoint buffer overflow (reference: plan.py:771 warning)");
@@ -537,7 +575,7 @@ static int collect_impl(siftb_plan *p, siftb_kp *out, int cap, int *n_out, int *
 extern "C" int siftb_plan_submit(siftb_plan *p, const void *image, int flags) {
     if (!p || !image) return fail(SIFTB_EINVAL, "null argument");
     std::lock_guard<std::mutex> lk(p->mtx);
-    if (p->in_flight) return fail(SIFTB_EINVAL, "a submit is already in flight on this plan");
+    if (p->n_flight >= 2) return fail(SIFTB_EINVAL, "two submits are already in flight on this plan");
     return submit_impl(p, image, flags);
 }
 extern "C" int siftb_plan_collect(siftb_plan *p, siftb_kp *out, int cap, int *n_out, int *n_per_octave,
@@ -550,15 +588,15 @@ extern "C" int siftb_plan_keypoints(siftb_plan *p, const void *image, int flags,
                                     int *n_out, int *n_per_octave, float *minmax) {
     if (!p || !image) return fail(SIFTB_EINVAL, "null argument");
     std::lock_guard<std::mutex> lk(p->mtx);
-    if (p->in_flight) return fail(SIFTB_EINVAL, "a submit is already in flight on this plan");
+    if (p->n_flight != 0) return fail(SIFTB_EINVAL, "a submit is already in flight on this plan");
     int rc = submit_impl(p, image, flags);
     if (rc) return rc;
     return collect_impl(p, out, cap, n_out, n_per_octave, minmax);
 }
 extern "C" int siftb_plan_result_dev(const siftb_plan *p, const siftb_kp **recs, const int **count) {
     if (!p) return fail(SIFTB_EINVAL, "null plan");
-    if (recs) *recs = reinterpret_cast<const siftb_kp *>(p->out);
-    if (count) *count = p->d_cnt;
+    if (recs) *recs = reinterpret_cast<const siftb_kp *>(p->outs[p->last]);
+    if (count) *count = p->d_cnts[p->last];
     return 0;
 }
 extern "C" int siftb_plan_events(siftb_plan *p, const char *const **names, const float **ms, int *n) {
@@ -582,7 +620,7 @@ extern "C" int siftb_plan_events(siftb_plan *p, const char *const **names, const
 extern "C" int siftb_plan_stage_counts(siftb_plan *p, int *counts) {
     if (!p || !counts) return fail(SIFTB_EINVAL, "null argument");
     std::lock_guard<std::mutex> lk(p->mtx);
-    memcpy(counts, p->h_cnt + 1 + 4 * p->n_oct, sizeof(int) * 9 * p->n_oct);
+    memcpy(counts, p->h_cnts[p->last] + 1 + 4 * p->n_oct, sizeof(int) * 9 * p->n_oct);
     return 0;
 }
 

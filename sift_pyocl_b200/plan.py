@@ -117,13 +117,20 @@ class SiftPlan(object):
             lib.siftb_plan_set_profile(handle, 1)
         self.last_counts = numpy.zeros(self.octave_max, numpy.int32)
         self._out = None  # host record buffer, allocated on first use
-        self._pending = False
+        self._pending = 0
+        self._keep = []
         logger.info("SiftPlan %s %s on CUDA device %d: %d octaves, kpsize %d, %.1f MB", self.shape, self.dtype,
                     self.device, self.octave_max, self.kpsize, self.memory / 1e6)
 
     def __del__(self):
         """Destructor: release all buffers (reference plan.py:203-211)."""
         plan, self._plan = getattr(self, "_plan", None), None
+        if getattr(self, "_out_pinned", False):
+            try:
+                _lib.pinned_free(self._out)
+            except Exception:
+                pass
+            self._out = None
         if plan:
             try:
                 _lib.load().siftb_plan_destroy(plan)
@@ -154,7 +161,11 @@ class SiftPlan(object):
 
     def _records(self):
         if self._out is None:
-            self._out = numpy.empty(self._capacity, dtype=self.dtype_kp)
+            try:  # page-locked: the D->H copy of the records runs at full PCIe speed
+                self._out = _lib.pinned_empty((self._capacity,), self.dtype_kp)
+                self._out_pinned = True
+            except Exception:
+                self._out = numpy.empty(self._capacity, dtype=self.dtype_kp)
         return self._out
 
     def keypoints(self, image):
@@ -167,6 +178,7 @@ class SiftPlan(object):
         self.reset_timer()
         with self._sem:
             t0 = time.time()
+            assert self._pending == 0, "images are in flight: collect() them first"
             pointer, flags, keep = self._image_args(image)
             lib = _lib.load()
             out = self._records()
@@ -197,39 +209,61 @@ class SiftPlan(object):
 
     # -- split form, for callers that overlap copies with compute (no reference equivalent) -----
     def submit(self, image):
-        """Enqueue copy + all kernels for ``image`` and return immediately; pair with collect()."""
-        self._sem.acquire()
-        try:
+        """Enqueue copy + all kernels for ``image`` and return immediately; pair with collect().
+
+        Up to two images may be in flight: the H->D copy of image k+1 and the D->H copy of the records of
+        image k then overlap the kernels of the other image (results come back in submission order).
+        Host images should live in page-locked memory (``pinned_empty``) for the copies to be asynchronous.
+        """
+        with self._sem:
+            assert self._pending < 2, "two images are already in flight: call collect() first"
             pointer, flags, keep = self._image_args(image)
             _lib.check(_lib.load().siftb_plan_submit(self._plan, pointer, flags))
-            self._keep = keep
-            self._pending = True
-        except Exception:
-            self._sem.release()
-            raise
+            self._keep.append(keep)
+            self._pending += 1
 
     def collect(self, records=True):
-        """Wait for the submitted image and return its keypoints.  With ``records=False`` the records
+        """Wait for the oldest submitted image and return its keypoints.  With ``records=False`` the records
         stay on the device (see device_records()) and only their number is returned."""
-        assert self._pending, "collect() without submit()"
-        try:
-            lib = _lib.load()
-            n = ctypes.c_int()
-            mm = numpy.zeros(2, numpy.float32)
-            out = _lib.ptr(self._records()) if records else None
-            rc = lib.siftb_plan_collect(self._plan, out, self._capacity, ctypes.byref(n),
-                                        self.last_counts.ctypes.data_as(_lib.c_int_p),
-                                        mm.ctypes.data_as(_lib.c_float_p))
-            if not records:
-                if rc != _lib.SIFTB_EOVERFLOW:
-                    _lib.check(rc)
-                self.buffers["min"].value[0], self.buffers["max"].value[0] = mm[0], mm[1]
-                return min(n.value, self._capacity)
-            return self._finish(rc, n.value, mm)
-        finally:
-            self._pending = False
-            self._keep = None
-            self._sem.release()
+        with self._sem:
+            assert self._pending > 0, "collect() without submit()"
+            try:
+                lib = _lib.load()
+                n = ctypes.c_int()
+                mm = numpy.zeros(2, numpy.float32)
+                out = _lib.ptr(self._records()) if records else None
+                rc = lib.siftb_plan_collect(self._plan, out, self._capacity, ctypes.byref(n),
+                                            self.last_counts.ctypes.data_as(_lib.c_int_p),
+                                            mm.ctypes.data_as(_lib.c_float_p))
+                if not records:
+                    if rc != _lib.SIFTB_EOVERFLOW:
+                        _lib.check(rc)
+                    self.buffers["min"].value[0], self.buffers["max"].value[0] = mm[0], mm[1]
+                    return min(n.value, self._capacity)
+                return self._finish(rc, n.value, mm)
+            finally:
+                self._pending -= 1
+                self._keep.pop(0)
+
+    def keypoints_many(self, images):
+        """Generator: keypoints of every image of ``images`` in order, with the copies of one image
+        overlapping the kernels of the next (two images in flight)."""
+        it = iter(images)
+        n_sub = 0
+        for image in it:
+            self.submit(image)
+            n_sub += 1
+            if n_sub == 2:
+                yield self.collect()
+                n_sub -= 1
+        while n_sub:
+            yield self.collect()
+            n_sub -= 1
+
+    @staticmethod
+    def pinned_empty(shape, dtype=numpy.float32):
+        """numpy array in page-locked host memory (asynchronous H<->D copies)."""
+        return _lib.pinned_empty(shape, dtype)
 
     def device_records(self):
         """(device pointer of the record array, device pointer of the int32 record count) of the last

@@ -272,6 +272,28 @@ def test_plan_reuse_and_device_input(sift, oracle):
     assert np.array_equal(_sort_kp(plan.collect()), _sort_kp(k1))
 
 
+def test_pipelined_two_in_flight(sift, oracle):
+    imgs = [_ms(320, 40 + i) for i in range(5)]
+    plan = sift.SiftPlan(shape=imgs[0].shape, dtype=np.float32)
+    pinned = []
+    for im in imgs:  # page-locked inputs: asynchronous H->D copies
+        buf = plan.pinned_empty(im.shape)
+        buf[...] = im
+        pinned.append(buf)
+    got = list(plan.keypoints_many(pinned))
+    assert len(got) == len(imgs)
+    for im, kp in zip(imgs, got):
+        assert np.array_equal(_sort_kp(kp), _sort_kp(oracle.keypoints(im)))
+    plan.submit(pinned[0])
+    plan.submit(pinned[1])
+    with pytest.raises(AssertionError):
+        plan.submit(pinned[2])  # at most two images in flight
+    a, b = plan.collect(), plan.collect()
+    assert np.array_equal(_sort_kp(a), _sort_kp(got[0])) and np.array_equal(_sort_kp(b), _sort_kp(got[1]))
+    with pytest.raises(AssertionError):
+        plan.collect()
+
+
 def test_error_behaviour(sift):
     with pytest.raises(RuntimeError):
         sift.SiftPlan(shape=(4, 4, 4, 4), dtype=np.float32)  # plan.py:151

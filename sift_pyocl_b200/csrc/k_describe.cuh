@@ -232,16 +232,21 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 8) k_describe(GradPlanes G, c
                                                                const int *__restrict__ n_base_p,
                                                                const int *__restrict__ n_extra_p, int cap, int octsize,
                                                                KpRecord *__restrict__ out, int out_cap,
-                                                               int *__restrict__ n_out, int *__restrict__ n_out_oct) {
+                                                               int *__restrict__ n_out, int *__restrict__ n_out_oct,
+                                                               int *__restrict__ queue) {
     __shared__ float s_hist[DESC_WARPS * 4][DESC_HSTRIDE];
     __shared__ DescRows s_rows[DESC_WARPS * 4];
     const int lane = threadIdx.x & 31, l8 = lane & 7, obase = lane & 24;
     float *hist = s_hist[threadIdx.x >> 3];
     const int n = min(min(*n_base_p, cap) + *n_extra_p, cap);
-    const int noct = (gridDim.x * blockDim.x) >> 3;
-    const int rounds = (n + noct - 1) / noct;
-    int gid0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    for (int it = 0; it < rounds; it++, gid0 += noct) {  // warp-uniform trip count
+    // dynamic work queue: every warp fetches 4 keypoints at a time, so warps with small windows simply fetch
+    // more often and the last wave is not quantised to the grid size
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(queue, 4);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const int gid0 = base + (lane >> 3);
         bool act = gid0 < n;
         float4 k = make_float4(0.f, 0.f, 1.f, 0.f);
         int sc = 1;

@@ -117,6 +117,7 @@ struct siftb_plan {
     int *kp_scale = nullptr;
     KpRecord *outs[2] = {nullptr, nullptr};
     // device counters: [0]=n_out, [1..]: per octave {n_cand, n_kp, n_extra, n_out_oct}; then stage[n_oct][3][3]; then mm[2]
+    int *d_queue = nullptr;  // [2][MAX_OCT] work-queue heads of k_describe
     int *d_cnts[2] = {nullptr, nullptr};
     int *h_cnts[2] = {nullptr, nullptr};  // pinned mirrors
     cudaStream_t copy_stream = nullptr;
@@ -187,7 +188,7 @@ extern "C" int siftb_plan_destroy(siftb_plan *p) {
     for (auto q : p->D) cudaFree(q);
     for (auto q : p->grad) cudaFree(q);
     for (auto q : p->ori) cudaFree(q);
-    cudaFree(p->cand); cudaFree(p->kp); cudaFree(p->kp_scale);
+    cudaFree(p->cand); cudaFree(p->kp); cudaFree(p->kp_scale); cudaFree(p->d_queue);
     for (int s = 0; s < 2; s++) {
         if (p->h_cnts[s]) cudaFreeHost(p->h_cnts[s]);
         if (p->ev_h2d[s]) cudaEventDestroy(p->ev_h2d[s]);
@@ -262,6 +263,7 @@ static int plan_create_impl(siftb_plan *p) {
     if ((rc = dalloc(p, &p->cand, (size_t)p->kpsize * sizeof(float4)))) return rc;
     if ((rc = dalloc(p, &p->kp, (size_t)p->kpsize * sizeof(float4)))) return rc;
     if ((rc = dalloc(p, &p->kp_scale, (size_t)p->kpsize * sizeof(int)))) return rc;
+    if ((rc = dalloc(p, &p->d_queue, 2 * MAX_OCT * sizeof(int)))) return rc;
     p->out_cap = 2 * p->kpsize;
     for (int s = 0; s < 2; s++) if ((rc = dalloc(p, &p->outs[s], (size_t)p->out_cap * sizeof(KpRecord)))) return rc;
     if (tb_get_encode()) {
@@ -441,6 +443,7 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
     // the records of this slot's previous image must have left the device before they are overwritten
     CK(cudaStreamWaitEvent(st, p->ev_d2h[slot], 0));
     CK(cudaMemsetAsync(p->d_cnts[slot], 0, p->cnt_ints * sizeof(int), st));
+    CK(cudaMemsetAsync(p->d_queue + slot * MAX_OCT, 0, MAX_OCT * sizeof(int), st));
     unsigned *mm = p->c_mm(slot);
     const float *img;
     int rc;
@@ -523,7 +526,8 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
         {
             ProfScope ps(p, "descriptors", o);
             k_describe<<<148 * 8, DESC_WARPS * 32, 0, st>>>(gp, p->kp, p->kp_scale, c + 1, c + 2, p->kpsize, octsize,
-                                                p->outs[slot], p->out_cap, p->c_nout(slot), c + 3);
+                                                p->outs[slot], p->out_cap, p->c_nout(slot), c + 3,
+                                                p->d_queue + slot * MAX_OCT + o);
             CKL();
             p->launches += 1;
         }

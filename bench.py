@@ -35,6 +35,9 @@ if ROOT not in sys.path:
 SIZE = 4096
 OCTAVES = 3
 N_IMAGES = 2  # distinct images cycled per rank (working set per image ~1.2 GB >> 126 MB L2)
+# dram__bytes_read.sum + dram__bytes_write.sum per octave-0 blur+DoG launch from the committed ncu --set full
+# capture (profiles/r01_blur_ncu_full.csv), averaged over the five tap counts; None until measured
+TRAFFIC_PER_LAUNCH = 148.6e6
 
 
 def _peaks():
@@ -182,7 +185,7 @@ def main():
     launches0 = plan.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    nkp, blur_ms, stage_ms = 0, 0.0, {}
+    nkp, blur_ms, blur0_ms, stage_ms = 0, 0.0, 0.0, {}
     ev0.record(stream)
     t0 = time.perf_counter()
     for i in range(args.steps):
@@ -192,6 +195,8 @@ def main():
             stage_ms[key] = stage_ms.get(key, 0.0) + ms
             if "blur" in name:
                 blur_ms += ms
+            if name == "blur + DoG octave 0":
+                blur0_ms += ms
     cur = torch.cuda.current_stream()
     cur.wait_stream(stream)  # the gather (if any) runs on torch's stream after the plan's stream
     ev1.record(cur)
@@ -237,7 +242,10 @@ def main():
 
     peak, peak_src = _peaks()
     bbytes = blur_bytes_per_step(plan) * args.steps
-    achieved = bbytes / (blur_ms / 1e3) / 1e9 if blur_ms > 0 else None
+    achieved_all = bbytes / (blur_ms / 1e3) / 1e9 if blur_ms > 0 else None
+    # dominant kernel: the five blur+DoG launches on the full-resolution planes (octave 0), 12*W*H bytes each
+    b0bytes = 5 * 12 * SIZE * SIZE
+    achieved = b0bytes * args.steps / (blur0_ms / 1e3) / 1e9 if blur0_ms > 0 else None
     line = {
         "metric": "keypoints/sec on 4096x4096 float32", "value": nkp / dev_s, "unit": "keypoints/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps,
@@ -252,11 +260,17 @@ def main():
                 "api": "SiftPlan.keypoints_many (2 images in flight)",
                 "ms_per_step_one_at_a_time": 1e3 * e2e_sync_s / args.steps},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "k_blur (Gaussian blur + DoG family, all launches of a step)",
+        "roofline": {"bound": "hbm",
+                     "kernel": "k_blur_tma: the 5 blur+DoG launches on the 4096x4096 planes (octave 0), 11..27 taps",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                     "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_step": bbytes // args.steps,
-                     "ms_per_step": blur_ms / args.steps},
+                     "traffic": TRAFFIC_PER_LAUNCH, "peak_source": peak_src + " (burst copy figure)",
+                     "algorithmic_bytes_per_launch": 12 * SIZE * SIZE, "launches_per_step": 5,
+                     "avg_launch_ms": blur0_ms / args.steps / 5,
+                     "all_blur_launches": {"note": "all %d blur launches of the step incl. first blur and octaves >= 1"
+                                                   % (1 + 5 * plan.octave_max),
+                                           "achieved": achieved_all, "frac": (achieved_all / peak) if achieved_all else None,
+                                           "algorithmic_bytes_per_step": bbytes // args.steps,
+                                           "ms_per_step": blur_ms / args.steps}},
         "stage_ms_per_step": {k: v / args.steps for k, v in sorted(stage_ms.items())},
         "wall_ms_per_step": 1e3 * wall / args.steps,
         "clocks": sampler.summary(),

@@ -9,9 +9,9 @@
 //      are read with conflict-free LDS.128 (row pitch = 4*odd words), every output is one
 //      sequential chain sum = fmaf(in, tap, sum), taps coming straight from the constant bank
 //      (kernel parameter), results go to a second shared buffer;
-//   3. vertical pass: each thread owns 2 adjacent columns x 16 rows (32 independent FMA chains),
-//      streaming the 16+2C rows it needs with LDS.64;
-//   4. epilogue from registers: G[s+1] (STG.64), DoG[s] = G[s] - G[s+1] with G[s] re-read from L2
+//   3. vertical pass: each thread owns 4 adjacent columns x 8 rows (32 independent FMA chains),
+//      streaming the 8+2C rows it needs with LDS.128;
+//   4. epilogue from registers: G[s+1] (STG.128), DoG[s] = G[s] - G[s+1] with G[s] re-read from L2
 //      (so the staged tile is dead after the row pass and the next tile's TMA load overlaps the column
 //      pass), and for s == 2 the decimated next-octave base G[3][::2, ::2].
 // CTAs are persistent (grid = min(tiles, 2 x 148)) and walk the tiles with a stride of gridDim.x.
@@ -64,8 +64,8 @@ k_blur_tma(const __grid_constant__ CUtensorMap tmap, BlurArgs a, Taps taps, int 
     constexpr int DELTA = tb_delta(C);     // tile column of global x is x - (x0 - C - DELTA)
     constexpr int WIN4 = tb_win4(C, TB_TW);
     static_assert(WIN4 * 4 >= WIN + DELTA, "window");
-    constexpr int RV = TB_R;               // rows per thread in the vertical pass
-    static_assert((TB_TW / 2) * (TB_TH / RV) == TB_THREADS, "column-pass mapping");
+    constexpr int RV = 8;                  // rows per thread in the vertical pass
+    static_assert(32 * (TB_TH / RV) == TB_THREADS, "column-pass mapping");
     constexpr int LW = C + DELTA;          // left halo width in tile columns
     extern __shared__ __align__(128) float smem[];
     float *tile = smem;                    // BH x BW
@@ -192,73 +192,101 @@ k_blur_tma(const __grid_constant__ CUtensorMap tmap, BlurArgs a, Taps taps, int 
                 ::"r"(smem_u32(tile)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(nx0 - C - DELTA), "r"(ny0 - C),
                 "r"(smem_u32(bar)) : "memory");
         }
-        // ---- vertical pass: thread -> column pair cp, rows [r0, r0 + 16) -------------------------------
-        const int cp = tid % (TB_TW / 2), r0 = (tid / (TB_TW / 2)) * RV;
-        const int gx = x0 + 2 * cp, gy0 = y0 + r0;
+        // ---- vertical pass: thread -> CV adjacent columns x RV rows (CV*RV independent FMA chains) -------
+        constexpr int CV = TB_TW / 32;  // 4 columns (LDS.128 / STG.128) on 128-wide tiles, 2 on 64-wide
+        const int cq = tid & 31, r0 = (tid >> 5) * RV;
+        const int gx = x0 + CV * cq, gy0 = y0 + r0;
         const bool full = x0 + TB_TW <= a.w && y0 + TB_TH <= a.h;
         // G[s] centre values for the DoG: requested from L2 now, consumed after the column pass, so that
-        // their latency hides behind the FMA chains (ncu: 20 % of the stall samples sat on these loads)
-        float2 ctr[RV];
+        // their latency hides behind the FMA chains
+        float ctr[RV][CV];
         if (MODE != TB_NORM && full) {
             const float *pC = a.in + (size_t)gy0 * a.in_pitch + gx;
 #pragma unroll
-            for (int o = 0; o < RV; o++) ctr[o] = __ldg(reinterpret_cast<const float2 *>(pC + o * a.in_pitch));
+            for (int o = 0; o < RV; o++) {
+                if (CV == 4) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(pC + o * a.in_pitch));
+                    ctr[o][0] = v.x; ctr[o][1] = v.y; ctr[o][CV - 2] = v.z; ctr[o][CV - 1] = v.w;
+                } else {
+                    const float2 v = __ldg(reinterpret_cast<const float2 *>(pC + o * a.in_pitch));
+                    ctr[o][0] = v.x; ctr[o][1] = v.y;
+                }
+            }
         }
-        float2 acc[RV];
+        float acc[RV][CV];
 #pragma unroll
-        for (int o = 0; o < RV; o++) acc[o] = make_float2(0.0f, 0.0f);
-        const float *col = hbuf + r0 * TB_HP + 2 * cp;
+        for (int o = 0; o < RV; o++)
+#pragma unroll
+            for (int c = 0; c < CV; c++) acc[o][c] = 0.0f;
+        const float *col = hbuf + r0 * TB_HP + CV * cq;
 #pragma unroll
         for (int k = 0; k < RV + 2 * C; k++) {
-            const float2 v = *reinterpret_cast<const float2 *>(col + k * TB_HP);
+            float v[CV];
+            if (CV == 4) {
+                const float4 t4 = *reinterpret_cast<const float4 *>(col + k * TB_HP);
+                v[0] = t4.x; v[1] = t4.y; v[CV - 2] = t4.z; v[CV - 1] = t4.w;
+            } else {
+                const float2 t2 = *reinterpret_cast<const float2 *>(col + k * TB_HP);
+                v[0] = t2.x; v[1] = t2.y;
+            }
 #pragma unroll
             for (int o = 0; o < RV; o++) {
                 const int j = k - o;  // tap index of row k for output o: ascending in k, as the reference
                 if (j >= 0 && j < N) {
-                    acc[o].x = __fmaf_rn(v.x, taps.f[N - 1 - j], acc[o].x);
-                    acc[o].y = __fmaf_rn(v.y, taps.f[N - 1 - j], acc[o].y);
+#pragma unroll
+                    for (int c = 0; c < CV; c++) acc[o][c] = __fmaf_rn(v[c], taps.f[N - 1 - j], acc[o][c]);
                 }
             }
         }
         // ---- epilogue ----------------------------------------------------------------------------------
-        if (full) {  // full tile: no per-element predicates
+        if (full) {  // full tile: no per-element predicates, vector stores
             float *pG = a.outG + (size_t)gy0 * a.out_pitch + gx;
-            if (MODE != TB_NORM) {
-                float *pD = a.outD + (size_t)gy0 * a.out_pitch + gx;
+            float *pD = (MODE != TB_NORM) ? a.outD + (size_t)gy0 * a.out_pitch + gx : nullptr;
 #pragma unroll
-                for (int o = 0; o < RV; o++) {
-                    *reinterpret_cast<float2 *>(pG + o * a.out_pitch) = acc[o];
-                    *reinterpret_cast<float2 *>(pD + o * a.out_pitch) =
-                        make_float2(ctr[o].x - acc[o].x, ctr[o].y - acc[o].y);
+            for (int o = 0; o < RV; o++) {
+                if (CV == 4) {
+                    *reinterpret_cast<float4 *>(pG + o * a.out_pitch) =
+                        make_float4(acc[o][0], acc[o][1], acc[o][CV - 2], acc[o][CV - 1]);
+                    if (MODE != TB_NORM)
+                        *reinterpret_cast<float4 *>(pD + o * a.out_pitch) =
+                            make_float4(ctr[o][0] - acc[o][0], ctr[o][1] - acc[o][1], ctr[o][CV - 2] - acc[o][CV - 2],
+                                        ctr[o][CV - 1] - acc[o][CV - 1]);
+                } else {
+                    *reinterpret_cast<float2 *>(pG + o * a.out_pitch) = make_float2(acc[o][0], acc[o][1]);
+                    if (MODE != TB_NORM)
+                        *reinterpret_cast<float2 *>(pD + o * a.out_pitch) =
+                            make_float2(ctr[o][0] - acc[o][0], ctr[o][1] - acc[o][1]);
                 }
-            } else {
-#pragma unroll
-                for (int o = 0; o < RV; o++) *reinterpret_cast<float2 *>(pG + o * a.out_pitch) = acc[o];
             }
             if (MODE == TB_DOG_HALF) {
-                float *pH = a.outHalf + (size_t)(gy0 >> 1) * a.half_pitch + (gx >> 1);
 #pragma unroll
-                for (int o = 0; o < RV; o += 2)
-                    if (((gy0 + o) >> 1) < a.half_h && (gx >> 1) < a.half_w) pH[(o >> 1) * a.half_pitch] = acc[o].x;
+                for (int o = 0; o < RV; o += 2) {
+                    const int hy = (gy0 + o) >> 1;
+                    if (hy < a.half_h) {
+#pragma unroll
+                        for (int c = 0; c < CV; c += 2)
+                            if (((gx + c) >> 1) < a.half_w)
+                                a.outHalf[(size_t)hy * a.half_pitch + ((gx + c) >> 1)] = acc[o][c];
+                    }
+                }
             }
-        } else if (gx < a.w) {
-            const bool pair = gx + 1 < a.w;
+        } else {
 #pragma unroll
             for (int o = 0; o < RV; o++) {
                 const int gy = gy0 + o;
                 if (gy < a.h) {
-                    const size_t p = (size_t)gy * a.out_pitch + gx;
-                    if (pair) *reinterpret_cast<float2 *>(a.outG + p) = acc[o];
-                    else a.outG[p] = acc[o].x;
-                    if (MODE != TB_NORM) {
-                        const float *ctr = a.in + (size_t)gy * a.in_pitch + gx;
-                        const float dx = ctr[0] - acc[o].x;
-                        if (pair) *reinterpret_cast<float2 *>(a.outD + p) = make_float2(dx, ctr[1] - acc[o].y);
-                        else a.outD[p] = dx;
-                    }
-                    if (MODE == TB_DOG_HALF) {
-                        if (!(o & 1) && (gy >> 1) < a.half_h && (gx >> 1) < a.half_w)
-                            a.outHalf[(size_t)(gy >> 1) * a.half_pitch + (gx >> 1)] = acc[o].x;
+#pragma unroll
+                    for (int c = 0; c < CV; c++) {
+                        const int x = gx + c;
+                        if (x < a.w) {
+                            const size_t p = (size_t)gy * a.out_pitch + x;
+                            a.outG[p] = acc[o][c];
+                            if (MODE != TB_NORM) a.outD[p] = a.in[(size_t)gy * a.in_pitch + x] - acc[o][c];
+                            if (MODE == TB_DOG_HALF) {
+                                if (!(o & 1) && !(c & 1) && (gy >> 1) < a.half_h && (x >> 1) < a.half_w)
+                                    a.outHalf[(size_t)(gy >> 1) * a.half_pitch + (x >> 1)] = acc[o][c];
+                            }
+                        }
                     }
                 }
             }

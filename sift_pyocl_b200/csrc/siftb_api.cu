@@ -346,7 +346,7 @@ static int launch_blur(cudaStream_t st, const float *in, int in_pitch, int w, in
     if (norm_mm && !outD && !outHalf) mode = TB_NORM;
     else if (!norm_mm && outD && outHalf) mode = TB_DOG_HALF;
     else if (!norm_mm && outD && !outHalf) mode = TB_DOG;
-    const bool out_ok = (out_pitch % 2 == 0) && (((uintptr_t)outG & 7) == 0) && (!outD || ((uintptr_t)outD & 7) == 0);
+    const bool out_ok = (out_pitch % 4 == 0) && (((uintptr_t)outG & 15) == 0) && (!outD || ((uintptr_t)outD & 15) == 0);
     if (!force_generic && mode >= 0 && tb_supported(ntaps, mode) && tb_source_ok(in, in_pitch) && out_ok &&
         tb_get_encode()) {
         CUtensorMap local;

@@ -77,6 +77,11 @@ k_blur_tma(const __grid_constant__ CUtensorMap tmap, BlurArgs a, Taps taps, int 
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // Programmatic dependent launch: this grid may become resident while the previous kernel of the stream
+    // (the blur that produces our input) is still draining; everything above overlaps its tail.  Nothing
+    // below may run before that kernel has completed and flushed its writes.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // let the next blur get resident early too
     __syncthreads();
     // persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA load of the next tile is issued
     // as soon as the row pass has consumed the staged tile, so it overlaps the column pass + epilogue.
@@ -360,8 +365,17 @@ static cudaError_t tb_launch_tw(cudaStream_t st, const CUtensorMap &map, const B
     const int ntx = (a.w + TW - 1) / TW, nty = (a.h + TB_TH - 1) / TB_TH;
     const int ntiles = ntx * nty;
     const int grid = ntiles < 2 * 148 ? ntiles : 2 * 148;  // persistent: 2 CTAs per SM, 148 SMs
-    k_blur_tma<C, MODE, TW><<<grid, 256, tb_smem_bytes(C, TW), st>>>(map, a, taps, ntx, ntiles);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = tb_smem_bytes(C, TW);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_blur_tma<C, MODE, TW>, map, a, taps, ntx, ntiles);
 }
 
 template <int C, int MODE>

@@ -49,35 +49,58 @@ def _peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled through NVML every few ms during the timed regions
+    (nvidia-smi is the fallback; it only manages a few samples per second)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag, self.max_mhz = index, [], False, None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def run(self):
+        n = self.nvml
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
+                if n is not None:
+                    mhz = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                    r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                    self.samples.append((mhz, bool(r & n.nvmlClocksEventReasonHwSlowdown),
+                                         bool(r & n.nvmlClocksEventReasonHwThermalSlowdown),
+                                         bool(r & n.nvmlClocksEventReasonSwThermalSlowdown),
+                                         bool(r & n.nvmlClocksEventReasonSwPowerCap)))
+                    time.sleep(0.004)
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                         timeout=5).stdout
+                    f = [x.strip() for x in out.strip().split(",")]
+                    if len(f) >= 6 and f[0].isdigit():
+                        self.max_mhz = int(f[1]) if f[1].isdigit() else self.max_mhz
+                        self.samples.append((int(f[0]),) + tuple(x.lower().startswith("active") for x in f[2:6]))
+                    time.sleep(0.05)
             except Exception:
-                pass
-            time.sleep(0.1)
+                time.sleep(0.05)
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"]}
+        sm = sorted(s[0] for s in self.samples)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.samples)}
+        reasons = [nm for i, nm in enumerate(names) if any(s[1 + i] for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(self.samples), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def _workload_name():
@@ -202,7 +225,6 @@ def main():
     ev1.record(cur)
     barrier()
     wall = time.perf_counter() - t0
-    sampler.stop_flag = True
     dev_s = ev0.elapsed_time(ev1) / 1e3
     launches = plan.launches - launches0
     plan.set_profile(False)
@@ -227,6 +249,7 @@ def main():
         plan.keypoints(host_imgs[i % N_IMAGES])
     barrier()
     e2e_sync_s = time.perf_counter() - t0
+    sampler.stop_flag = True
 
     if world > 1:
         t = torch.tensor([dev_s, e2e_s, float(nkp), float(e2e_kp), float(launches)], dtype=torch.float64, device="cuda")

@@ -50,6 +50,31 @@ enum { TB_DOG = 0, TB_DOG_HALF = 1, TB_NORM = 2 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One row-pass task: R consecutive outputs of one tile row.  src points at the (16-byte aligned) tile column of
+// the first output minus C + DELTA... i.e. input i of output o is src[DELTA + o + i]; dst receives the R sums.
+template <int C, int R, int DELTA>
+__device__ __forceinline__ void tb_row_task(const float *__restrict__ src, float *__restrict__ dst, const Taps &taps) {
+    constexpr int N = 2 * C + 1;
+    constexpr int W4 = (R + 2 * C + DELTA + 3) / 4;
+    float in[W4 * 4];
+#pragma unroll
+    for (int i = 0; i < W4; i++) {
+        const float4 v = reinterpret_cast<const float4 *>(src)[i];
+        in[4 * i] = v.x; in[4 * i + 1] = v.y; in[4 * i + 2] = v.z; in[4 * i + 3] = v.w;
+    }
+    float acc[R];
+#pragma unroll
+    for (int o = 0; o < R; o++) acc[o] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+#pragma unroll
+        for (int o = 0; o < R; o++) acc[o] = __fmaf_rn(in[DELTA + o + j], taps.f[N - 1 - j], acc[o]);
+    }
+#pragma unroll
+    for (int i = 0; i < R / 4; i++)
+        reinterpret_cast<float4 *>(dst)[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+}
+
 template <int C, int MODE, int TB_TW>
 __global__ void __launch_bounds__(256, 2)
 k_blur_tma(const __grid_constant__ CUtensorMap tmap, BlurArgs a, Taps taps, int ntx, int ntiles) {
@@ -161,28 +186,22 @@ k_blur_tma(const __grid_constant__ CUtensorMap tmap, BlurArgs a, Taps taps, int 
             }
             __syncthreads();
         }
-        // ---- horizontal pass: task q -> (row = q % BH, segment = q / BH) ------------------------------
-        for (int q = tid; q < BH * NSEG; q += TB_THREADS) {
-            const int seg = q / BH, row = q - seg * BH;
-            const float4 *src = reinterpret_cast<const float4 *>(tile + row * BW + seg * RH);
-            float in[WIN4 * 4];
-#pragma unroll
-            for (int i = 0; i < WIN4; i++) {
-                const float4 v = src[i];
-                in[4 * i] = v.x; in[4 * i + 1] = v.y; in[4 * i + 2] = v.z; in[4 * i + 3] = v.w;
+        // ---- horizontal pass --------------------------------------------------------------------------
+        // Tasks of RH outputs fill whole rounds of the 256 threads (rows [0, ROWS_A)); the remaining rows are
+        // cut into tasks of RH/2 outputs so that the last round is not mostly idle (BH*NSEG is not a multiple
+        // of 256 for any of the tap counts).
+        constexpr int ROWS_A = (BH * NSEG / TB_THREADS) * (TB_THREADS / NSEG);
+        constexpr int ROWS_B = BH - ROWS_A;
+        for (int q = tid; q < ROWS_A * NSEG; q += TB_THREADS) {
+            const int seg = q / ROWS_A, row = q - seg * ROWS_A;
+            tb_row_task<C, RH, DELTA>(tile + row * BW + seg * RH, hbuf + row * TB_HP + seg * RH, taps);
+        }
+        if (ROWS_B > 0) {
+            constexpr int RB = RH / 2;
+            for (int q = tid; q < ROWS_B * NSEG * 2; q += TB_THREADS) {
+                const int seg = q / ROWS_B, row = ROWS_A + (q - seg * ROWS_B);
+                tb_row_task<C, RB, DELTA>(tile + row * BW + seg * RB, hbuf + row * TB_HP + seg * RB, taps);
             }
-            float acc[RH];
-#pragma unroll
-            for (int o = 0; o < RH; o++) acc[o] = 0.0f;
-#pragma unroll
-            for (int j = 0; j < N; j++) {
-#pragma unroll
-                for (int o = 0; o < RH; o++) acc[o] = __fmaf_rn(in[DELTA + o + j], taps.f[N - 1 - j], acc[o]);
-            }
-            float4 *dst = reinterpret_cast<float4 *>(hbuf + row * TB_HP + seg * RH);
-#pragma unroll
-            for (int i = 0; i < RH / 4; i++)
-                dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
         }
         __syncthreads();
         // the staged tile is dead (the DoG centre is re-read from global/L2): prefetch the next one

@@ -186,22 +186,11 @@ k_blur_tma(const __grid_constant__ CUtensorMap tmap, BlurArgs a, Taps taps, int 
             }
             __syncthreads();
         }
-        // ---- horizontal pass --------------------------------------------------------------------------
-        // Tasks of RH outputs fill whole rounds of the 256 threads (rows [0, ROWS_A)); the remaining rows are
-        // cut into tasks of RH/2 outputs so that the last round is not mostly idle (BH*NSEG is not a multiple
-        // of 256 for any of the tap counts).
-        constexpr int ROWS_A = (BH * NSEG / TB_THREADS) * (TB_THREADS / NSEG);
-        constexpr int ROWS_B = BH - ROWS_A;
-        for (int q = tid; q < ROWS_A * NSEG; q += TB_THREADS) {
-            const int seg = q / ROWS_A, row = q - seg * ROWS_A;
+        // ---- horizontal pass: task q -> (row = q % BH, segment = q / BH) ------------------------------
+        // (splitting the last, partly filled round into half-size tasks was measured slower: 53.0 vs 51.8 us)
+        for (int q = tid; q < BH * NSEG; q += TB_THREADS) {
+            const int seg = q / BH, row = q - seg * BH;
             tb_row_task<C, RH, DELTA>(tile + row * BW + seg * RH, hbuf + row * TB_HP + seg * RH, taps);
-        }
-        if (ROWS_B > 0) {
-            constexpr int RB = RH / 2;
-            for (int q = tid; q < ROWS_B * NSEG * 2; q += TB_THREADS) {
-                const int seg = q / ROWS_B, row = ROWS_A + (q - seg * ROWS_B);
-                tb_row_task<C, RB, DELTA>(tile + row * BW + seg * RB, hbuf + row * TB_HP + seg * RB, taps);
-            }
         }
         __syncthreads();
         // the staged tile is dead (the DoG centre is re-read from global/L2): prefetch the next one

@@ -32,9 +32,21 @@ struct DescRows {          // per-octet table of the window rows: only the j-int
     short pfx[DESC_MAXROWS + 1];   // exclusive prefix sum of the number of 8-sample passes per row
 };
 
+// Per-sample record staged in shared memory by the evaluating lane, laid out BY RESULT PARITY so that the lane of
+// parity class (pr, pc, po) picks its operands with fixed offsets: the cell with row parity pr / column parity
+// pc, the row weight of the row with parity pr, the column factor of the column with parity pc, the orientation
+// bin with parity po and its factor.
+struct DescRec {
+    uint32_t cells;   // byte (pr*2+pc): cell index r*4+c (0..15) or 0xff when that neighbour is outside the 4x4 grid
+    uint32_t obins;   // byte po: orientation bin of parity po; byte 2: 1 when both terms go to the same bin
+    float rwp[2];     // mag*(1-rfrac) / mag*rfrac, indexed by the parity of the row they go to
+    float cfp[2];     // (1-cfrac) / cfrac, indexed by the parity of the column
+    float ow[2];      // (1-ofrac) / ofrac, indexed by the parity of the orientation bin (in order when byte 2 set)
+};
+
 // One warp, 4 keypoints (octet g handles kp[g] when act is true for that octet).
 // hist: this octet's 128 floats in shared memory, index (r*4+c)*8 + o (the descriptor order).
-__device__ __forceinline__ void describe_octets(float *hist, DescRows &rows, bool act, const float4 k,
+__device__ __forceinline__ void describe_octets(float *hist, DescRows &rows, DescRec *recs, bool act, const float4 k,
                                                 const float *__restrict__ grad, const float *__restrict__ orim,
                                                 int pitch, int grad_width, int grad_height, int octsize,
                                                 uint8_t *out128) {
@@ -100,8 +112,7 @@ __device__ __forceinline__ void describe_octets(float *hist, DescRows &rows, boo
     int rcur = 0;
     for (int p = 0; p < passes_max; p++) {
         bool valid = false;
-        float rw0 = 0.f, rw1 = 0.f, cfrac = 0.f, ofrac = 0.f;
-        int packed = 0;
+        DescRec rec;
         int i = 0, j = 0;
         bool in_window = false;
         if (p < my_passes) {
@@ -132,48 +143,66 @@ __device__ __forceinline__ void describe_octets(float *hist, DescRows &rows, boo
                 const int ri = (int)((rx >= 0.0f) ? rx : rx - 1.0f);
                 const int ci = (int)((cx >= 0.0f) ? cx : cx - 1.0f);
                 const int oi = (int)((oval >= 0.0f) ? oval : oval - 1.0f);
-                const float rfrac = rx - (float)ri;
-                cfrac = cx - (float)ci;
-                ofrac = oval - (float)oi;
+                const float rfrac = rx - (float)ri, cfrac = cx - (float)ci, ofrac = oval - (float)oi;
                 if ((ri >= -1 && ri < 4 && oi >= 0 && oi <= 8 && rfrac >= 0.0f && rfrac <= 1.0f)) {
                     valid = true;
-                    rw0 = mag * (1.0f - rfrac);  // rweight for r == 0
-                    rw1 = mag * rfrac;           // rweight for r == 1
                     const int o0 = (oi >= 8) ? 0 : oi;  // oindex = oi + orr; if (oindex >= 8) oindex = 0
                     const int o1 = (oi + 1 >= 8) ? 0 : oi + 1;
-                    packed = (ri + 1) | ((ci + 1) << 8) | (o0 << 16) | (o1 << 24);
-                }
-            }
-        }
-        // commit the valid samples of every octet in lane (= sample) order
-        unsigned m = __ballot_sync(0xffffffffu, valid) & omask;
-        while (__any_sync(0xffffffffu, m != 0)) {
-            const bool have = m != 0;
-            const int src = have ? (__ffs(m) - 1) : lane;  // lane of my octet holding the sample
-            m &= m - 1;
-            const int u = __shfl_sync(0xffffffffu, packed, src);
-            const float s_rw0 = __shfl_sync(0xffffffffu, rw0, src);
-            const float s_rw1 = __shfl_sync(0xffffffffu, rw1, src);
-            const float s_cf = __shfl_sync(0xffffffffu, cfrac, src);
-            const float s_of = __shfl_sync(0xffffffffu, ofrac, src);
-            if (have) {
-                const int ri = (u & 0xff) - 1, ci = ((u >> 8) & 0xff) - 1, o0 = (u >> 16) & 0xff, o1 = (u >> 24) & 0xff;
-                const int dr = (pr ^ ri) & 1, dc = (pc ^ ci) & 1;  // the neighbour of my parity
-                const int rr = ri + dr, cc = ci + dc;
-                if (rr >= 0 && rr < 4 && cc >= 0 && cc < 4) {
-                    const float rweight = dr ? s_rw1 : s_rw0;
-                    const float cweight = rweight * (dc ? s_cf : 1.0f - s_cf);
-                    float *hb = hist + (rr * 4 + cc) * 8;
+                    const int rp = ri & 1, cpp = ci & 1;  // parity of row ri / column ci (ri = -1 -> 1)
+                    const float rw0 = mag * (1.0f - rfrac);  // rweight for r == 0 -> row ri
+                    const float rw1 = mag * rfrac;           // rweight for r == 1 -> row ri + 1
+                    const float cf0 = 1.0f - cfrac;
+                    rec.rwp[0] = rp ? rw1 : rw0;
+                    rec.rwp[1] = rp ? rw0 : rw1;
+                    rec.cfp[0] = cpp ? cfrac : cf0;
+                    rec.cfp[1] = cpp ? cf0 : cfrac;
+                    uint32_t cells = 0;
+#pragma unroll
+                    for (int d = 0; d < 4; d++) {
+                        const int rr = ri + (d >> 1), cc = ci + (d & 1);
+                        const uint32_t cell = (rr >= 0 && rr < 4 && cc >= 0 && cc < 4) ? (uint32_t)(rr * 4 + cc) : 0xffu;
+                        cells |= cell << (8 * (((rr & 1) << 1) | (cc & 1)));
+                    }
+                    rec.cells = cells;
                     if (o0 != o1) {
-                        const bool first = (o0 & 1) == po;  // which of the two orientation terms is mine
-                        hb[first ? o0 : o1] += cweight * (first ? 1.0f - s_of : s_of);
-                    } else if (po == (o0 & 1)) {  // ori == 2*pi: both terms land in the same bin, in order
-                        hb[o0] += cweight * (1.0f - s_of);
-                        hb[o0] += cweight * s_of;
+                        const float of0 = 1.0f - ofrac;
+                        const bool odd = o0 & 1;  // o0 and o1 have different parities
+                        rec.ow[0] = odd ? ofrac : of0;
+                        rec.ow[1] = odd ? of0 : ofrac;
+                        rec.obins = odd ? ((uint32_t)o1 | ((uint32_t)o0 << 8)) : ((uint32_t)o0 | ((uint32_t)o1 << 8));
+                    } else {  // ori == 2*pi exactly: both terms go to bin o0, first (1-ofrac) then ofrac
+                        rec.ow[0] = 1.0f - ofrac;
+                        rec.ow[1] = ofrac;
+                        rec.obins = (uint32_t)o0 | ((uint32_t)o0 << 8) | (1u << 16);
                     }
                 }
             }
         }
+        // stage the valid samples of each octet, compacted in lane (= sample) order
+        const unsigned m = __ballot_sync(0xffffffffu, valid) & omask;
+        if (valid) recs[__popc(m & lanemask_lt())] = rec;
+        const int cnt = __popc(m);
+        const int cnt_max = __reduce_max_sync(0xffffffffu, cnt);
+        __syncwarp();
+        // commit them one at a time: lane (pr, pc, po) adds the one contribution of its parity class
+        for (int sidx = 0; sidx < cnt_max; sidx++) {
+            if (sidx < cnt) {
+                const DescRec &r = recs[sidx];
+                const uint32_t cell = (r.cells >> (8 * ((pr << 1) | pc))) & 0xffu;
+                if (cell != 0xffu) {
+                    const float cweight = r.rwp[pr] * r.cfp[pc];
+                    const uint32_t ob = r.obins;
+                    float *hb = hist + cell * 8;
+                    if (!(ob >> 16)) {
+                        hb[(ob >> (8 * po)) & 0xffu] += cweight * r.ow[po];
+                    } else if (po == (int)(ob & 1u)) {
+                        hb[ob & 0xffu] += cweight * r.ow[0];
+                        hb[ob & 0xffu] += cweight * r.ow[1];
+                    }
+                }
+            }
+        }
+        __syncwarp();
     }
     __syncwarp();
     // finish, keypoints_cpu.cl:127-160: each lane of the octet owns 16 consecutive descriptor entries
@@ -236,6 +265,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 8) k_describe(GradPlanes G, c
                                                                int *__restrict__ queue) {
     __shared__ float s_hist[DESC_WARPS * 4][DESC_HSTRIDE];
     __shared__ DescRows s_rows[DESC_WARPS * 4];
+    __shared__ DescRec s_recs[DESC_WARPS * 4][8];
     const int lane = threadIdx.x & 31, l8 = lane & 7, obase = lane & 24;
     float *hist = s_hist[threadIdx.x >> 3];
     const int n = min(min(*n_base_p, cap) + *n_extra_p, cap);
@@ -265,8 +295,8 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 8) k_describe(GradPlanes G, c
         if (slot >= out_cap) act = false;
         KpRecord *o = out + (act ? slot : 0);
         if (act && l8 == 0) { o->x = k.x; o->y = k.y; o->scale = k.z; o->angle = k.w; }
-        describe_octets(hist, s_rows[threadIdx.x >> 3], act, k, G.grad[sc - 1], G.ori[sc - 1], G.pitch, G.w, G.h, octsize,
-                        o->desc);
+        describe_octets(hist, s_rows[threadIdx.x >> 3], s_recs[threadIdx.x >> 3], act, k, G.grad[sc - 1], G.ori[sc - 1],
+                        G.pitch, G.w, G.h, octsize, o->desc);
     }
 }
 
@@ -277,6 +307,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 8) k_describe_rows(const floa
                                                                     int octsize, uint8_t *__restrict__ desc) {
     __shared__ float s_hist[DESC_WARPS * 4][DESC_HSTRIDE];
     __shared__ DescRows s_rows[DESC_WARPS * 4];
+    __shared__ DescRec s_recs[DESC_WARPS * 4][8];
     float *hist = s_hist[threadIdx.x >> 3];
     const int noct = (gridDim.x * blockDim.x) >> 3;
     const int rounds = (n + noct - 1) / noct;
@@ -288,7 +319,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 8) k_describe_rows(const floa
             k = kp[gid0];
             act = k.y >= 0.0f;
         }
-        describe_octets(hist, s_rows[threadIdx.x >> 3], act, k, grad, ori, pitch, w, h, octsize,
+        describe_octets(hist, s_rows[threadIdx.x >> 3], s_recs[threadIdx.x >> 3], act, k, grad, ori, pitch, w, h, octsize,
                         desc + 128L * (act ? gid0 : 0));
     }
 }

@@ -151,6 +151,11 @@ SIFTB_API int siftb_match_l1(const siftb_kp *kp1, int n1, const siftb_kp *kp2, i
 SIFTB_API int siftb_transform(const float *image, int height, int width, float *out, int out_height, int out_width,
                     const float matrix[4], const float offset[2], float fill, int mode, int device);
 
+/* transform.cl:116 transform_RGB: interleaved uint8 [h][w][3] in and out (alignment.py:329-331) */
+SIFTB_API int siftb_transform_rgb(const uint8_t *image, int height, int width, uint8_t *out, int out_height,
+                                  int out_width, const float matrix[4], const float offset[2], float fill, int mode,
+                                  int device);
+
 #ifdef __cplusplus
 }
 #endif

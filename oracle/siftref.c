@@ -821,3 +821,44 @@ API void siftref_transform(const float *image, float *output, const float *matri
         }
     }
 }
+
+/* transform.cl:116-203  transform_RGB: interleaved uint8, one colour channel at a time */
+API void siftref_transform_rgb(const uint8_t *image, uint8_t *output, const float *matrix4, const float *offset2,
+                               int image_width, int image_height, int output_width, int output_height, float fill,
+                               int mode) {
+#pragma omp parallel for schedule(static)
+    for (int gid1 = 0; gid1 < output_height; gid1++) {
+        for (int gid0 = 0; gid0 < output_width; gid0++) {
+            for (int color = 0; color < 3; color++) {
+                int x = gid0, y = gid1;
+                float tx, ty;
+                { float a = matrix4[2] * (float)y, b = matrix4[3] * (float)x; tx = a + b; }
+                { float a = matrix4[0] * (float)y, b = matrix4[1] * (float)x; ty = a + b; }
+                tx += offset2[1];
+                ty += offset2[0];
+                int tx_next = ((int)tx) + 1, tx_prev = (int)tx, ty_next = ((int)ty) + 1, ty_prev = (int)ty;
+                float interp = fill;
+                if (0.0f <= tx && tx < image_width && 0.0f <= ty && ty < image_height) {
+                    if (mode == 1) {
+                        int xo = tx_next >= image_width, yo = ty_next >= image_height;
+                        float image_p = image[3 * ((long)ty_prev * image_width + tx_prev) + color];
+                        float image_x = xo ? fill : image[3 * ((long)ty_prev * image_width + tx_next) + color];
+                        float image_y = yo ? fill : image[3 * ((long)ty_next * image_width + tx_prev) + color];
+                        float image_n = (xo || yo) ? fill : image[3 * ((long)ty_next * image_width + tx_next) + color];
+                        float wxn = (float)(tx_next - tx), wxp = (float)(tx - tx_prev);
+                        float wyn = (float)(ty_next - ty), wyp = (float)(ty - ty_prev);
+                        float interp1, interp2;
+                        { float a = wxn * image_p, b = wxp * image_x; interp1 = a + b; }
+                        { float a = wxn * image_y, b = wxp * image_n; interp2 = a + b; }
+                        { float a = wyn * interp1, b = wyp * interp2; interp = a + b; }
+                    } else {
+                        interp = image[3 * ((long)((int)ty) * image_width + ((int)tx)) + color];
+                    }
+                }
+                if (tx >= image_width + -0.5f) interp = fill;
+                if (ty >= image_height + -0.5f) interp = fill;
+                output[3 * ((long)gid1 * output_width + gid0) + color] = (uint8_t)(int)interp;
+            }
+        }
+    }
+}

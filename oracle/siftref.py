@@ -271,3 +271,15 @@ def multiscale_image(n, seed=1234, shape=None):
         z = r if k == 1 else zoom(r, k, order=1)
         img += np.float32(np.sqrt(k)) * z[:h, :w].astype(np.float32)
     return img
+
+
+def transform_rgb(img, matrix, offset, fill, out_shape=None, mode=1):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape[:2]
+    oh, ow = (h, w) if out_shape is None else out_shape
+    out = np.empty((oh, ow, 3), np.uint8)
+    m = _f32(np.asarray(matrix).reshape(4))
+    o = _f32(np.asarray(offset).reshape(2))
+    lib().siftref_transform_rgb(img.ctypes.data_as(_c_u8_p), out.ctypes.data_as(_c_u8_p), _fp(m), _fp(o), w, h, ow, oh,
+                                ctypes.c_float(fill), mode)
+    return out

@@ -69,6 +69,8 @@ SIGNATURES = {
     "siftb_match_l1": (c_int, [c_void_p, c_int, c_void_p, c_int, c_float, c_int, c_int, c_void_p, c_int, c_int_p]),
     "siftb_transform": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_float_p, c_float_p, c_float,
                                 c_int, c_int]),
+    "siftb_transform_rgb": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_float_p, c_float_p, c_float,
+                                    c_int, c_int]),
 }
 
 _lib = None

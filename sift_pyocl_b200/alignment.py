@@ -15,13 +15,23 @@ logger = logging.getLogger("sift.alignment")
 
 
 def transform(image, matrix, offset, fill, out_shape=None, mode=1, device=0):
-    """Inverse-mapped affine warp, bilinear (mode 1) or nearest (mode 0): transform.cl:22-108."""
+    """Inverse-mapped affine warp, bilinear (mode 1) or nearest (mode 0): transform.cl:22-108; an (H, W, 3)
+    uint8 image goes through transform_RGB (transform.cl:116-203)."""
+    m = numpy.ascontiguousarray(numpy.asarray(matrix, numpy.float32).reshape(4))
+    o = numpy.ascontiguousarray(numpy.asarray(offset, numpy.float32).reshape(2))
+    if numpy.ndim(image) == 3:
+        image = numpy.ascontiguousarray(image, numpy.uint8)
+        h, w = image.shape[:2]
+        oh, ow = (h, w) if out_shape is None else out_shape
+        out = numpy.empty((oh, ow, 3), numpy.uint8)
+        _lib.check(_lib.load().siftb_transform_rgb(_lib.ptr(image), h, w, _lib.ptr(out), oh, ow,
+                                                   m.ctypes.data_as(_lib.c_float_p), o.ctypes.data_as(_lib.c_float_p),
+                                                   ctypes.c_float(fill), int(mode), int(device)))
+        return out
     image = numpy.ascontiguousarray(image, numpy.float32)
     h, w = image.shape
     oh, ow = (h, w) if out_shape is None else out_shape
     out = numpy.empty((oh, ow), numpy.float32)
-    m = numpy.ascontiguousarray(numpy.asarray(matrix, numpy.float32).reshape(4))
-    o = numpy.ascontiguousarray(numpy.asarray(offset, numpy.float32).reshape(2))
     _lib.check(_lib.load().siftb_transform(_lib.ptr(image), h, w, _lib.ptr(out), oh, ow,
                                            m.ctypes.data_as(_lib.c_float_p), o.ctypes.data_as(_lib.c_float_p),
                                            ctypes.c_float(fill), int(mode), int(device)))
@@ -43,7 +53,6 @@ class LinearAlign(object):
         if len(self.shape) == 3:
             self.RGB = True
             self.shape = self.shape[:2]
-            raise NotImplementedError("RGB alignment (transform.cl:116 transform_RGB) is not built yet")
         elif len(self.shape) == 2:
             self.RGB = False
         else:
@@ -83,7 +92,10 @@ class LinearAlign(object):
         :return: aligned image, or all information, or None when no keypoint matches
         """
         logger.debug("ref_keypoints: %s" % self.ref_kp.size)
-        data = numpy.ascontiguousarray(img, numpy.float32)
+        if self.RGB:
+            data = numpy.ascontiguousarray(img, numpy.uint8)  # alignment.py:237-238
+        else:
+            data = numpy.ascontiguousarray(img, numpy.float32)
         with self.sem:
             kp = self.sift.keypoints(data)
             logger.debug("mod image keypoints: %s" % kp.size)
@@ -140,7 +152,7 @@ class LinearAlign(object):
                 matrix = numpy.ascontiguousarray(self.relative_transfo[:2, :2], dtype=numpy.float32)
                 offset = numpy.ascontiguousarray(self.relative_transfo[:2, 2], dtype=numpy.float32)
             fill = self.sift.buffers["min"].get()[0]  # alignment.py:345
-            result = transform(data, matrix, offset, fill, self.outshape, 1, self.sift.device)
+            result = transform(data, matrix, offset, float(fill), self.outshape, 1, self.sift.device)
         if return_all:
             corr = numpy.dot(matrix, numpy.vstack((matching[:, 0].y, matching[:, 0].x))).T + offset.T - \
                 numpy.vstack((matching[:, 1].y, matching[:, 1].x)).T

@@ -1,4 +1,4 @@
-// k_match.cuh -- brute-force L1 matcher with ratio test, and the affine warp.
+// k_match.cuh -- brute-force L1 matcher with ratio test, and the affine warps (grey and RGB).
 //
 // k_match_l1 replaces matching_gpu.cl:52 / matching_cpu.cl:57 `matching` plus memset.cl
 // memset_kp/memset_int (match.py:244-255).  k_transform replaces transform.cl:22 `transform`
@@ -93,4 +93,40 @@ __global__ void __launch_bounds__(256) k_transform(const float *__restrict__ ima
     if (tx >= (float)image_width + -0.5f) interp = fill;
     if (ty >= (float)image_height + -0.5f) interp = fill;
     output[(long)y * output_width + x] = interp;
+}
+
+// transform.cl:116-203 transform_RGB: same mapping per colour channel of an interleaved uint8 image.
+// grid (ceil(3*out_w/256), out_h): one thread per output byte.
+__global__ void __launch_bounds__(256) k_transform_rgb(const uint8_t *__restrict__ image, uint8_t *__restrict__ output,
+                                                        float m0, float m1, float m2, float m3, float off0, float off1,
+                                                        int image_width, int image_height, int output_width,
+                                                        int output_height, float fill, int mode) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (i >= 3 * output_width || y >= output_height) return;
+    const int x = i / 3, color = i - 3 * x;
+    float tx = m2 * (float)y + m3 * (float)x;
+    float ty = m0 * (float)y + m1 * (float)x;
+    tx += off1;
+    ty += off0;
+    const int tx_next = ((int)tx) + 1, tx_prev = (int)tx, ty_next = ((int)ty) + 1, ty_prev = (int)ty;
+    float interp = fill;
+    if (0.0f <= tx && tx < (float)image_width && 0.0f <= ty && ty < (float)image_height) {
+        if (mode == 1) {
+            const bool xo = tx_next >= image_width, yo = ty_next >= image_height;
+            const float image_p = (float)image[3 * ((long)ty_prev * image_width + tx_prev) + color];
+            const float image_x = xo ? fill : (float)image[3 * ((long)ty_prev * image_width + tx_next) + color];
+            const float image_y = yo ? fill : (float)image[3 * ((long)ty_next * image_width + tx_prev) + color];
+            const float image_n = (xo || yo) ? fill : (float)image[3 * ((long)ty_next * image_width + tx_next) + color];
+            const float wxn = (float)tx_next - tx, wxp = tx - (float)tx_prev;
+            const float wyn = (float)ty_next - ty, wyp = ty - (float)ty_prev;
+            const float interp1 = wxn * image_p + wxp * image_x;
+            const float interp2 = wxn * image_y + wxp * image_n;
+            interp = wyn * interp1 + wyp * interp2;
+        } else {
+            interp = (float)image[3 * ((long)((int)ty) * image_width + ((int)tx)) + color];
+        }
+    }
+    if (tx >= (float)image_width + -0.5f) interp = fill;
+    if (ty >= (float)image_height + -0.5f) interp = fill;
+    output[3 * ((long)y * output_width + x) + color] = (uint8_t)(int)interp;  // implicit float -> uchar store
 }

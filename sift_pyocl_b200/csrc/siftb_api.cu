@@ -902,3 +902,20 @@ extern "C" int siftb_transform(const float *image, int height, int width, float 
     CK(cudaMemcpy(out, O.p, (size_t)out_height * out_width * 4, cudaMemcpyDeviceToHost));
     return 0;
 }
+
+extern "C" int siftb_transform_rgb(const uint8_t *image, int height, int width, uint8_t *out, int out_height,
+                                   int out_width, const float matrix[4], const float offset[2], float fill, int mode,
+                                   int device) {
+    if (!image || !out || !matrix || !offset || height <= 0 || width <= 0 || out_height <= 0 || out_width <= 0)
+        return fail(SIFTB_EINVAL, "bad argument");
+    CK(cudaSetDevice(device));
+    DevBuf I, O;
+    DALLOC(I, (size_t)height * width * 3); DALLOC(O, (size_t)out_height * out_width * 3);
+    CK(cudaMemcpy(I.p, image, (size_t)height * width * 3, cudaMemcpyHostToDevice));
+    dim3 grid((3 * out_width + 255) / 256, out_height);
+    k_transform_rgb<<<grid, 256>>>(I.as<uint8_t>(), O.as<uint8_t>(), matrix[0], matrix[1], matrix[2], matrix[3],
+                                   offset[0], offset[1], width, height, out_width, out_height, fill, mode);
+    CKL();
+    CK(cudaMemcpy(out, O.p, (size_t)out_height * out_width * 3, cudaMemcpyDeviceToHost));
+    return 0;
+}

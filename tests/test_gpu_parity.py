@@ -397,6 +397,30 @@ def test_transform(sift, oracle):  # test_transform.py (no asserts in the refere
             assert np.array_equal(transform(img, M, off, -1.0, shape, mode), oracle.transform(img, M, off, -1.0, shape, mode))
 
 
+def test_transform_rgb_and_rgb_align(sift, oracle):  # transform.cl:116 transform_RGB, alignment.py:329-331
+    from scipy.ndimage import affine_transform
+    from sift_pyocl_b200.alignment import transform
+    rgb = np.random.default_rng(17).integers(0, 256, (97, 131, 3), dtype=np.uint8)
+    M = np.array([[1.1, -0.1], [0.05, 0.9]], np.float32)
+    off = np.array([7.0, 5.0], np.float32)
+    for mode in (0, 1):
+        for shape in (None, (117, 151)):
+            assert np.array_equal(transform(rgb, M, off, 3.0, shape, mode), oracle.transform_rgb(rgb, M, off, 3.0, shape, mode))
+    g = _ms(384, 33)
+    g = (g / g.max() * 255)
+    ref = np.stack([g, 0.8 * g, 0.6 * g + 40], axis=-1).astype(np.uint8)
+    Ma, offa = np.array([[1.01, -0.02], [0.02, 0.99]]), np.array([3.0, -2.0])
+    moved = np.stack([affine_transform(ref[..., c].astype(np.float32), Ma, offset=offa, order=1, mode="reflect")
+                      for c in range(3)], axis=-1).astype(np.uint8)
+    la = sift.LinearAlign(ref)
+    out = la.align(moved, return_all=True)
+    assert out is not None and out["result"].shape == ref.shape and out["result"].dtype == np.uint8
+    core = (slice(48, -48), slice(48, -48))
+    before = abs(moved.astype(int) - ref.astype(int))[core].mean()
+    after = abs(out["result"].astype(int) - ref.astype(int))[core].mean()
+    assert after < 0.5 * before
+
+
 def test_linear_align(sift, oracle):  # test_align.py:66-99 (prints only in the reference)
     from scipy.ndimage import affine_transform
     ref = _ms(512, 31)

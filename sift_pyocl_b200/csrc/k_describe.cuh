@@ -254,15 +254,28 @@ __device__ __forceinline__ void describe_octets(float *hist, DescRows &rows, Des
     __syncwarp();
 }
 
-// Pipeline form: octets grid-stride over the keypoints of the octave; rows with NaN are dropped
-// (plan.py:546-550) and survivors appended to the final record array (plan.py:555-565).
-__global__ void __launch_bounds__(DESC_WARPS * 32, 8) k_describe(GradPlanes G, const float4 *__restrict__ kp,
-                                                               const int *__restrict__ kp_scale,
+// prefix of the per-octave record counts -> first record slot of every octave, and the total
+__global__ void k_octave_offsets(const int *__restrict__ oct_valid, int n_oct, int *__restrict__ oct_offset,
+                                 int *__restrict__ n_out, int *__restrict__ n_out_oct /* stride 4 */) {
+    int acc = 0;
+    for (int o = 0; o < n_oct; o++) {
+        oct_offset[o] = acc;
+        acc += oct_valid[o];
+        n_out_oct[4 * o] = oct_valid[o];
+    }
+    *n_out = acc;
+}
+
+// Pipeline form: octets fetch keypoints of ALL octaves from a work queue; rows with NaN are dropped
+// (plan.py:546-550); the survivors of octave o go to out[oct_offset[o] + ...], i.e. the output is grouped by
+// octave in octave order like the reference's concatenation (plan.py:555-565).
+__global__ void __launch_bounds__(DESC_WARPS * 32, 8) k_describe(OctTable T, const float4 *__restrict__ kp,
+                                                               const int *__restrict__ kp_tag,
                                                                const int *__restrict__ n_base_p,
-                                                               const int *__restrict__ n_extra_p, int cap, int octsize,
+                                                               const int *__restrict__ n_extra_p, int cap,
                                                                KpRecord *__restrict__ out, int out_cap,
-                                                               int *__restrict__ n_out, int *__restrict__ n_out_oct,
-                                                               int *__restrict__ queue) {
+                                                               const int *__restrict__ oct_offset,
+                                                               int *__restrict__ oct_fill, int *__restrict__ queue) {
     __shared__ float s_hist[DESC_WARPS * 4][DESC_HSTRIDE];
     __shared__ DescRows s_rows[DESC_WARPS * 4];
     __shared__ DescRec s_recs[DESC_WARPS * 4][8];
@@ -279,24 +292,23 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 8) k_describe(GradPlanes G, c
         const int gid0 = base + (lane >> 3);
         bool act = gid0 < n;
         float4 k = make_float4(0.f, 0.f, 1.f, 0.f);
-        int sc = 1;
+        int sc = 1, oct = 0;
         if (act) {
             k = kp[gid0];
-            sc = kp_scale[gid0];
+            const int tag = kp_tag[gid0];
+            sc = tag & 0xff;
+            oct = tag >> 8;
             const float s = ((k.x + k.y) + k.z) + k.w;
             act = (k.y >= 0.0f) && !(s != s);
         }
         int slot = 0;
-        if (act && l8 == 0) {
-            slot = atomicAdd(n_out, 1);
-            atomicAdd(n_out_oct, 1);
-        }
+        if (act && l8 == 0) slot = oct_offset[oct] + atomicAdd(&oct_fill[oct], 1);
         slot = __shfl_sync(0xffffffffu, slot, obase);
         if (slot >= out_cap) act = false;
         KpRecord *o = out + (act ? slot : 0);
         if (act && l8 == 0) { o->x = k.x; o->y = k.y; o->scale = k.z; o->angle = k.w; }
-        describe_octets(hist, s_rows[threadIdx.x >> 3], s_recs[threadIdx.x >> 3], act, k, G.grad[sc - 1], G.ori[sc - 1],
-                        G.pitch, G.w, G.h, octsize, o->desc);
+        describe_octets(hist, s_rows[threadIdx.x >> 3], s_recs[threadIdx.x >> 3], act, k, T.grad[oct][sc - 1],
+                        T.ori[oct][sc - 1], T.pitch[oct], T.w[oct], T.h[oct], T.octsize[oct], o->desc);
     }
 }
 

@@ -137,8 +137,9 @@ __device__ __forceinline__ bool interp_one(const DogStack &D, float4 k, float pe
 // grid-stride over the device-resident candidate count; survivors appended to kp / kp_scale
 __global__ void __launch_bounds__(128) k_refine(DogStack D, const float4 *__restrict__ cand,
                                                  const int *__restrict__ n_cand, int cap, float peak_thresh,
-                                                 float InitSigma, float4 *__restrict__ kp, int *__restrict__ kp_scale,
-                                                 int *__restrict__ n_kp, int *__restrict__ stage) {
+                                                 float InitSigma, float4 *__restrict__ kp, int *__restrict__ kp_tag,
+                                                 int kp_cap, int *__restrict__ n_kp, int *__restrict__ stage,
+                                                 int octave, int *__restrict__ n_kp_oct) {
     const int n = min(*n_cand, cap);
     const int stride = gridDim.x * blockDim.x;
     const int rounds = (n + stride - 1) / stride;
@@ -154,8 +155,9 @@ __global__ void __launch_bounds__(128) k_refine(DogStack D, const float4 *__rest
         }
         int slot = warp_append(keep, n_kp);
         if (keep) {
-            if (slot < cap) { kp[slot] = res; kp_scale[slot] = scale; }
+            if (slot < kp_cap) { kp[slot] = res; kp_tag[slot] = (octave << 8) | scale; }
             if (stage) atomicAdd(&stage[(scale - 1) * 3 + 1], 1);
+            if (n_kp_oct) atomicAdd(n_kp_oct, 1);
         }
     }
 }

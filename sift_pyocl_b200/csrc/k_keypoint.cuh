@@ -35,17 +35,23 @@ __global__ void __launch_bounds__(256) k_gradient(GradArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-struct GradPlanes {
-    const float *grad[3];
-    const float *ori[3];
-    int pitch, w, h;
+// Gradient / orientation planes of EVERY octave of an image: orientation assignment and descriptors run once
+// per image over the keypoints of all octaves (a keypoint carries tag = octave << 8 | scale), so that the
+// small octaves do not each pay the latency of a nearly empty launch.
+#define SIFTB_KOCT 16
+struct OctTable {
+    const float *grad[SIFTB_KOCT][3];
+    const float *ori[SIFTB_KOCT][3];
+    int pitch[SIFTB_KOCT], w[SIFTB_KOCT], h[SIFTB_KOCT];
+    int octsize[SIFTB_KOCT];
 };
 
 // One warp per keypoint (grid-stride).  kp rows in: (peak, row, col, sigma); out: (x, y, sigma*oct, angle).
 // Extra-orientation keypoints are appended at n_base + atomicAdd(n_extra).
-__global__ void __launch_bounds__(256) k_orient(GradPlanes G, float4 *__restrict__ kp, int *__restrict__ kp_scale,
+// stage: [octave][3 scales][3] counters (may be null); oct_valid[o]: records octave o will emit (non-NaN rows).
+__global__ void __launch_bounds__(256) k_orient(OctTable T, float4 *__restrict__ kp, int *__restrict__ kp_tag,
                                                  const int *__restrict__ n_base_p, int *__restrict__ n_extra, int cap,
-                                                 int octsize, float OriSigma, int *__restrict__ stage) {
+                                                 float OriSigma, int *__restrict__ stage, int *__restrict__ oct_valid) {
     __shared__ float s_hist[8][36];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int n_base = min(*n_base_p, cap);
@@ -53,14 +59,16 @@ __global__ void __launch_bounds__(256) k_orient(GradPlanes G, float4 *__restrict
     float *hist = s_hist[wib];
     for (int gid0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; gid0 < n_base; gid0 += nwarps) {
         float4 k = kp[gid0];
-        const int sc = kp_scale[gid0];
+        const int tag = kp_tag[gid0];
+        const int sc = tag & 0xff, oct = tag >> 8;
         if (!(k.y >= 0.0f)) continue;  // warp-uniform
-        const float *grad = G.grad[sc - 1], *ori = G.ori[sc - 1];
+        const float *grad = T.grad[oct][sc - 1], *ori = T.ori[oct][sc - 1];
+        const int Gpitch = T.pitch[oct], Gw = T.w[oct], Gh = T.h[oct], octsize = T.octsize[oct];
         const int row = (int)((double)k.y + 0.5), col = (int)((double)k.z + 0.5);  // orientation_cpu.cl:67-68
         const float sigma = OriSigma * k.w;
         const int radius = (int)((double)sigma * 3.0);  // :71
         const int rmin = max(0, row - radius), cmin = max(0, col - radius);
-        const int rmax = min(row + radius, G.h - 2), cmax = min(col + radius, G.w - 2);
+        const int rmax = min(row + radius, Gh - 2), cmax = min(col + radius, Gw - 2);
         const float two_s2 = (2.0f * sigma) * sigma;
         const float rad2 = ((float)(radius * radius)) + 0.5f;
         const int ncols = cmax - cmin + 1, nrows = rmax - rmin + 1;
@@ -75,13 +83,13 @@ __global__ void __launch_bounds__(256) k_orient(GradPlanes G, float4 *__restrict
             if (idx < total) {
                 const int rr = idx / ncols;
                 const int r = rmin + rr, c = cmin + (idx - rr * ncols);
-                const float gval = grad[(long)r * G.pitch + c];
+                const float gval = grad[(long)r * Gpitch + c];
                 float dif = ((float)r - k.y);
                 float distsq = dif * dif;
                 dif = ((float)c - k.z);
                 distsq += dif * dif;
                 if (gval > 0.0f && distsq < rad2) {
-                    const float angle = ori[(long)r * G.pitch + c];
+                    const float angle = ori[(long)r * Gpitch + c];
                     int b = (int)(36.0f * ((angle + SIFTB_M_PI_F) + 0.001f) / (2.0f * SIFTB_M_PI_F));
                     if (b >= 0 && b <= 36) {
                         bin = min(b, 35);
@@ -146,13 +154,15 @@ __global__ void __launch_bounds__(256) k_orient(GradPlanes G, float4 *__restrict
                         const int old = n_base + atomicAdd(n_extra, 1);
                         if (old < cap) {
                             kp[old] = make_float4(o.x, o.y, o.z, a2);
-                            kp_scale[old] = sc;
+                            kp_tag[old] = tag;
                         }
                         added++;
                     }
                 }
             }
-            if (stage) atomicAdd(&stage[(sc - 1) * 3 + 2], added);
+            if (stage) atomicAdd(&stage[oct * 9 + (sc - 1) * 3 + 2], added);
+            // rows whose angle is NaN (flat histogram) are dropped on output (plan.py:546-550)
+            if (oct_valid) atomicAdd(&oct_valid[oct], added - ((angle != angle) ? 1 : 0));
         }
         __syncwarp();
     }

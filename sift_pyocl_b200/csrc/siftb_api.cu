@@ -30,6 +30,7 @@
 
 #define SIFTB_VERSION 100
 #define MAX_OCT 32
+#define AUX_INTS (8 + 3 * SIFTB_KOCT)
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) {
@@ -112,12 +113,17 @@ struct siftb_plan {
     // images are serialised on the compute stream).
     void *d_raws[2] = {nullptr, nullptr};  // staging for host input (plan dtype)
     float *d_img = nullptr;    // dense fp32 plane for converted integer/RGB/f64 input
-    float *G[6] = {}, *D[5] = {}, *grad[3] = {}, *ori[3] = {};
+    float *G[6] = {}, *D[5] = {};
+    float *gradp[SIFTB_KOCT][3] = {}, *orip[SIFTB_KOCT][3] = {};  // gradient planes of every octave (k_keypoint.cuh)
+    OctTable table;
     float4 *cand = nullptr, *kp = nullptr;
-    int *kp_scale = nullptr;
+    int *kp_tag = nullptr;  // octave << 8 | scale
+    int kp_cap = 0;         // keypoints of one image over all octaves
     KpRecord *outs[2] = {nullptr, nullptr};
     // device counters: [0]=n_out, [1..]: per octave {n_cand, n_kp, n_extra, n_out_oct}; then stage[n_oct][3][3]; then mm[2]
-    int *d_queue = nullptr;  // [2][MAX_OCT] work-queue heads of k_describe
+    // per slot AUX_INTS ints: [0] describe work-queue head, [1] refined keypoints (all octaves), [2] extra
+    // orientations, [8..8+KOCT) records per octave, [8+KOCT..) first record slot per octave, [8+2KOCT..) fill
+    int *d_queue = nullptr;
     int *d_cnts[2] = {nullptr, nullptr};
     int *h_cnts[2] = {nullptr, nullptr};  // pinned mirrors
     cudaStream_t copy_stream = nullptr;
@@ -186,9 +192,9 @@ extern "C" int siftb_plan_destroy(siftb_plan *p) {
     cudaFree(p->d_img);
     for (auto q : p->G) cudaFree(q);
     for (auto q : p->D) cudaFree(q);
-    for (auto q : p->grad) cudaFree(q);
-    for (auto q : p->ori) cudaFree(q);
-    cudaFree(p->cand); cudaFree(p->kp); cudaFree(p->kp_scale); cudaFree(p->d_queue);
+    for (int o = 0; o < SIFTB_KOCT; o++)
+        for (int i = 0; i < 3; i++) { cudaFree(p->gradp[o][i]); cudaFree(p->orip[o][i]); }
+    cudaFree(p->cand); cudaFree(p->kp); cudaFree(p->kp_tag); cudaFree(p->d_queue);
     for (int s = 0; s < 2; s++) {
         if (p->h_cnts[s]) cudaFreeHost(p->h_cnts[s]);
         if (p->ev_h2d[s]) cudaEventDestroy(p->ev_h2d[s]);
@@ -256,14 +262,26 @@ static int plan_create_impl(siftb_plan *p) {
     if (p->dtype != SIFTB_F32 && (rc = dalloc(p, &p->d_img, N * sizeof(float)))) return rc;
     for (int i = 0; i < 6; i++) if ((rc = dalloc(p, &p->G[i], plane))) return rc;
     for (int i = 0; i < 5; i++) if ((rc = dalloc(p, &p->D[i], plane))) return rc;
-    for (int i = 0; i < 3; i++) {
-        if ((rc = dalloc(p, &p->grad[i], plane))) return rc;
-        if ((rc = dalloc(p, &p->ori[i], plane))) return rc;
+    if (p->n_oct > SIFTB_KOCT) return fail(SIFTB_EINVAL, "image too large: more than 16 octaves");
+    memset(&p->table, 0, sizeof(p->table));
+    for (int o = 0; o < p->n_oct; o++) {
+        const size_t pl = (size_t)p->opitch[o] * p->oh[o] * sizeof(float);
+        for (int i = 0; i < 3; i++) {
+            if ((rc = dalloc(p, &p->gradp[o][i], pl))) return rc;
+            if ((rc = dalloc(p, &p->orip[o][i], pl))) return rc;
+            p->table.grad[o][i] = p->gradp[o][i];
+            p->table.ori[o][i] = p->orip[o][i];
+        }
+        p->table.pitch[o] = p->opitch[o];
+        p->table.w[o] = p->ow[o];
+        p->table.h[o] = p->oh[o];
+        p->table.octsize[o] = 1 << o;
     }
     if ((rc = dalloc(p, &p->cand, (size_t)p->kpsize * sizeof(float4)))) return rc;
-    if ((rc = dalloc(p, &p->kp, (size_t)p->kpsize * sizeof(float4)))) return rc;
-    if ((rc = dalloc(p, &p->kp_scale, (size_t)p->kpsize * sizeof(int)))) return rc;
-    if ((rc = dalloc(p, &p->d_queue, 2 * MAX_OCT * sizeof(int)))) return rc;
+    p->kp_cap = 2 * p->kpsize;
+    if ((rc = dalloc(p, &p->kp, (size_t)p->kp_cap * sizeof(float4)))) return rc;
+    if ((rc = dalloc(p, &p->kp_tag, (size_t)p->kp_cap * sizeof(int)))) return rc;
+    if ((rc = dalloc(p, &p->d_queue, 2 * AUX_INTS * sizeof(int)))) return rc;
     p->out_cap = 2 * p->kpsize;
     for (int s = 0; s < 2; s++) if ((rc = dalloc(p, &p->outs[s], (size_t)p->out_cap * sizeof(KpRecord)))) return rc;
     if (tb_get_encode()) {
@@ -277,7 +295,7 @@ static int plan_create_impl(siftb_plan *p) {
             if (p->d_img) p->tmap_img_ok = tb_encode(&p->tmap_img, p->d_img, p->w, p->h, p->w, p->ntaps[5] >> 1) == 0;
         }
     }
-    p->cnt_ints = 1 + 13 * p->n_oct + 2;
+    p->cnt_ints = 1 + 13 * p->n_oct + 2 + 2;  // ... + min/max + {refined, extra} totals
     for (int s = 0; s < 2; s++) {
         if ((rc = dalloc(p, &p->d_cnts[s], p->cnt_ints * sizeof(int)))) return rc;
         CK(cudaHostAlloc((void **)&p->h_cnts[s], p->cnt_ints * sizeof(int), cudaHostAllocDefault));
@@ -443,7 +461,10 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
     // the records of this slot's previous image must have left the device before they are overwritten
     CK(cudaStreamWaitEvent(st, p->ev_d2h[slot], 0));
     CK(cudaMemsetAsync(p->d_cnts[slot], 0, p->cnt_ints * sizeof(int), st));
-    CK(cudaMemsetAsync(p->d_queue + slot * MAX_OCT, 0, MAX_OCT * sizeof(int), st));
+    int *aux = p->d_queue + slot * AUX_INTS;
+    CK(cudaMemsetAsync(aux, 0, AUX_INTS * sizeof(int), st));
+    int *q_head = aux, *n_kp = aux + 1, *n_extra = aux + 2;
+    int *oct_valid = aux + 8, *oct_offset = aux + 8 + SIFTB_KOCT, *oct_fill = aux + 8 + 2 * SIFTB_KOCT;
     unsigned *mm = p->c_mm(slot);
     const float *img;
     int rc;
@@ -469,6 +490,7 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
             return rc;
         p->launches += 1;
     }
+    // per octave: pyramid, extrema, refinement (into the image-wide keypoint list), gradient planes
     for (int o = 0; o < p->n_oct; o++) {
         const int w = p->ow[o], h = p->oh[o], pitch = p->opitch[o];
         const int octsize = 1 << o;
@@ -499,39 +521,38 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
         {
             ProfScope ps(p, "interp_keypoint + compact", o);
             k_refine<<<148 * 4, 128, 0, st>>>(ds, p->cand, c + 0, p->kpsize, kPeakThresh, (float)p->init_sigma, p->kp,
-                                              p->kp_scale, c + 1, stage);
+                                              p->kp_tag, p->kp_cap, n_kp, stage, o, c + 1);
             CKL();
             p->launches += 1;
         }
-        GradPlanes gp;
-        for (int i = 0; i < 3; i++) { gp.grad[i] = p->grad[i]; gp.ori[i] = p->ori[i]; }
-        gp.pitch = pitch; gp.w = w; gp.h = h;
         {
             ProfScope ps(p, "compute_gradient_orientation", o);
             GradArgs ga;
-            for (int i = 0; i < 3; i++) { ga.g[i] = p->G[i + 1]; ga.grad[i] = p->grad[i]; ga.ori[i] = p->ori[i]; }
+            for (int i = 0; i < 3; i++) { ga.g[i] = p->G[i + 1]; ga.grad[i] = p->gradp[o][i]; ga.ori[i] = p->orip[o][i]; }
             ga.pitch = pitch; ga.w = w; ga.h = h;
             dim3 grid((w + 255) / 256, h, 3);
             k_gradient<<<grid, 256, 0, st>>>(ga);
             CKL();
             p->launches += 1;
         }
-        {
-            ProfScope ps(p, "orientation_assignment", o);
-            k_orient<<<148 * 4, 256, 0, st>>>(gp, p->kp, p->kp_scale, c + 1, c + 2, p->kpsize, octsize, kOriSigma,
-                                              stage);
-            CKL();
-            p->launches += 1;
-        }
-        {
-            ProfScope ps(p, "descriptors", o);
-            k_describe<<<148 * 8, DESC_WARPS * 32, 0, st>>>(gp, p->kp, p->kp_scale, c + 1, c + 2, p->kpsize, octsize,
-                                                p->outs[slot], p->out_cap, p->c_nout(slot), c + 3,
-                                                p->d_queue + slot * MAX_OCT + o);
-            CKL();
-            p->launches += 1;
-        }
     }
+    // once per image: orientation assignment and descriptors over the keypoints of all octaves
+    {
+        ProfScope ps(p, "orientation_assignment");
+        k_orient<<<148 * 4, 256, 0, st>>>(p->table, p->kp, p->kp_tag, n_kp, n_extra, p->kp_cap, kOriSigma,
+                                          p->c_stage(slot, 0), oct_valid);
+        CKL();
+        p->launches += 1;
+    }
+    {
+        ProfScope ps(p, "descriptors");
+        k_octave_offsets<<<1, 1, 0, st>>>(oct_valid, p->n_oct, oct_offset, p->c_nout(slot), p->c_oct(slot, 0) + 3);
+        k_describe<<<148 * 8, DESC_WARPS * 32, 0, st>>>(p->table, p->kp, p->kp_tag, n_kp, n_extra, p->kp_cap,
+                                                        p->outs[slot], p->out_cap, oct_offset, oct_fill, q_head);
+        CKL();
+        p->launches += 2;
+    }
+    CK(cudaMemcpyAsync(p->d_cnts[slot] + 1 + 13 * p->n_oct + 2, n_kp, 2 * sizeof(int), cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(p->h_cnts[slot], p->d_cnts[slot], p->cnt_ints * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(p->ev_done[slot], st));
     p->n_flight++;
@@ -554,8 +575,12 @@ static int collect_impl(siftb_plan *p, siftb_kp *out, int cap, int *n_out, int *
     if (out && ncopy > cap) { ncopy = cap; rc = SIFTB_EOVERFLOW; }
     for (int o = 0; o < p->n_oct; o++) {
         const int *c = h_cnt + 1 + 4 * o;
-        if (c[0] > p->kpsize || c[1] + c[2] > p->kpsize) rc = SIFTB_EOVERFLOW;
+        if (c[0] > p->kpsize || c[1] > p->kpsize) rc = SIFTB_EOVERFLOW;  // per-octave slots, plan.py:243
         if (n_per_octave) n_per_octave[o] = c[3];
+    }
+    {
+        const int *tot = h_cnt + 1 + 13 * p->n_oct + 2;
+        if (tot[0] + tot[1] > p->kp_cap) rc = SIFTB_EOVERFLOW;
     }
     if (minmax) {
         const unsigned *mm = reinterpret_cast<const unsigned *>(h_cnt + 1 + 13 * p->n_oct);
@@ -805,7 +830,7 @@ extern "C" int siftb_interp(const float *dogs5, int height, int width, const flo
     for (int i = 0; i < 5; i++) Dp[i] = D.as<float>() + i * np;
     DogStack ds = make_dogstack(Dp, width, width, height);
     k_refine<<<148 * 4, 128>>>(ds, Kin.as<float4>(), C.as<int>(), n_in, kPeakThresh, init_sigma, Kout.as<float4>(),
-                               S.as<int>(), C.as<int>() + 1, nullptr);
+                               S.as<int>(), n_in, C.as<int>() + 1, nullptr, 0, nullptr);
     CKL();
     CK(cudaMemcpy(cnt, C.p, 8, cudaMemcpyDeviceToHost));
     *n_out = cnt[1];
@@ -826,10 +851,11 @@ extern "C" int siftb_orientation(const float *kp4_in, int n, const float *grad, 
     CK(cudaMemcpy(S.p, ones.data(), (size_t)cap * 4, cudaMemcpyHostToDevice));
     int cnt[2] = {n, 0};
     CK(cudaMemcpy(C.p, cnt, 8, cudaMemcpyHostToDevice));
-    GradPlanes gp;
-    for (int i = 0; i < 3; i++) { gp.grad[i] = Gd.as<float>(); gp.ori[i] = Od.as<float>(); }
-    gp.pitch = width; gp.w = width; gp.h = height;
-    k_orient<<<148 * 4, 256>>>(gp, K.as<float4>(), S.as<int>(), C.as<int>(), C.as<int>() + 1, cap, octsize, kOriSigma,
+    OctTable tb;  // a one-octave table; every row carries tag (0 << 8) | 1
+    memset(&tb, 0, sizeof(tb));
+    for (int i = 0; i < 3; i++) { tb.grad[0][i] = Gd.as<float>(); tb.ori[0][i] = Od.as<float>(); }
+    tb.pitch[0] = width; tb.w[0] = width; tb.h[0] = height; tb.octsize[0] = octsize;
+    k_orient<<<148 * 4, 256>>>(tb, K.as<float4>(), S.as<int>(), C.as<int>(), C.as<int>() + 1, cap, kOriSigma, nullptr,
                                nullptr);
     CKL();
     CK(cudaMemcpy(cnt, C.p, 8, cudaMemcpyDeviceToHost));

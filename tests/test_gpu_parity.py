@@ -212,6 +212,10 @@ def _compare_whole(sift, oracle, img, **kw):
     exact = all(np.array_equal(a[f], b[f]) for f in ("x", "y", "scale", "angle"))
     assert exact, "fp32 fields are expected to be bit-identical to the oracle"
     assert np.array_equal(a.desc, b.desc)
+    # records are grouped by octave, in octave order, like the reference's per-octave concatenation (plan.py:555-565)
+    off = np.concatenate([[0], np.cumsum(plan.last_counts)])
+    for o in range(plan.octave_max):
+        assert np.array_equal(_sort_kp(kp[off[o]:off[o + 1]]), _sort_kp(ref[off[o]:off[o + 1]])), "octave %d" % o
     assert plan.buffers["min"].get()[0] == info["minmax"][0]
     return plan, kp
 

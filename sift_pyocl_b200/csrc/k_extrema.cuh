@@ -50,29 +50,38 @@ __device__ __forceinline__ bool maxmin_pixel(const DogStack &D, int gid0, int gi
     return val != 0.0f;
 }
 
-// grid: (ceil(w/128), h-2*border, 3 scales), block 128 threads along x
-// cand rows: (val, row, col, scale).  counters[0] = total candidates, stage[s-1] = per-scale count.
+#define EXT_ROWS 8
+// grid: (ceil(w/128), ceil((h-2*border)/EXT_ROWS)), block 128 threads along x; every thread walks EXT_ROWS rows
+// and nscales scales of its column (one-pixel blocks were bound by block scheduling, not by memory).
+// cand rows: (val, row, col, scale).  n_cand = total candidates, stage[(s-1)*3] = per-scale count.
 __global__ void __launch_bounds__(128) k_extrema(DogStack D, int border, float peak_thresh, float edthresh,
                                                   float4 *__restrict__ cand, int cap, int *__restrict__ n_cand,
-                                                  int *__restrict__ stage /* [3][3] or null */, int scale_lo) {
-    const int scale = scale_lo + blockIdx.z;
+                                                  int *__restrict__ stage /* [3][3] or null */, int scale_lo,
+                                                  int nscales) {
     const int gid0 = blockIdx.x * blockDim.x + threadIdx.x;
-    const int gid1 = border + blockIdx.y;
-    bool hit = false;
-    float val = 0.f;
-    if (gid0 >= border && gid0 < D.w - border && gid1 < D.h - border)
-        hit = maxmin_pixel(D, gid0, gid1, scale, peak_thresh, edthresh, &val);
-    unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (m == 0) return;
-    int lane = threadIdx.x & 31, leader = __ffs(m) - 1, base = 0;
-    if (lane == leader) {
-        base = atomicAdd(n_cand, __popc(m));
-        if (stage) atomicAdd(&stage[(scale - 1) * 3 + 0], __popc(m));
-    }
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (hit) {
-        int slot = base + __popc(m & lanemask_lt());
-        if (slot < cap) cand[slot] = make_float4(val, (float)gid1, (float)gid0, (float)scale);  // image.cl:202-208
+    const int row0 = border + blockIdx.y * EXT_ROWS;
+    const int lane = threadIdx.x & 31;
+    const bool col_ok = gid0 >= border && gid0 < D.w - border;
+    for (int scale = scale_lo; scale < scale_lo + nscales; scale++) {
+        for (int r = 0; r < EXT_ROWS; r++) {
+            const int gid1 = row0 + r;
+            bool hit = false;
+            float val = 0.f;
+            if (col_ok && gid1 < D.h - border) hit = maxmin_pixel(D, gid0, gid1, scale, peak_thresh, edthresh, &val);
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m == 0) continue;
+            const int leader = __ffs(m) - 1;
+            int base = 0;
+            if (lane == leader) {
+                base = atomicAdd(n_cand, __popc(m));
+                if (stage) atomicAdd(&stage[(scale - 1) * 3 + 0], __popc(m));
+            }
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (hit) {
+                const int slot = base + __popc(m & lanemask_lt());
+                if (slot < cap) cand[slot] = make_float4(val, (float)gid1, (float)gid0, (float)scale);  // image.cl:202-208
+            }
+        }
     }
 }
 

@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256) k_gradient(GradArgs a) {
     else if (y == a.h - 1) ygrad = 2.0f * (g[pos - a.pitch] - g[pos]);
     else ygrad = g[pos - a.pitch] - g[pos + a.pitch];
     a.grad[z][pos] = sqrtf(xgrad * xgrad + ygrad * ygrad);
-    a.ori[z][pos] = cr_atan2f(-ygrad, xgrad);
+    a.ori[z][pos] = cr_atan2f_fast(-ygrad, xgrad);
 }
 
 // ---------------------------------------------------------------------------------------------

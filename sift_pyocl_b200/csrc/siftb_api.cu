@@ -512,9 +512,9 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
         DogStack ds = make_dogstack(p->D, pitch, w, h);
         if (w > 2 * kBorderDist && h > 2 * kBorderDist) {
             ProfScope ps(p, "local_maxmin", o);
-            dim3 grid((w + 127) / 128, h - 2 * kBorderDist, kScales);
+            dim3 grid((w + 127) / 128, (h - 2 * kBorderDist + EXT_ROWS - 1) / EXT_ROWS);
             k_extrema<<<grid, 128, 0, st>>>(ds, kBorderDist, kPeakThresh, octsize <= 1 ? kEdgeThresh1 : kEdgeThresh,
-                                            p->cand, p->kpsize, c + 0, stage, 1);
+                                            p->cand, p->kpsize, c + 0, stage, 1, kScales);
             CKL();
             p->launches += 1;
         }
@@ -804,9 +804,9 @@ extern "C" int siftb_local_maxmin(const float *dogs5, int height, int width, int
         float *Dp[5];
         for (int i = 0; i < 5; i++) Dp[i] = D.as<float>() + i * np;
         DogStack ds = make_dogstack(Dp, width, width, height);
-        dim3 grid((width + 127) / 128, height - 2 * kBorderDist, 1);
+        dim3 grid((width + 127) / 128, (height - 2 * kBorderDist + EXT_ROWS - 1) / EXT_ROWS);
         k_extrema<<<grid, 128>>>(ds, kBorderDist, kPeakThresh, octsize <= 1 ? kEdgeThresh1 : kEdgeThresh,
-                                 K.as<float4>(), cap, C.as<int>(), nullptr, scale);
+                                 K.as<float4>(), cap, C.as<int>(), nullptr, scale, 1);
         CKL();
     }
     CK(cudaMemcpy(n, C.p, 4, cudaMemcpyDeviceToHost));

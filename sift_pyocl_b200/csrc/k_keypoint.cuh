@@ -10,7 +10,7 @@
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------------------------
-// image.cl:47-81.  grid (ceil(w/256), h, nplanes), block 256
+// image.cl:47-81
 struct GradArgs {
     const float *g[3];
     float *grad[3];
@@ -18,20 +18,38 @@ struct GradArgs {
     int pitch, w, h;
 };
 
+#define GRAD_ROWS 8
+// grid (ceil(w/256), ceil(h/GRAD_ROWS), nplanes), block 256: a thread walks GRAD_ROWS rows of its column, keeping
+// the vertical neighbours in registers (one coalesced centre load per pixel; left/right come from L1).
 __global__ void __launch_bounds__(256) k_gradient(GradArgs a) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.z;
+    const int y0 = blockIdx.y * GRAD_ROWS;
     if (x >= a.w) return;
     const float *g = a.g[z];
-    const long pos = (long)y * a.pitch + x;
-    float xgrad, ygrad;
-    if (x == 0) xgrad = 2.0f * (g[pos + 1] - g[pos]);
-    else if (x == a.w - 1) xgrad = 2.0f * (g[pos] - g[pos - 1]);
-    else xgrad = g[pos + 1] - g[pos - 1];
-    if (y == 0) ygrad = 2.0f * (g[pos] - g[pos + a.pitch]);
-    else if (y == a.h - 1) ygrad = 2.0f * (g[pos - a.pitch] - g[pos]);
-    else ygrad = g[pos - a.pitch] - g[pos + a.pitch];
-    a.grad[z][pos] = sqrtf(xgrad * xgrad + ygrad * ygrad);
-    a.ori[z][pos] = cr_atan2f_fast(-ygrad, xgrad);
+    float *gradp = a.grad[z], *orip = a.ori[z];
+    const int xm = x == 0 ? 0 : x - 1, xp = x == a.w - 1 ? x : x + 1;
+    const float xs = (x == 0 || x == a.w - 1) ? 2.0f : 1.0f;  // one-sided differences are doubled (image.cl:61-66)
+    // sliding window of the centre column: up, cur, down
+    float up = g[(long)(y0 > 0 ? y0 - 1 : 0) * a.pitch + x];
+    float cur = g[(long)y0 * a.pitch + x];
+#pragma unroll
+    for (int r = 0; r < GRAD_ROWS; r++) {
+        const int y = y0 + r;
+        if (y >= a.h) break;
+        const long pos = (long)y * a.pitch + x;
+        const float dn = g[(long)(y + 1 < a.h ? y + 1 : y) * a.pitch + x];
+        // image.cl:58-66: xgrad = I[x+1]-I[x-1], doubled one-sided at the borders (then I[xm] or I[xp] is the centre)
+        const float xgrad = xs * (g[(long)y * a.pitch + xp] - g[(long)y * a.pitch + xm]);
+        // image.cl:67-72: ygrad = I[y-1]-I[y+1] ("up minus down"), doubled one-sided at the borders
+        float ygrad;
+        if (y == 0) ygrad = 2.0f * (cur - dn);
+        else if (y == a.h - 1) ygrad = 2.0f * (up - cur);
+        else ygrad = up - dn;
+        gradp[pos] = sqrtf(xgrad * xgrad + ygrad * ygrad);
+        orip[pos] = cr_atan2f_fast(-ygrad, xgrad);
+        up = cur;
+        cur = dn;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -530,7 +530,7 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
             GradArgs ga;
             for (int i = 0; i < 3; i++) { ga.g[i] = p->G[i + 1]; ga.grad[i] = p->gradp[o][i]; ga.ori[i] = p->orip[o][i]; }
             ga.pitch = pitch; ga.w = w; ga.h = h;
-            dim3 grid((w + 255) / 256, h, 3);
+            dim3 grid((w + 255) / 256, (h + GRAD_ROWS - 1) / GRAD_ROWS, 3);
             k_gradient<<<grid, 256, 0, st>>>(ga);
             CKL();
             p->launches += 1;
@@ -783,7 +783,7 @@ extern "C" int siftb_gradient(const float *image, int height, int width, float *
     GradArgs ga;
     for (int i = 0; i < 3; i++) { ga.g[i] = d.as<float>(); ga.grad[i] = g.as<float>(); ga.ori[i] = o.as<float>(); }
     ga.pitch = width; ga.w = width; ga.h = height;
-    dim3 grid((width + 255) / 256, height, 1);
+    dim3 grid((width + 255) / 256, (height + GRAD_ROWS - 1) / GRAD_ROWS, 1);
     k_gradient<<<grid, 256>>>(ga);
     CKL();
     CK(cudaMemcpy(grad, g.p, n * 4, cudaMemcpyDeviceToHost));

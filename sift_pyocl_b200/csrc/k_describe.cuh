@@ -256,7 +256,8 @@ __device__ __forceinline__ void describe_octets(float *hist, DescRows &rows, Des
 
 // prefix of the per-octave record counts -> first record slot of every octave, and the total
 __global__ void k_octave_offsets(const int *__restrict__ oct_valid, int n_oct, int *__restrict__ oct_offset,
-                                 int *__restrict__ n_out, int *__restrict__ n_out_oct /* stride 4 */) {
+                                 int *__restrict__ n_out, int *__restrict__ n_out_oct /* stride 4 */,
+                                 const int *__restrict__ size_hist, int *__restrict__ size_start) {
     int acc = 0;
     for (int o = 0; o < n_oct; o++) {
         oct_offset[o] = acc;
@@ -264,18 +265,37 @@ __global__ void k_octave_offsets(const int *__restrict__ oct_valid, int n_oct, i
         n_out_oct[4 * o] = oct_valid[o];
     }
     *n_out = acc;
+    acc = 0;  // processing order: largest windows first
+    for (int b = DESC_CLASSES - 1; b >= 0; b--) {
+        size_start[b] = acc;
+        acc += size_hist[b];
+    }
+}
+
+// order[] = keypoint indices sorted by descending descriptor-window size class (counting sort, unstable)
+__global__ void __launch_bounds__(256) k_size_order(const float4 *__restrict__ kp, const int *__restrict__ kp_tag,
+                                                     const int *__restrict__ n_base_p, const int *__restrict__ n_extra_p,
+                                                     int cap, const int *__restrict__ size_start,
+                                                     int *__restrict__ size_fill, int *__restrict__ order) {
+    const int n = min(min(*n_base_p, cap) + *n_extra_p, cap);
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int b = desc_size_class(kp[i].z, 1 << (kp_tag[i] >> 8));
+        order[size_start[b] + atomicAdd(&size_fill[b], 1)] = i;
+    }
 }
 
 // Pipeline form: octets fetch keypoints of ALL octaves from a work queue; rows with NaN are dropped
 // (plan.py:546-550); the survivors of octave o go to out[oct_offset[o] + ...], i.e. the output is grouped by
 // octave in octave order like the reference's concatenation (plan.py:555-565).
-__global__ void __launch_bounds__(DESC_WARPS * 32, 8) k_describe(OctTable T, const float4 *__restrict__ kp,
+__global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe(OctTable T, const float4 *__restrict__ kp,
                                                                const int *__restrict__ kp_tag,
                                                                const int *__restrict__ n_base_p,
                                                                const int *__restrict__ n_extra_p, int cap,
                                                                KpRecord *__restrict__ out, int out_cap,
                                                                const int *__restrict__ oct_offset,
-                                                               int *__restrict__ oct_fill, int *__restrict__ queue) {
+                                                               int *__restrict__ oct_fill, int *__restrict__ queue,
+                                                               const int *__restrict__ order) {
     __shared__ float s_hist[DESC_WARPS * 4][DESC_HSTRIDE];
     __shared__ DescRows s_rows[DESC_WARPS * 4];
     __shared__ DescRec s_recs[DESC_WARPS * 4][8];
@@ -289,8 +309,8 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 8) k_describe(OctTable T, con
         if (lane == 0) base = atomicAdd(queue, 4);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n) break;
-        const int gid0 = base + (lane >> 3);
-        bool act = gid0 < n;
+        bool act = base + (lane >> 3) < n;
+        const int gid0 = act ? order[base + (lane >> 3)] : 0;
         float4 k = make_float4(0.f, 0.f, 1.f, 0.f);
         int sc = 1, oct = 0;
         if (act) {

@@ -64,12 +64,23 @@ struct OctTable {
     int octsize[SIFTB_KOCT];
 };
 
+// Size class of a keypoint's descriptor window = its radius in pixels (keypoints_cpu.cl:60-61), clamped to 63.
+// k_describe processes the keypoints in descending class order so that the four keypoints sharing a warp have
+// windows of the same size (the warp runs as long as its largest window).
+#define DESC_CLASSES 64
+__device__ __forceinline__ int desc_size_class(float sigma_oct, int octsize) {
+    const float spacing = sigma_oct / (float)octsize * 3.0f;
+    const int iradius = (int)(((1.414f * spacing) * 2.5f) + 0.5f);
+    return min(max(iradius, 0), DESC_CLASSES - 1);
+}
+
 // One warp per keypoint (grid-stride).  kp rows in: (peak, row, col, sigma); out: (x, y, sigma*oct, angle).
 // Extra-orientation keypoints are appended at n_base + atomicAdd(n_extra).
 // stage: [octave][3 scales][3] counters (may be null); oct_valid[o]: records octave o will emit (non-NaN rows).
 __global__ void __launch_bounds__(256) k_orient(OctTable T, float4 *__restrict__ kp, int *__restrict__ kp_tag,
                                                  const int *__restrict__ n_base_p, int *__restrict__ n_extra, int cap,
-                                                 float OriSigma, int *__restrict__ stage, int *__restrict__ oct_valid) {
+                                                 float OriSigma, int *__restrict__ stage, int *__restrict__ oct_valid,
+                                                 int *__restrict__ size_hist) {
     __shared__ float s_hist[8][36];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int n_base = min(*n_base_p, cap);
@@ -181,6 +192,8 @@ __global__ void __launch_bounds__(256) k_orient(OctTable T, float4 *__restrict__
             if (stage) atomicAdd(&stage[oct * 9 + (sc - 1) * 3 + 2], added);
             // rows whose angle is NaN (flat histogram) are dropped on output (plan.py:546-550)
             if (oct_valid) atomicAdd(&oct_valid[oct], added - ((angle != angle) ? 1 : 0));
+            // descriptor-window size class of this keypoint and of its extra orientations (same sigma)
+            if (size_hist) atomicAdd(&size_hist[desc_size_class(o.z, octsize)], added);
         }
         __syncwarp();
     }

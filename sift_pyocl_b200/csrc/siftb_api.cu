@@ -30,7 +30,7 @@
 
 #define SIFTB_VERSION 100
 #define MAX_OCT 32
-#define AUX_INTS (8 + 3 * SIFTB_KOCT)
+#define AUX_INTS (8 + 3 * SIFTB_KOCT + 3 * DESC_CLASSES)
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) {
@@ -118,6 +118,7 @@ struct siftb_plan {
     OctTable table;
     float4 *cand = nullptr, *kp = nullptr;
     int *kp_tag = nullptr;  // octave << 8 | scale
+    int *kp_order = nullptr;  // keypoint indices by descending descriptor-window size
     int kp_cap = 0;         // keypoints of one image over all octaves
     KpRecord *outs[2] = {nullptr, nullptr};
     // device counters: [0]=n_out, [1..]: per octave {n_cand, n_kp, n_extra, n_out_oct}; then stage[n_oct][3][3]; then mm[2]
@@ -194,7 +195,7 @@ extern "C" int siftb_plan_destroy(siftb_plan *p) {
     for (auto q : p->D) cudaFree(q);
     for (int o = 0; o < SIFTB_KOCT; o++)
         for (int i = 0; i < 3; i++) { cudaFree(p->gradp[o][i]); cudaFree(p->orip[o][i]); }
-    cudaFree(p->cand); cudaFree(p->kp); cudaFree(p->kp_tag); cudaFree(p->d_queue);
+    cudaFree(p->cand); cudaFree(p->kp); cudaFree(p->kp_tag); cudaFree(p->kp_order); cudaFree(p->d_queue);
     for (int s = 0; s < 2; s++) {
         if (p->h_cnts[s]) cudaFreeHost(p->h_cnts[s]);
         if (p->ev_h2d[s]) cudaEventDestroy(p->ev_h2d[s]);
@@ -281,6 +282,7 @@ static int plan_create_impl(siftb_plan *p) {
     p->kp_cap = 2 * p->kpsize;
     if ((rc = dalloc(p, &p->kp, (size_t)p->kp_cap * sizeof(float4)))) return rc;
     if ((rc = dalloc(p, &p->kp_tag, (size_t)p->kp_cap * sizeof(int)))) return rc;
+    if ((rc = dalloc(p, &p->kp_order, (size_t)p->kp_cap * sizeof(int)))) return rc;
     if ((rc = dalloc(p, &p->d_queue, 2 * AUX_INTS * sizeof(int)))) return rc;
     p->out_cap = 2 * p->kpsize;
     for (int s = 0; s < 2; s++) if ((rc = dalloc(p, &p->outs[s], (size_t)p->out_cap * sizeof(KpRecord)))) return rc;
@@ -465,6 +467,7 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
     CK(cudaMemsetAsync(aux, 0, AUX_INTS * sizeof(int), st));
     int *q_head = aux, *n_kp = aux + 1, *n_extra = aux + 2;
     int *oct_valid = aux + 8, *oct_offset = aux + 8 + SIFTB_KOCT, *oct_fill = aux + 8 + 2 * SIFTB_KOCT;
+    int *size_hist = aux + 8 + 3 * SIFTB_KOCT, *size_start = size_hist + DESC_CLASSES, *size_fill = size_start + DESC_CLASSES;
     unsigned *mm = p->c_mm(slot);
     const float *img;
     int rc;
@@ -540,17 +543,20 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
     {
         ProfScope ps(p, "orientation_assignment");
         k_orient<<<148 * 4, 256, 0, st>>>(p->table, p->kp, p->kp_tag, n_kp, n_extra, p->kp_cap, kOriSigma,
-                                          p->c_stage(slot, 0), oct_valid);
+                                          p->c_stage(slot, 0), oct_valid, size_hist);
         CKL();
         p->launches += 1;
     }
     {
         ProfScope ps(p, "descriptors");
-        k_octave_offsets<<<1, 1, 0, st>>>(oct_valid, p->n_oct, oct_offset, p->c_nout(slot), p->c_oct(slot, 0) + 3);
-        k_describe<<<148 * 8, DESC_WARPS * 32, 0, st>>>(p->table, p->kp, p->kp_tag, n_kp, n_extra, p->kp_cap,
-                                                        p->outs[slot], p->out_cap, oct_offset, oct_fill, q_head);
+        k_octave_offsets<<<1, 1, 0, st>>>(oct_valid, p->n_oct, oct_offset, p->c_nout(slot), p->c_oct(slot, 0) + 3,
+                                          size_hist, size_start);
+        k_size_order<<<148, 256, 0, st>>>(p->kp, p->kp_tag, n_kp, n_extra, p->kp_cap, size_start, size_fill, p->kp_order);
+        k_describe<<<148 * 6, DESC_WARPS * 32, 0, st>>>(p->table, p->kp, p->kp_tag, n_kp, n_extra, p->kp_cap,
+                                                        p->outs[slot], p->out_cap, oct_offset, oct_fill, q_head,
+                                                        p->kp_order);
         CKL();
-        p->launches += 2;
+        p->launches += 3;
     }
     CK(cudaMemcpyAsync(p->d_cnts[slot] + 1 + 13 * p->n_oct + 2, n_kp, 2 * sizeof(int), cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(p->h_cnts[slot], p->d_cnts[slot], p->cnt_ints * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -856,7 +862,7 @@ extern "C" int siftb_orientation(const float *kp4_in, int n, const float *grad, 
     for (int i = 0; i < 3; i++) { tb.grad[0][i] = Gd.as<float>(); tb.ori[0][i] = Od.as<float>(); }
     tb.pitch[0] = width; tb.w[0] = width; tb.h[0] = height; tb.octsize[0] = octsize;
     k_orient<<<148 * 4, 256>>>(tb, K.as<float4>(), S.as<int>(), C.as<int>(), C.as<int>() + 1, cap, kOriSigma, nullptr,
-                               nullptr);
+                               nullptr, nullptr);
     CKL();
     CK(cudaMemcpy(cnt, C.p, 8, cudaMemcpyDeviceToHost));
     int total = n + cnt[1];

@@ -37,7 +37,7 @@ struct DescRows {          // per-octet table of the window rows: only the j-int
 // pc, the row weight of the row with parity pr, the column factor of the column with parity pc, the orientation
 // bin with parity po and its factor.
 struct DescRec {
-    uint32_t cells;   // byte (pr*2+pc): cell index r*4+c (0..15) or 0xff when that neighbour is outside the 4x4 grid
+    uint32_t cells;   // byte (pr*2+pc): hist offset/4 of cell (r, c), or 0xff when that neighbour is outside the 4x4 grid
     uint32_t obins;   // byte po: orientation bin of parity po; byte 2: 1 when both terms go to the same bin
     float rwp[2];     // mag*(1-rfrac) / mag*rfrac, indexed by the parity of the row they go to
     float cfp[2];     // (1-cfrac) / cfrac, indexed by the parity of the column
@@ -46,14 +46,18 @@ struct DescRec {
 
 // One warp, 4 keypoints (octet g handles kp[g] when act is true for that octet).
 // hist: this octet's 128 floats in shared memory, index (r*4+c)*8 + o (the descriptor order).
-__device__ __forceinline__ void describe_octets(float *hist, DescRows &rows, DescRec *recs, bool act, const float4 k,
+// hist layout: bin (r, c, o) lives at 32*r + 8*c + 4*(r&1) + o, so that the 8 lanes of an octet (2 rows x 2 columns
+// x 2 orientations) always hit 8 different shared-memory banks.
+#define DESC_HIDX(i) ((i) + 4 * (((i) >> 5) & 1))  /* descriptor index i = (r*4+c)*8+o -> hist slot */
+__device__ __forceinline__ void describe_octets(float *__restrict__ hist, DescRows &rows, DescRec *__restrict__ recs,
+                                                bool act, const float4 k,
                                                 const float *__restrict__ grad, const float *__restrict__ orim,
                                                 int pitch, int grad_width, int grad_height, int octsize,
                                                 uint8_t *out128) {
     const int lane = threadIdx.x & 31, l8 = lane & 7, obase = lane & 24;
     const unsigned omask = 0xffu << obase;  // lanes of my octet
     const int pr = (l8 >> 2) & 1, pc = (l8 >> 1) & 1, po = l8 & 1;  // parity class of this lane
-    for (int i = l8; i < 128; i += 8) hist[i] = 0.0f;
+    for (int i = l8; i < 132; i += 8) hist[i] = 0.0f;
     // keypoints_cpu.cl:55-61
     const float row = k.y / (float)octsize, col = k.x / (float)octsize, angle = k.w;
     const int irow = (int)(row + 0.5f), icol = (int)(col + 0.5f);
@@ -160,7 +164,8 @@ __device__ __forceinline__ void describe_octets(float *hist, DescRows &rows, Des
 #pragma unroll
                     for (int d = 0; d < 4; d++) {
                         const int rr = ri + (d >> 1), cc = ci + (d & 1);
-                        const uint32_t cell = (rr >= 0 && rr < 4 && cc >= 0 && cc < 4) ? (uint32_t)(rr * 4 + cc) : 0xffu;
+                        // stored as the hist offset / 4 of the cell: 8*rr + 2*cc + (rr&1)  (0..31), 0xff = outside
+                        const uint32_t cell = (rr >= 0 && rr < 4 && cc >= 0 && cc < 4) ? (uint32_t)(8 * rr + 2 * cc + (rr & 1)) : 0xffu;
                         cells |= cell << (8 * (((rr & 1) << 1) | (cc & 1)));
                     }
                     rec.cells = cells;
@@ -184,20 +189,32 @@ __device__ __forceinline__ void describe_octets(float *hist, DescRows &rows, Des
         const int cnt = __popc(m);
         const int cnt_max = __reduce_max_sync(0xffffffffu, cnt);
         __syncwarp();
-        // commit them one at a time: lane (pr, pc, po) adds the one contribution of its parity class
+        // commit them one at a time: lane (pr, pc, po) adds the one contribution of its parity class.  The operands
+        // of sample s+1 are fetched before the shared-memory add of sample s so their latency overlaps it.
+        uint32_t n_cells = 0, n_ob = 0;
+        float n_rw = 0.f, n_cf = 0.f, n_ow0 = 0.f, n_ow1 = 0.f;
+        if (cnt > 0) {
+            n_cells = recs[0].cells; n_ob = recs[0].obins; n_rw = recs[0].rwp[pr]; n_cf = recs[0].cfp[pc];
+            n_ow0 = recs[0].ow[po]; n_ow1 = recs[0].ow[1];
+        }
         for (int sidx = 0; sidx < cnt_max; sidx++) {
-            if (sidx < cnt) {
-                const DescRec &r = recs[sidx];
-                const uint32_t cell = (r.cells >> (8 * ((pr << 1) | pc))) & 0xffu;
+            const uint32_t c_cells = n_cells, ob = n_ob;
+            const float c_rw = n_rw, c_cf = n_cf, c_ow0 = n_ow0, c_ow1 = n_ow1;
+            const bool mine = sidx < cnt;
+            if (sidx + 1 < cnt) {
+                const DescRec &nx = recs[sidx + 1];
+                n_cells = nx.cells; n_ob = nx.obins; n_rw = nx.rwp[pr]; n_cf = nx.cfp[pc]; n_ow0 = nx.ow[po]; n_ow1 = nx.ow[1];
+            }
+            if (mine) {
+                const uint32_t cell = (c_cells >> (8 * ((pr << 1) | pc))) & 0xffu;
                 if (cell != 0xffu) {
-                    const float cweight = r.rwp[pr] * r.cfp[pc];
-                    const uint32_t ob = r.obins;
-                    float *hb = hist + cell * 8;
+                    const float cweight = c_rw * c_cf;
+                    float *hb = hist + cell * 4;
                     if (!(ob >> 16)) {
-                        hb[(ob >> (8 * po)) & 0xffu] += cweight * r.ow[po];
-                    } else if (po == (int)(ob & 1u)) {
-                        hb[ob & 0xffu] += cweight * r.ow[0];
-                        hb[ob & 0xffu] += cweight * r.ow[1];
+                        hb[(ob >> (8 * po)) & 0xffu] += cweight * c_ow0;
+                    } else if (po == (int)(ob & 1u)) {  // both orientation terms in one bin: ow[0] then ow[1]
+                        hb[ob & 0xffu] += cweight * ((po == 0) ? c_ow0 : recs[sidx].ow[0]);
+                        hb[ob & 0xffu] += cweight * c_ow1;
                     }
                 }
             }
@@ -208,7 +225,7 @@ __device__ __forceinline__ void describe_octets(float *hist, DescRows &rows, Des
     // finish, keypoints_cpu.cl:127-160: each lane of the octet owns 16 consecutive descriptor entries
     float v[16];
 #pragma unroll
-    for (int q = 0; q < 16; q++) v[q] = hist[l8 * 16 + q];
+    for (int q = 0; q < 16; q++) v[q] = hist[DESC_HIDX(l8 * 16 + q)];
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < 16; q++) hist[l8 * 16 + q] = v[q] * v[q];

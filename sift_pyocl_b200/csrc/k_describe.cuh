@@ -23,7 +23,7 @@
 #include "k_keypoint.cuh"
 
 #define DESC_WARPS 4  // warps per CTA -> 16 keypoints per CTA
-#define DESC_HSTRIDE 136  // floats between the histograms of two octets (128 + 8: spreads the banks)
+#define DESC_HSTRIDE 144  // floats between the histograms of two octets (140 used; 144 = 16 banks apart)
 
 #define DESC_MAXROWS 100  // window rows per keypoint handled by the interval table (iradius <= 49; default sigmas need 97)
 
@@ -46,9 +46,9 @@ struct DescRec {
 
 // One warp, 4 keypoints (octet g handles kp[g] when act is true for that octet).
 // hist: this octet's 128 floats in shared memory, index (r*4+c)*8 + o (the descriptor order).
-// hist layout: bin (r, c, o) lives at 32*r + 8*c + 4*(r&1) + o, so that the 8 lanes of an octet (2 rows x 2 columns
-// x 2 orientations) always hit 8 different shared-memory banks.
-#define DESC_HIDX(i) ((i) + 4 * (((i) >> 5) & 1))  /* descriptor index i = (r*4+c)*8+o -> hist slot */
+// hist layout: bin (r, c, o) lives at 36*r + 8*c + o (rows padded by 4 floats), so that the 8 lanes of an octet
+// (2 rows x 2 columns x 2 orientations) always hit 8 different shared-memory banks.
+#define DESC_HIDX(i) ((i) + 4 * ((i) >> 5))  /* descriptor index i = (r*4+c)*8+o -> hist slot */
 __device__ __forceinline__ void describe_octets(float *__restrict__ hist, DescRows &rows, DescRec *__restrict__ recs,
                                                 bool act, const float4 k,
                                                 const float *__restrict__ grad, const float *__restrict__ orim,
@@ -57,7 +57,7 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ hist, DescRo
     const int lane = threadIdx.x & 31, l8 = lane & 7, obase = lane & 24;
     const unsigned omask = 0xffu << obase;  // lanes of my octet
     const int pr = (l8 >> 2) & 1, pc = (l8 >> 1) & 1, po = l8 & 1;  // parity class of this lane
-    for (int i = l8; i < 132; i += 8) hist[i] = 0.0f;
+    for (int i = l8; i < 140; i += 8) hist[i] = 0.0f;
     // keypoints_cpu.cl:55-61
     const float row = k.y / (float)octsize, col = k.x / (float)octsize, angle = k.w;
     const int irow = (int)(row + 0.5f), icol = (int)(col + 0.5f);
@@ -164,8 +164,8 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ hist, DescRo
 #pragma unroll
                     for (int d = 0; d < 4; d++) {
                         const int rr = ri + (d >> 1), cc = ci + (d & 1);
-                        // stored as the hist offset / 4 of the cell: 8*rr + 2*cc + (rr&1)  (0..31), 0xff = outside
-                        const uint32_t cell = (rr >= 0 && rr < 4 && cc >= 0 && cc < 4) ? (uint32_t)(8 * rr + 2 * cc + (rr & 1)) : 0xffu;
+                        // stored as the hist offset / 4 of the cell: 9*rr + 2*cc (0..33), 0xff = outside
+                        const uint32_t cell = (rr >= 0 && rr < 4 && cc >= 0 && cc < 4) ? (uint32_t)(9 * rr + 2 * cc) : 0xffu;
                         cells |= cell << (8 * (((rr & 1) << 1) | (cc & 1)));
                     }
                     rec.cells = cells;

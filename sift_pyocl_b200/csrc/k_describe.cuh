@@ -189,32 +189,21 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ hist, DescRo
         const int cnt = __popc(m);
         const int cnt_max = __reduce_max_sync(0xffffffffu, cnt);
         __syncwarp();
-        // commit them one at a time: lane (pr, pc, po) adds the one contribution of its parity class.  The operands
-        // of sample s+1 are fetched before the shared-memory add of sample s so their latency overlaps it.
-        uint32_t n_cells = 0, n_ob = 0;
-        float n_rw = 0.f, n_cf = 0.f, n_ow0 = 0.f, n_ow1 = 0.f;
-        if (cnt > 0) {
-            n_cells = recs[0].cells; n_ob = recs[0].obins; n_rw = recs[0].rwp[pr]; n_cf = recs[0].cfp[pc];
-            n_ow0 = recs[0].ow[po]; n_ow1 = recs[0].ow[1];
-        }
+        // commit them one at a time: lane (pr, pc, po) adds the one contribution of its parity class
+        // (fetching the operands of sample s+1 ahead of the add of sample s was measured slower: registers)
         for (int sidx = 0; sidx < cnt_max; sidx++) {
-            const uint32_t c_cells = n_cells, ob = n_ob;
-            const float c_rw = n_rw, c_cf = n_cf, c_ow0 = n_ow0, c_ow1 = n_ow1;
-            const bool mine = sidx < cnt;
-            if (sidx + 1 < cnt) {
-                const DescRec &nx = recs[sidx + 1];
-                n_cells = nx.cells; n_ob = nx.obins; n_rw = nx.rwp[pr]; n_cf = nx.cfp[pc]; n_ow0 = nx.ow[po]; n_ow1 = nx.ow[1];
-            }
-            if (mine) {
-                const uint32_t cell = (c_cells >> (8 * ((pr << 1) | pc))) & 0xffu;
+            if (sidx < cnt) {
+                const DescRec &r = recs[sidx];
+                const uint32_t cell = (r.cells >> (8 * ((pr << 1) | pc))) & 0xffu;
                 if (cell != 0xffu) {
-                    const float cweight = c_rw * c_cf;
+                    const float cweight = r.rwp[pr] * r.cfp[pc];
+                    const uint32_t ob = r.obins;
                     float *hb = hist + cell * 4;
                     if (!(ob >> 16)) {
-                        hb[(ob >> (8 * po)) & 0xffu] += cweight * c_ow0;
-                    } else if (po == (int)(ob & 1u)) {  // both orientation terms in one bin: ow[0] then ow[1]
-                        hb[ob & 0xffu] += cweight * ((po == 0) ? c_ow0 : recs[sidx].ow[0]);
-                        hb[ob & 0xffu] += cweight * c_ow1;
+                        hb[(ob >> (8 * po)) & 0xffu] += cweight * r.ow[po];
+                    } else if (po == (int)(ob & 1u)) {
+                        hb[ob & 0xffu] += cweight * r.ow[0];
+                        hb[ob & 0xffu] += cweight * r.ow[1];
                     }
                 }
             }

@@ -36,17 +36,18 @@ __device__ double c_atan_a[17] = {0x0.0p+0, 0x1.921fb54442d18p-5, 0x1.921fb54442
 __device__ double c_atan_t[17] = {0x1.92346247a91f0p-6, 0x1.2e239ccff3831p-4, 0x1.f93183a8db9e9p-4, 0x1.635c990ce0d36p-3, 0x1.cbe4ceb4b4cf2p-3, 0x1.1b6103d3597e8p-2, 0x1.5248ae1701b18p-2, 0x1.8b00196b3d021p-2, 0x1.c5e87185e67b6p-2, 0x1.01b819b5a7cf7p-1, 0x1.220b5ef047825p-1, 0x1.44386db9ce5dap-1, 0x1.6897514751db6p-1, 0x1.8f9197bf85eeap-1, 0x1.b9a77c18c1af2p-1, 0x1.e776eafc91705p-1, 1e300};
 
 __device__ __forceinline__ float cr_atan2f_fast(float yf, float xf) {
-    const double x = (double)xf, y = (double)yf;
-    const double ax = fabs(x), ay = fabs(y);
-    const double hi = ax > ay ? ax : ay, lo = ax > ay ? ay : ax;
+    const float axf = fabsf(xf), ayf = fabsf(yf);
+    const float hif = fmaxf(axf, ayf), lof = fminf(axf, ayf);
     double a = 0.0;
-    if (lo != 0.0) {
-        // tables live in global memory and are read through L1 (__ldg): the index differs per lane, which the
+    if (lof != 0.0f) {
+        // breakpoint search in fp32 (any neighbouring breakpoint is as good at an interval boundary); tables
+        // live in global memory and are read through L1 (__ldg): the index differs per lane, which the
         // constant cache would serialise
-        int k = (lo > 0x1.8b00196b3d021p-2 * hi) ? 8 : 0;  // c_atan_t[7]
-        k += (lo > __ldg(&c_atan_t[k + 3]) * hi) ? 4 : 0;
-        k += (lo > __ldg(&c_atan_t[k + 1]) * hi) ? 2 : 0;
-        k += (lo > __ldg(&c_atan_t[k]) * hi) ? 1 : 0;
+        int k = (lof > (float)0x1.8b00196b3d021p-2 * hif) ? 8 : 0;  // c_atan_t[7]
+        k += (lof > (float)__ldg(&c_atan_t[k + 3]) * hif) ? 4 : 0;
+        k += (lof > (float)__ldg(&c_atan_t[k + 1]) * hif) ? 2 : 0;
+        k += (lof > (float)__ldg(&c_atan_t[k]) * hif) ? 1 : 0;
+        const double hi = (double)hif, lo = (double)lof;
         const double c = __ldg(&c_atan_c[k]);
         const double r = __ddiv_rn(fma(-c, hi, lo), fma(c, lo, hi));
         const double r2 = r * r;
@@ -57,9 +58,9 @@ __device__ __forceinline__ float cr_atan2f_fast(float yf, float xf) {
         p = p * r2;
         a = __ldg(&c_atan_a[k]) + fma(r, p, r);
     }
-    if (ay > ax) a = 1.5707963267948966 - a;
-    if (signbit(x)) a = 3.141592653589793 - a;
-    return (float)copysign(a, y);
+    if (ayf > axf) a = 1.5707963267948966 - a;
+    if (signbit(xf)) a = 3.141592653589793 - a;
+    return copysignf((float)a, yf);
 }
 
 // reference mirror rule, convolution.cl:41-50: p<0 -> -p-1 ; p>=dim -> 2*dim-1-p

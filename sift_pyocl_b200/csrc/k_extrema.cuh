@@ -13,33 +13,40 @@ struct DogStack {
     int pitch, w, h;
 };
 
-// image.cl:141-212 for one pixel; returns true when (gid0, gid1, scale) is a keypoint candidate
-__device__ __forceinline__ bool maxmin_pixel(const DogStack &D, int gid0, int gid1, int scale, float peak_thresh,
-                                             float edthresh, float *val_out) {
-    const float *dp = D.d[scale - 1], *dc = D.d[scale], *dn = D.d[scale + 1];
-    const long pos = (long)gid1 * D.pitch + gid0;
-    const float val = dc[pos];
-    *val_out = val;
-    // image.cl:152 -- double comparison (0.8 is a double literal)
-    if (!(fabs((double)val) > (0.8 * (double)peak_thresh))) return false;
-    // image.cl:155-170: maximum test for val > 0, minimum test otherwise, strict comparisons (plateaus
-    // fire).  Same result as the reference's flag loops, with an early exit: the in-plane neighbours are
-    // tested first because they reject most pixels after a few (L1-resident) loads.
-    const bool want_max = val > 0.0f;
-    const float sgn = want_max ? 1.0f : -1.0f;  // compare sgn*n > sgn*val : exact (sign flip only)
-    const float sval = sgn * val;
-    for (int plane = 0; plane < 3; plane++) {
-        const float *pl = plane == 0 ? dc : (plane == 1 ? dp : dn);
+// image.cl:141-212 for one pixel and one scale, given the five DoG values c[0..4] at that pixel.
+// gate: smallest fp32 strictly above 0.8*peak_thresh evaluated in double (image.cl:152 compares in double:
+// fabs(val) > 0.8*peak_thresh  <=>  fabsf(val) >= gate for fp32 val); computed on the host.
+// Returns true when (gid0, gid1, scale) is a keypoint candidate.  Same decisions as the reference's flag loops
+// (strict comparisons, plateaus fire); the tests are ordered so that most pixels leave after a few compares on
+// values that are already in registers or L1.
+__device__ __forceinline__ bool maxmin_pixel(const DogStack &D, long pos, int scale, const float c[5], float gate,
+                                             float edthresh) {
+    const float val = c[scale];
+    if (!(fabsf(val) >= gate)) return false;
+    const float sgn = (val > 0.0f) ? 1.0f : -1.0f;  // maximum test for val > 0, minimum test otherwise
+    const float sval = sgn * val;                   // sign flips are exact
+    if (sgn * c[scale - 1] > sval || sgn * c[scale + 1] > sval) return false;  // same pixel, neighbouring scales
+    const float *dc = D.d[scale];
+    if (sgn * dc[pos - 1] > sval || sgn * dc[pos + 1] > sval) return false;
 #pragma unroll
-        for (int dr = -1; dr <= 1; dr++) {
-            const float *rowp = pl + pos + (long)dr * D.pitch;
+    for (int dr = -1; dr <= 1; dr += 2) {
+        const float *rowp = dc + pos + (long)dr * D.pitch;
+        if (sgn * rowp[-1] > sval || sgn * rowp[0] > sval || sgn * rowp[1] > sval) return false;
+    }
+#pragma unroll
+    for (int dpl = -1; dpl <= 1; dpl += 2) {
+        const float *pl = D.d[scale + dpl] + pos;
+        if (sgn * pl[-1] > sval || sgn * pl[1] > sval) return false;
+#pragma unroll
+        for (int dr = -1; dr <= 1; dr += 2) {
+            const float *rowp = pl + (long)dr * D.pitch;
             if (sgn * rowp[-1] > sval || sgn * rowp[0] > sval || sgn * rowp[1] > sval) return false;
         }
     }
     // image.cl:180-186: H00/H11 in double (literal 2.0), H01 float differences then /4.0
     const long up = pos - D.pitch, dn_ = pos + D.pitch;
-    float H00 = (float)(((double)dc[up] - 2.0 * (double)dc[pos]) + (double)dc[dn_]);
-    float H11 = (float)(((double)dc[pos - 1] - 2.0 * (double)dc[pos]) + (double)dc[pos + 1]);
+    float H00 = (float)(((double)dc[up] - 2.0 * (double)val) + (double)dc[dn_]);
+    float H11 = (float)(((double)dc[pos - 1] - 2.0 * (double)val) + (double)dc[pos + 1]);
     float d1 = dc[dn_ + 1] - dc[dn_ - 1];
     float d2 = dc[up + 1] - dc[up - 1];
     float H01 = (float)((double)(d1 - d2) / 4.0);
@@ -52,9 +59,9 @@ __device__ __forceinline__ bool maxmin_pixel(const DogStack &D, int gid0, int gi
 
 #define EXT_ROWS 8
 // grid: (ceil(w/128), ceil((h-2*border)/EXT_ROWS)), block 128 threads along x; every thread walks EXT_ROWS rows
-// and nscales scales of its column (one-pixel blocks were bound by block scheduling, not by memory).
+// of its column and tests nscales scales per pixel from the five DoG values loaded together.
 // cand rows: (val, row, col, scale).  n_cand = total candidates, stage[(s-1)*3] = per-scale count.
-__global__ void __launch_bounds__(128) k_extrema(DogStack D, int border, float peak_thresh, float edthresh,
+__global__ void __launch_bounds__(128) k_extrema(DogStack D, int border, float gate, float edthresh,
                                                   float4 *__restrict__ cand, int cap, int *__restrict__ n_cand,
                                                   int *__restrict__ stage /* [3][3] or null */, int scale_lo,
                                                   int nscales) {
@@ -62,12 +69,20 @@ __global__ void __launch_bounds__(128) k_extrema(DogStack D, int border, float p
     const int row0 = border + blockIdx.y * EXT_ROWS;
     const int lane = threadIdx.x & 31;
     const bool col_ok = gid0 >= border && gid0 < D.w - border;
-    for (int scale = scale_lo; scale < scale_lo + nscales; scale++) {
-        for (int r = 0; r < EXT_ROWS; r++) {
-            const int gid1 = row0 + r;
-            bool hit = false;
-            float val = 0.f;
-            if (col_ok && gid1 < D.h - border) hit = maxmin_pixel(D, gid0, gid1, scale, peak_thresh, edthresh, &val);
+    for (int r = 0; r < EXT_ROWS; r++) {
+        const int gid1 = row0 + r;
+        const bool in = col_ok && gid1 < D.h - border;
+        const long pos = (long)gid1 * D.pitch + gid0;
+        float c[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        if (in) {
+#pragma unroll
+            for (int i = 0; i < 5; i++) c[i] = D.d[i][pos];
+        }
+#pragma unroll
+        for (int si = 0; si < 3; si++) {
+            const int scale = 1 + si;
+            if (scale < scale_lo || scale >= scale_lo + nscales) continue;  // block-uniform
+            const bool hit = in && maxmin_pixel(D, pos, scale, c, gate, edthresh);
             const unsigned m = __ballot_sync(0xffffffffu, hit);
             if (m == 0) continue;
             const int leader = __ffs(m) - 1;
@@ -79,7 +94,7 @@ __global__ void __launch_bounds__(128) k_extrema(DogStack D, int border, float p
             base = __shfl_sync(0xffffffffu, base, leader);
             if (hit) {
                 const int slot = base + __popc(m & lanemask_lt());
-                if (slot < cap) cand[slot] = make_float4(val, (float)gid1, (float)gid0, (float)scale);  // image.cl:202-208
+                if (slot < cap) cand[slot] = make_float4(c[scale], (float)gid1, (float)gid0, (float)scale);  // image.cl:202-208
             }
         }
     }

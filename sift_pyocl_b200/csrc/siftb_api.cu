@@ -53,6 +53,14 @@ static const float kPeakThresh = (float)(255.0 * 0.04 / 3.0), kEdgeThresh = 0.06
                    kOriSigma = 1.5f;
 
 static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+// image.cl:152 `fabs(val) > 0.8 * peak_thresh` is a double comparison; for an fp32 val it equals
+// fabsf(val) >= (smallest fp32 strictly above the double product)
+static float contrast_gate(float peak_thresh) {
+    const double thr = 0.8 * (double)peak_thresh;
+    float f = (float)thr;                       // nearest fp32
+    if ((double)f > thr) f = nextafterf(f, 0.0f);  // largest fp32 <= thr
+    return nextafterf(f, INFINITY);
+}
 // SIFTB_FORCE_GENERIC=1 routes every blur through the generic kernel (A/B testing of the TMA kernel)
 static int env_force_generic() {
     const char *e = getenv("SIFTB_FORCE_GENERIC");
@@ -516,8 +524,9 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
         if (w > 2 * kBorderDist && h > 2 * kBorderDist) {
             ProfScope ps(p, "local_maxmin", o);
             dim3 grid((w + 127) / 128, (h - 2 * kBorderDist + EXT_ROWS - 1) / EXT_ROWS);
-            k_extrema<<<grid, 128, 0, st>>>(ds, kBorderDist, kPeakThresh, octsize <= 1 ? kEdgeThresh1 : kEdgeThresh,
-                                            p->cand, p->kpsize, c + 0, stage, 1, kScales);
+            k_extrema<<<grid, 128, 0, st>>>(ds, kBorderDist, contrast_gate(kPeakThresh),
+                                            octsize <= 1 ? kEdgeThresh1 : kEdgeThresh, p->cand, p->kpsize, c + 0, stage, 1,
+                                            kScales);
             CKL();
             p->launches += 1;
         }
@@ -811,7 +820,7 @@ extern "C" int siftb_local_maxmin(const float *dogs5, int height, int width, int
         for (int i = 0; i < 5; i++) Dp[i] = D.as<float>() + i * np;
         DogStack ds = make_dogstack(Dp, width, width, height);
         dim3 grid((width + 127) / 128, (height - 2 * kBorderDist + EXT_ROWS - 1) / EXT_ROWS);
-        k_extrema<<<grid, 128>>>(ds, kBorderDist, kPeakThresh, octsize <= 1 ? kEdgeThresh1 : kEdgeThresh,
+        k_extrema<<<grid, 128>>>(ds, kBorderDist, contrast_gate(kPeakThresh), octsize <= 1 ? kEdgeThresh1 : kEdgeThresh,
                                  K.as<float4>(), cap, C.as<int>(), nullptr, scale, 1);
         CKL();
     }

@@ -17,7 +17,8 @@ static inline double fast_atan2(float yf, float xf){
   else {
     // interval: largest k with lo >= TB[k-1]*hi ... nearest breakpoint c_k = tan(k*pi/64)
     int k=0; // binary search over TB (16 thresholds): k = number of thresholds with lo > TB*hi
-    k = (lo > TB[7]*hi) ? 8 : 0; k += (lo > TB[k+3]*hi) ? 4 : 0; k += (lo > TB[k+1]*hi) ? 2 : 0; k += (lo > TB[k]*hi) ? 1 : 0; /* same 4-step search as common.cuh (k <= 15) */
+    { float lof=(float)lo, hif=(float)hi; /* fp32 search, as common.cuh (k <= 15) */
+      k = (lof > (float)TB[7]*hif) ? 8 : 0; k += (lof > (float)TB[k+3]*hif) ? 4 : 0; k += (lof > (float)TB[k+1]*hif) ? 2 : 0; k += (lof > (float)TB[k]*hif) ? 1 : 0; }
     double c=C[k];
     double r = fma(-c,hi,lo)/fma(c,lo,hi);
     double r2=r*r;

@@ -103,3 +103,33 @@ def keypoints_batch(plan, images, group=None, gather=True):
             out[i] = recs[start:start + all_sz[r, j]]
             start += all_sz[r, j]
     return out
+
+
+def match_sharded(match_plan, kp1, kp2, group=None):
+    """MatchPlan.match(kp1, kp2, raw_results=True) with the rows of ``kp1`` sharded over the ranks of ``group``
+    (SURVEY.md 8f rank 4): rank r matches kp1[r::world] against all of kp2, the index pairs are all-gathered.
+
+    Every rank passes the same kp1 / kp2 and receives the same int32 [m, 2] array, sorted by the kp1 index (the
+    reference's output order is nondeterministic: atomic_inc, matching_gpu.cl:100).
+    """
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    mine = numpy.arange(rank, kp1.shape[0], world)
+    local = match_plan.match(kp1[mine], kp2, raw_results=True) if mine.size else numpy.zeros((0, 2), numpy.int32)
+    local = numpy.ascontiguousarray(local, numpy.int32).copy()
+    if local.shape[0]:
+        local[:, 0] = mine[local[:, 0]]  # back to indices into the full kp1
+    use_cuda = dist.get_backend(group) == "nccl"
+    dev = torch.device("cuda:%d" % match_plan.device) if use_cuda else torch.device("cpu")
+    t = torch.from_numpy(local).to(dev)
+    cnt = torch.tensor([t.shape[0]], dtype=torch.int64, device=dev)
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, cnt, group=group)
+    counts_h = counts.cpu()
+    nmax = max(int(counts_h.max()), 1)
+    padded = torch.zeros((nmax, 2), dtype=torch.int32, device=dev)
+    padded[:t.shape[0]] = t
+    gathered = torch.empty((world * nmax, 2), dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(gathered, padded, group=group)
+    gathered = gathered.view(world, nmax, 2).cpu().numpy()
+    out = numpy.concatenate([gathered[r, :int(counts_h[r])] for r in range(world)])
+    return out[numpy.argsort(out[:, 0], kind="stable")]

@@ -63,6 +63,43 @@ def test_sharded_batch_allgather_world2(n_images):
     assert res == [(0, True), (1, True)]
 
 
+class _StubMatch(object):
+    device = 0
+
+    def match(self, kp1, kp2, raw_results=True):  # nearest x, accepted when the x values agree
+        out = [(i, int(np.argmin(abs(kp2.x - a)))) for i, a in enumerate(kp1.x) if abs(kp2.x - a).min() < 1e-6]
+        return np.array(out, np.int32).reshape(-1, 2)
+
+
+def _match_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sift_pyocl_b200 import dist as sdist
+    from sift_pyocl_b200._lib import dtype_kp
+    rng = np.random.default_rng(5)
+    k1 = np.zeros(37, dtype_kp).view(np.recarray)
+    k2 = np.zeros(29, dtype_kp).view(np.recarray)
+    k1.x = rng.permutation(37)
+    k2.x = rng.permutation(45)[:29]
+    got = sdist.match_sharded(_StubMatch(), k1, k2)
+    want = _StubMatch().match(k1, k2)
+    q.put((rank, bool(np.array_equal(got, want[np.argsort(want[:, 0], kind="stable")]) and len(want) > 5)))
+    dist.destroy_process_group()
+
+
+def test_match_sharded_world2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_match_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert res == [(0, True), (1, True)]
+
+
 def test_shard_indices():
     from sift_pyocl_b200.dist import shard_indices
     assert shard_indices(64, 3, 8) == list(range(3, 64, 8))  # BASELINE config 3: 64 images over 8 GPUs

@@ -75,26 +75,37 @@ __device__ __forceinline__ void tb_row_task(const float *__restrict__ src, float
         reinterpret_cast<float4 *>(dst)[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
 }
 
+// TMA issue helper: one 2-D box of `rows` x BW floats at (x, y) into dst, completion on bar
+template <int BW>
+__device__ __forceinline__ void tb_issue_load(const CUtensorMap *map, float *dst, uint64_t *bar, int x, int y,
+                                              int rows) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"((uint32_t)(BW * rows * sizeof(float))) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+
+// tmap: box (BH rows) for the first tile of a vertical run; tmap_c: box (TB_TH rows) for the continuation tiles.
 template <int C, int MODE, int TB_TW>
 __global__ void __launch_bounds__(256, 2)
-k_blur_tma(const __grid_constant__ CUtensorMap tmap, BlurArgs a, Taps taps, int ntx, int ntiles) {
+k_blur_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_c, BlurArgs a, Taps taps,
+           int nty, int ntiles) {
     constexpr int N = 2 * C + 1;
-    constexpr int TB_THREADS = 256;        // column pass: (TW/2 column pairs) x (TH/R row groups) threads
+    constexpr int TB_THREADS = 256;        // column pass: 32 column groups x (TH/RV) row groups
     constexpr int TB_R = tb_r(TB_TW);
     constexpr int TB_HP = tb_hp(TB_TW);
     constexpr int BW = tb_box_w(C, TB_TW), BH = tb_box_h(C);
     constexpr int RH = TB_R;               // outputs per thread in the horizontal pass
     constexpr int NSEG = TB_TW / RH;       // segments per row
-    constexpr int WIN = RH + 2 * C;        // inputs per horizontal task
     constexpr int DELTA = tb_delta(C);     // tile column of global x is x - (x0 - C - DELTA)
-    constexpr int WIN4 = tb_win4(C, TB_TW);
-    static_assert(WIN4 * 4 >= WIN + DELTA, "window");
     constexpr int RV = 8;                  // rows per thread in the vertical pass
     static_assert(32 * (TB_TH / RV) == TB_THREADS, "column-pass mapping");
+    static_assert(2 * C <= TB_TH, "halo rows are carried between vertically adjacent tiles");
     constexpr int LW = C + DELTA;          // left halo width in tile columns
     extern __shared__ __align__(128) float smem[];
-    float *tile = smem;                    // BH x BW
-    float *hbuf = smem + BH * BW;          // BH x TB_HP
+    float *tile = smem;                    // BH x BW staged input rows
+    float *hbuf = smem + BH * BW;          // BH x TB_HP row-pass results; row hr <-> image row y0 - C + hr
     uint64_t *bar = reinterpret_cast<uint64_t *>(hbuf + BH * TB_HP);
     const int tid = threadIdx.x;
 
@@ -108,22 +119,31 @@ k_blur_tma(const __grid_constant__ CUtensorMap tmap, BlurArgs a, Taps taps, int 
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // let the next blur get resident early too
     __syncthreads();
-    // persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA load of the next tile is issued
-    // as soon as the row pass has consumed the staged tile, so it overlaps the column pass + epilogue.
-    int t = blockIdx.x;
-    if (tid == 0 && t < ntiles) {
-        const int tx0 = (t % ntx) * TB_TW, ty0 = (t / ntx) * TB_TH;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-                     "r"((uint32_t)(BW * BH * sizeof(float))) : "memory");
-        asm volatile(
-            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-            ::"r"(smem_u32(tile)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(tx0 - C - DELTA), "r"(ty0 - C),
-            "r"(smem_u32(bar)) : "memory");
+    // Persistent CTA over a contiguous range of the COLUMN-MAJOR tile list (t -> tile column t / nty, tile row
+    // t % nty): consecutive tiles are vertically adjacent, so all but the first tile of a run ("continuation"
+    // tiles) keep the last 2C row-pass rows of the tile above, load only TH new input rows and run the row pass
+    // on TH instead of TH + 2C rows.  The TMA load of the next tile is issued as soon as the row pass has consumed
+    // the staged rows, so it overlaps the column pass + epilogue.
+    const int t_begin = (int)(((long)ntiles * blockIdx.x) / gridDim.x);
+    const int t_end = (int)(((long)ntiles * (blockIdx.x + 1)) / gridDim.x);
+    if (tid == 0 && t_begin < t_end) {
+        const int tx0 = (t_begin / nty) * TB_TW, ty0 = (t_begin % nty) * TB_TH;
+        tb_issue_load<BW>(&tmap, tile, bar, tx0 - C - DELTA, ty0 - C, BH);
     }
     uint32_t phase = 0;
-    for (; t < ntiles; t += gridDim.x) {
-        const int x0 = (t % ntx) * TB_TW, y0 = (t / ntx) * TB_TH;
-        {   // wait for the staged tile
+    for (int t = t_begin; t < t_end; t++) {
+        const int tyi = t % nty;
+        const int x0 = (t / nty) * TB_TW, y0 = tyi * TB_TH;
+        const bool cont = (t > t_begin) && (tyi != 0);  // the tile above was the previous one of this CTA
+        const int nrows = cont ? TB_TH : BH;             // staged input rows = row-pass rows of this tile
+        const int hrow0 = cont ? 2 * C : 0;              // first hbuf row they produce
+        if (cont) {  // carry the 2C halo rows: hbuf rows [TH, TH + 2C) of the tile above are rows [0, 2C) here
+            for (int i = tid; i < 2 * C * (TB_TW / 4); i += TB_THREADS) {
+                const int r = i / (TB_TW / 4), c4 = i - r * (TB_TW / 4);
+                reinterpret_cast<float4 *>(hbuf + r * TB_HP)[c4] = reinterpret_cast<const float4 *>(hbuf + (TB_TH + r) * TB_HP)[c4];
+            }
+        }
+        {   // wait for the staged rows
             uint32_t done = 0;
             while (!done) {
                 asm volatile(
@@ -136,7 +156,7 @@ k_blur_tma(const __grid_constant__ CUtensorMap tmap, BlurArgs a, Taps taps, int 
             const float mn = ordered_to_float(a.norm_mm[0]);
             const float den = ordered_to_float(a.norm_mm[1]) - mn;
             float4 *t4 = reinterpret_cast<float4 *>(tile);
-            for (int i = tid; i < BH * BW / 4; i += TB_THREADS) {
+            for (int i = tid; i < nrows * BW / 4; i += TB_THREADS) {
                 float4 v = t4[i];
                 v.x = (255.0f * (v.x - mn)) / den; v.y = (255.0f * (v.y - mn)) / den;
                 v.z = (255.0f * (v.z - mn)) / den; v.w = (255.0f * (v.w - mn)) / den;
@@ -144,66 +164,56 @@ k_blur_tma(const __grid_constant__ CUtensorMap tmap, BlurArgs a, Taps taps, int 
             }
             __syncthreads();
         }
-        const bool left = x0 == 0, right = x0 + TB_TW + C > a.w, top = y0 == 0, bottom = y0 + TB_TH + C > a.h;
-        if (left || right) {  // block-uniform.  Mirror rule of convolution.cl:41-50: columns first ...
-            if (left) {
-                for (int i = tid; i < BH * LW; i += TB_THREADS) {
-                    const int ty = i / LW, tx = i - ty * LW;
-                    const int gx = tx - LW;                 // < 0
-                    const int mx = -gx - 1, sx = mx + LW;   // source column inside the tile
-                    if (mx < a.w && sx < BW) tile[ty * BW + tx] = tile[ty * BW + sx];
-                }
+        // horizontal mirror rule of convolution.cl:41-50 on the staged rows (tiles touching the left / right edge)
+        const bool left = x0 == 0, right = x0 + TB_TW + C > a.w;
+        if (left) {
+            for (int i = tid; i < nrows * LW; i += TB_THREADS) {
+                const int ty = i / LW, tx = i - ty * LW;
+                const int gx = tx - LW;                 // < 0
+                const int mx = -gx - 1, sx = mx + LW;   // source column inside the tile
+                if (mx < a.w && sx < BW) tile[ty * BW + tx] = tile[ty * BW + sx];
             }
-            if (right) {
-                const int txr = a.w - x0 + LW;              // first tile column beyond the image
-                const int nr = BW - txr;
-                for (int i = tid; i < BH * nr; i += TB_THREADS) {
-                    const int ty = i / nr, tx = txr + (i - ty * nr);
-                    const int gx = x0 - LW + tx;            // >= w
-                    const int mx = 2 * a.w - 1 - gx, sx = mx - x0 + LW;
-                    if (mx >= 0 && sx >= 0) tile[ty * BW + tx] = tile[ty * BW + sx];
-                }
-            }
-            __syncthreads();
         }
-        if (top || bottom) {  // ... then whole rows
-            if (top) {
-                for (int i = tid; i < C * BW; i += TB_THREADS) {
-                    const int ty = i / BW, tx = i - ty * BW;
-                    const int my = C - ty - 1, sy = my + C;  // gy = ty - C < 0 -> row -gy-1
-                    if (my < a.h && sy < BH) tile[ty * BW + tx] = tile[sy * BW + tx];
-                }
+        if (right) {
+            const int txr = a.w - x0 + LW;              // first tile column beyond the image
+            const int nr = BW - txr;
+            for (int i = tid; i < nrows * nr; i += TB_THREADS) {
+                const int ty = i / nr, tx = txr + (i - ty * nr);
+                const int gx = x0 - LW + tx;            // >= w
+                const int mx = 2 * a.w - 1 - gx, sx = mx - x0 + LW;
+                if (mx >= 0 && sx >= 0) tile[ty * BW + tx] = tile[ty * BW + sx];
             }
-            if (bottom) {
-                const int tyb = a.h - y0 + C;               // first tile row beyond the image
-                const int nb = BH - tyb;
-                for (int i = tid; i < nb * BW; i += TB_THREADS) {
-                    const int r = i / BW, tx = i - r * BW;
-                    const int ty = tyb + r, gy = y0 - C + ty;
-                    const int my = 2 * a.h - 1 - gy, sy = my - y0 + C;
-                    if (my >= 0 && sy >= 0) tile[ty * BW + tx] = tile[sy * BW + tx];
-                }
-            }
-            __syncthreads();
         }
-        // ---- horizontal pass: task q -> (row = q % BH, segment = q / BH) ------------------------------
-        // (splitting the last, partly filled round into half-size tasks was measured slower: 53.0 vs 51.8 us)
-        for (int q = tid; q < BH * NSEG; q += TB_THREADS) {
-            const int seg = q / BH, row = q - seg * BH;
-            tb_row_task<C, RH, DELTA>(tile + row * BW + seg * RH, hbuf + row * TB_HP + seg * RH, taps);
+        if (cont || left || right) __syncthreads();     // halo carry / patches done before the row pass
+        // ---- horizontal pass: task q -> (row = q % nrows, segment = q / nrows) --------------------------
+        for (int q = tid; q < nrows * NSEG; q += TB_THREADS) {
+            const int seg = q / nrows, row = q - seg * nrows;
+            tb_row_task<C, RH, DELTA>(tile + row * BW + seg * RH, hbuf + (hrow0 + row) * TB_HP + seg * RH, taps);
         }
         __syncthreads();
-        // the staged tile is dead (the DoG centre is re-read from global/L2): prefetch the next one
-        if (tid == 0 && t + (int)gridDim.x < ntiles) {
-            const int tn = t + gridDim.x;
-            const int nx0 = (tn % ntx) * TB_TW, ny0 = (tn / ntx) * TB_TH;
+        // the staged rows are dead (the DoG centre is re-read from global/L2): prefetch the next tile's rows
+        if (tid == 0 && t + 1 < t_end) {
+            const int tn = t + 1, nyi = tn % nty;
+            const int nx0 = (tn / nty) * TB_TW, ny0 = nyi * TB_TH;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic accesses above -> async write
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-                         "r"((uint32_t)(BW * BH * sizeof(float))) : "memory");
-            asm volatile(
-                "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                ::"r"(smem_u32(tile)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(nx0 - C - DELTA), "r"(ny0 - C),
-                "r"(smem_u32(bar)) : "memory");
+            if (nyi != 0) tb_issue_load<BW>(&tmap_c, tile, bar, nx0 - C - DELTA, ny0 + C, TB_TH);
+            else tb_issue_load<BW>(&tmap, tile, bar, nx0 - C - DELTA, ny0 - C, BH);
+        }
+        // vertical mirror rule on the row-pass results (the row pass commutes with mirroring rows): hbuf rows whose
+        // image row is above / below the image are copies of the mirrored image row's hbuf row
+        const bool top = y0 == 0, bottom = y0 + TB_TH + C > a.h;
+        if (top || bottom) {
+            for (int i = tid; i < BH * (TB_TW / 4); i += TB_THREADS) {
+                const int hr = i / (TB_TW / 4), c4 = i - hr * (TB_TW / 4);
+                const int gy = y0 - C + hr;
+                if (gy < 0 || gy >= a.h) {
+                    const int my = (gy < 0) ? -gy - 1 : 2 * a.h - 1 - gy;
+                    const int sr = my - y0 + C;
+                    if (my >= 0 && my < a.h && sr >= 0 && sr < BH)
+                        reinterpret_cast<float4 *>(hbuf + hr * TB_HP)[c4] = reinterpret_cast<const float4 *>(hbuf + sr * TB_HP)[c4];
+                }
+            }
+            __syncthreads();
         }
         // ---- vertical pass: thread -> CV adjacent columns x RV rows (CV*RV independent FMA chains) -------
         constexpr int CV = TB_TW / 32;  // 4 columns (LDS.128 / STG.128) on 128-wide tiles, 2 on 64-wide
@@ -304,7 +314,7 @@ k_blur_tma(const __grid_constant__ CUtensorMap tmap, BlurArgs a, Taps taps, int 
                 }
             }
         }
-        __syncthreads();  // hbuf is reused by the next tile's row pass
+        __syncthreads();  // hbuf is reused (halo carry / row pass) by the next tile
     }
 }
 
@@ -346,12 +356,13 @@ static inline int tb_tile_w(int w, int h) {
     return n128 >= 2 * 148 ? 128 : 64;
 }
 
-static int tb_encode(CUtensorMap *map, const float *base, int w, int h, int pitch, int C) {
+// rows < 0: the full box (TH + 2C rows, first tile of a vertical run); rows > 0: that many rows (continuation)
+static int tb_encode(CUtensorMap *map, const float *base, int w, int h, int pitch, int C, int rows = -1) {
     tb_encode_fn enc = tb_get_encode();
     if (!enc) return -1;
     cuuint64_t gdim[2] = {(cuuint64_t)w, (cuuint64_t)h};
     cuuint64_t gstride[1] = {(cuuint64_t)pitch * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)tb_box_w(C, tb_tile_w(w, h)), (cuuint32_t)tb_box_h(C)};
+    cuuint32_t box[2] = {(cuuint32_t)tb_box_w(C, tb_tile_w(w, h)), (cuuint32_t)(rows > 0 ? rows : tb_box_h(C))};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, gdim, gstride, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -360,7 +371,8 @@ static int tb_encode(CUtensorMap *map, const float *base, int w, int h, int pitc
 }
 
 template <int C, int MODE, int TW>
-static cudaError_t tb_launch_tw(cudaStream_t st, const CUtensorMap &map, const BlurArgs &a, const Taps &taps) {
+static cudaError_t tb_launch_tw(cudaStream_t st, const CUtensorMap &map, const CUtensorMap &map_c, const BlurArgs &a,
+                                const Taps &taps) {
     static bool attr_done[64] = {};  // per device: the attribute belongs to the function on the current device
     int dev = 0;
     cudaGetDevice(&dev);
@@ -383,25 +395,27 @@ static cudaError_t tb_launch_tw(cudaStream_t st, const CUtensorMap &map, const B
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, k_blur_tma<C, MODE, TW>, map, a, taps, ntx, ntiles);
+    return cudaLaunchKernelEx(&cfg, k_blur_tma<C, MODE, TW>, map, map_c, a, taps, nty, ntiles);
 }
 
 template <int C, int MODE>
-static cudaError_t tb_launch_one(cudaStream_t st, const CUtensorMap &map, const BlurArgs &a, const Taps &taps) {
-    if (tb_tile_w(a.w, a.h) == 128) return tb_launch_tw<C, MODE, 128>(st, map, a, taps);
-    return tb_launch_tw<C, MODE, 64>(st, map, a, taps);
+static cudaError_t tb_launch_one(cudaStream_t st, const CUtensorMap &map, const CUtensorMap &map_c, const BlurArgs &a,
+                                 const Taps &taps) {
+    if (tb_tile_w(a.w, a.h) == 128) return tb_launch_tw<C, MODE, 128>(st, map, map_c, a, taps);
+    return tb_launch_tw<C, MODE, 64>(st, map, map_c, a, taps);
 }
 
-static cudaError_t tb_launch(cudaStream_t st, const CUtensorMap &map, const BlurArgs &a, const Taps &taps, int mode) {
+static cudaError_t tb_launch(cudaStream_t st, const CUtensorMap &map, const CUtensorMap &map_c, const BlurArgs &a,
+                             const Taps &taps, int mode) {
     const int C = a.ntaps >> 1;
-    if (mode == TB_DOG_HALF) return tb_launch_one<8, TB_DOG_HALF>(st, map, a, taps);
-    if (mode == TB_NORM) return tb_launch_one<7, TB_NORM>(st, map, a, taps);
+    if (mode == TB_DOG_HALF) return tb_launch_one<8, TB_DOG_HALF>(st, map, map_c, a, taps);
+    if (mode == TB_NORM) return tb_launch_one<7, TB_NORM>(st, map, map_c, a, taps);
     switch (C) {
-    case 5: return tb_launch_one<5, TB_DOG>(st, map, a, taps);
-    case 7: return tb_launch_one<7, TB_DOG>(st, map, a, taps);
-    case 8: return tb_launch_one<8, TB_DOG>(st, map, a, taps);
-    case 10: return tb_launch_one<10, TB_DOG>(st, map, a, taps);
-    case 13: return tb_launch_one<13, TB_DOG>(st, map, a, taps);
+    case 5: return tb_launch_one<5, TB_DOG>(st, map, map_c, a, taps);
+    case 7: return tb_launch_one<7, TB_DOG>(st, map, map_c, a, taps);
+    case 8: return tb_launch_one<8, TB_DOG>(st, map, map_c, a, taps);
+    case 10: return tb_launch_one<10, TB_DOG>(st, map, map_c, a, taps);
+    case 13: return tb_launch_one<13, TB_DOG>(st, map, map_c, a, taps);
     }
     return cudaErrorInvalidValue;
 }

@@ -100,6 +100,14 @@ static void gaussian_taps(double sigma, int size, float *out) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// the two TMA boxes of a source plane: full (TH + 2C rows) and continuation (TH rows), k_blur_tma.cuh
+struct TbMaps {
+    CUtensorMap full, cont;
+};
+static int tb_encode_pair(TbMaps *m, const float *base, int w, int h, int pitch, int C) {
+    return tb_encode(&m->full, base, w, h, pitch, C) || tb_encode(&m->cont, base, w, h, pitch, C, TB_TH);
+}
+
 struct Event {
     std::string name;
     cudaEvent_t a, b;
@@ -142,9 +150,9 @@ struct siftb_plan {
     int cnt_ints = 0;
     bool profile = false;
     uint64_t launches = 0;
-    CUtensorMap tmaps[MAX_OCT][5];  // source G[s] of octave o, box for taps[s]
+    TbMaps tmaps[MAX_OCT][5];  // source G[s] of octave o, boxes for taps[s]
     bool tmaps_ok[MAX_OCT][5] = {};
-    CUtensorMap tmap_raws[2], tmap_img;  // first blur: from the host-staging buffers / the converted fp32 plane
+    TbMaps tmap_raws[2], tmap_img;  // first blur: from the host-staging buffers / the converted fp32 plane
     bool tmap_raw_ok = false, tmap_img_ok = false;
     int force_generic = 0;
     std::vector<Event> events;
@@ -298,11 +306,11 @@ static int plan_create_impl(siftb_plan *p) {
         for (int o = 0; o < p->n_oct; o++)
             for (int s = 0; s < 5; s++)
                 if (tb_supported(p->ntaps[s], s == kScales - 1 && o + 1 < p->n_oct ? TB_DOG_HALF : TB_DOG))
-                    p->tmaps_ok[o][s] = tb_encode(&p->tmaps[o][s], p->G[s], p->ow[o], p->oh[o], p->opitch[o], p->ntaps[s] >> 1) == 0;
+                    p->tmaps_ok[o][s] = tb_encode_pair(&p->tmaps[o][s], p->G[s], p->ow[o], p->oh[o], p->opitch[o], p->ntaps[s] >> 1) == 0;
         if (tb_supported(p->ntaps[5], TB_NORM) && p->w % 4 == 0) {
-            p->tmap_raw_ok = tb_encode(&p->tmap_raws[0], (const float *)p->d_raws[0], p->w, p->h, p->w, p->ntaps[5] >> 1) == 0 &&
-                             tb_encode(&p->tmap_raws[1], (const float *)p->d_raws[1], p->w, p->h, p->w, p->ntaps[5] >> 1) == 0;
-            if (p->d_img) p->tmap_img_ok = tb_encode(&p->tmap_img, p->d_img, p->w, p->h, p->w, p->ntaps[5] >> 1) == 0;
+            p->tmap_raw_ok = tb_encode_pair(&p->tmap_raws[0], (const float *)p->d_raws[0], p->w, p->h, p->w, p->ntaps[5] >> 1) == 0 &&
+                             tb_encode_pair(&p->tmap_raws[1], (const float *)p->d_raws[1], p->w, p->h, p->w, p->ntaps[5] >> 1) == 0;
+            if (p->d_img) p->tmap_img_ok = tb_encode_pair(&p->tmap_img, p->d_img, p->w, p->h, p->w, p->ntaps[5] >> 1) == 0;
         }
     }
     p->cnt_ints = 1 + 13 * p->n_oct + 2 + 2;  // ... + min/max + {refined, extra} totals
@@ -365,7 +373,7 @@ extern "C" int siftb_plan_set_profile(siftb_plan *p, int enable) {
 // premap: tensor map already encoded for (in, w, h, in_pitch, C) or null (encoded here).
 static int launch_blur(cudaStream_t st, const float *in, int in_pitch, int w, int h, float *outG, int out_pitch,
                        float *outD, float *outHalf, int half_pitch, const Taps &taps, int ntaps,
-                       const unsigned *norm_mm, const CUtensorMap *premap = nullptr, int force_generic = 0) {
+                       const unsigned *norm_mm, const TbMaps *premap = nullptr, int force_generic = 0) {
     BlurArgs a;
     a.in = in; a.in_pitch = in_pitch; a.outG = outG; a.out_pitch = out_pitch; a.outD = outD;
     a.outHalf = outHalf; a.half_pitch = half_pitch; a.half_w = w / 2; a.half_h = h / 2;
@@ -377,12 +385,12 @@ static int launch_blur(cudaStream_t st, const float *in, int in_pitch, int w, in
     const bool out_ok = (out_pitch % 4 == 0) && (((uintptr_t)outG & 15) == 0) && (!outD || ((uintptr_t)outD & 15) == 0);
     if (!force_generic && mode >= 0 && tb_supported(ntaps, mode) && tb_source_ok(in, in_pitch) && out_ok &&
         tb_get_encode()) {
-        CUtensorMap local;
+        TbMaps local;
         if (!premap) {
-            if (tb_encode(&local, in, w, h, in_pitch, ntaps >> 1)) return fail(SIFTB_ECUDA, "cuTensorMapEncodeTiled failed");
+            if (tb_encode_pair(&local, in, w, h, in_pitch, ntaps >> 1)) return fail(SIFTB_ECUDA, "cuTensorMapEncodeTiled failed");
             premap = &local;
         }
-        CK(tb_launch(st, *premap, a, taps, mode));
+        CK(tb_launch(st, premap->full, premap->cont, a, taps, mode));
         return 0;
     }
     dim3 grid((w + BLUR_TW - 1) / BLUR_TW, (h + BLUR_TH - 1) / BLUR_TH);
@@ -493,7 +501,7 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
     }
     {   // normalize fused into the initial blur (sigma = sqrt(init^2 - 0.5^2)), plan.py:525-539
         ProfScope ps(p, "normalize + init blur");
-        const CUtensorMap *pm = nullptr;
+        const TbMaps *pm = nullptr;
         if (img == (const float *)p->d_raws[slot] && p->tmap_raw_ok) pm = &p->tmap_raws[slot];
         else if (img == p->d_img && p->tmap_img_ok) pm = &p->tmap_img;
         if ((rc = launch_blur(st, img, p->w, p->w, p->h, p->G[0], p->opitch[0], nullptr, nullptr, 0, p->taps[5],

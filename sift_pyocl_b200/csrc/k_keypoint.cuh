@@ -105,20 +105,34 @@ __global__ void __launch_bounds__(256) k_orient(OctTable T, float4 *__restrict__
         hist[lane] = 0.0f;
         if (lane < 4) hist[32 + lane] = 0.0f;
         __syncwarp();
+        // the gradient / orientation values of chunk c+1 are requested before chunk c is evaluated and committed
+        // (L2 / DRAM gathers: ncu showed the warps mostly waiting on these loads)
+        float n_gval = 0.0f, n_ang = 0.0f;
+        if (lane < total) {
+            const int rr = lane / ncols;
+            const long q = (long)(rmin + rr) * Gpitch + cmin + (lane - rr * ncols);
+            n_gval = grad[q];
+            n_ang = ori[q];
+        }
         for (int base = 0; base < total; base += 32) {
             const int idx = base + lane;
+            const float gval = n_gval, angle = n_ang;
+            if (idx + 32 < total) {
+                const int rr = (idx + 32) / ncols;
+                const long q = (long)(rmin + rr) * Gpitch + cmin + ((idx + 32) - rr * ncols);
+                n_gval = grad[q];
+                n_ang = ori[q];
+            }
             int bin = -1;
             float w = 0.0f;
             if (idx < total) {
                 const int rr = idx / ncols;
                 const int r = rmin + rr, c = cmin + (idx - rr * ncols);
-                const float gval = grad[(long)r * Gpitch + c];
                 float dif = ((float)r - k.y);
                 float distsq = dif * dif;
                 dif = ((float)c - k.z);
                 distsq += dif * dif;
                 if (gval > 0.0f && distsq < rad2) {
-                    const float angle = ori[(long)r * Gpitch + c];
                     int b = (int)(36.0f * ((angle + SIFTB_M_PI_F) + 0.001f) / (2.0f * SIFTB_M_PI_F));
                     if (b >= 0 && b <= 36) {
                         bin = min(b, 35);

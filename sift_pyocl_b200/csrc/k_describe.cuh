@@ -114,33 +114,51 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ hist, DescRo
     // warp-uniform trip count: the longest of the 4 octets
     const int passes_max = __reduce_max_sync(0xffffffffu, my_passes);
     int rcur = 0;
+    // Sample of this lane in pass pp: window coordinates and (if the pixel is inside the image) its gradient /
+    // orientation values.  The values of pass p+1 are requested before pass p is evaluated and committed, so the
+    // L2 / DRAM gather latency overlaps the commit loop (ncu: these loads were the top stall of the kernel).
+    int n_i = 0, n_j = 0;
+    bool n_in = false;
+    float n_g = 0.0f, n_o = 0.0f;
+    auto fetch = [&](int pp) {
+        n_in = false;
+        if (pp < my_passes) {
+            bool in_window;
+            if (tabled) {
+                while (pp >= rows.pfx[rcur + 1]) rcur++;
+                n_i = rcur - iradius;
+                n_j = rows.jlo[rcur] + ((pp - rows.pfx[rcur]) << 3) + l8;
+                in_window = n_j <= iradius;
+            } else {
+                const int t = pp * 8 + l8, ti = t / nrows;
+                n_i = ti - iradius;
+                n_j = (t - ti * nrows) - iradius;
+                in_window = t < nrows * nrows;
+            }
+            n_in = in_window && (irow + n_i) >= 0 && (irow + n_i) < grad_height && (icol + n_j) >= 0 &&
+                   (icol + n_j) < grad_width;
+            if (n_in) {
+                const long q = (long)(irow + n_i) * pitch + (icol + n_j);
+                n_g = grad[q];
+                n_o = orim[q];
+            }
+        }
+    };
+    fetch(0);
     for (int p = 0; p < passes_max; p++) {
         bool valid = false;
         DescRec rec;
-        int i = 0, j = 0;
-        bool in_window = false;
-        if (p < my_passes) {
-            if (tabled) {
-                while (p >= rows.pfx[rcur + 1]) rcur++;
-                i = rcur - iradius;
-                j = rows.jlo[rcur] + ((p - rows.pfx[rcur]) << 3) + l8;
-                in_window = j <= iradius;
-            } else {
-                const int t = p * 8 + l8, ti = t / nrows;
-                i = ti - iradius;
-                j = (t - ti * nrows) - iradius;
-                in_window = t < nrows * nrows;
-            }
-        }
-        if (in_window) {
+        const int i = n_i, j = n_j;
+        const bool in_image = n_in;
+        const float g_val = n_g, o_val = n_o;
+        fetch(p + 1);
+        if (in_image) {
             const float rx = ((cosine * (float)i - sine * (float)j) - drow) / spacing + 1.5f;
             const float cx = ((sine * (float)i + cosine * (float)j) - dcol) / spacing + 1.5f;
-            if ((rx > -1.0f && rx < 4.0f && cx > -1.0f && cx < 4.0f && (irow + i) >= 0 && (irow + i) < grad_height &&
-                 (icol + j) >= 0 && (icol + j) < grad_width)) {
-                const long q = (long)(irow + i) * pitch + (icol + j);
+            if (rx > -1.0f && rx < 4.0f && cx > -1.0f && cx < 4.0f) {
                 const float er = rx - 1.5f, ec = cx - 1.5f;
-                const float mag = grad[q] * cr_expf(-0.125f * (er * er + ec * ec));
-                float ori = orim[q] - angle;
+                const float mag = g_val * cr_expf(-0.125f * (er * er + ec * ec));
+                float ori = o_val - angle;
                 while (ori > 2.0f * SIFTB_M_PI_F) ori -= 2.0f * SIFTB_M_PI_F;
                 while (ori < 0.0f) ori += 2.0f * SIFTB_M_PI_F;
                 const float oval = (4.0f * ori) * SIFTB_M_1_PI_F;

@@ -32,16 +32,18 @@ struct DescRows {          // per-octet table of the window rows: only the j-int
     short pfx[DESC_MAXROWS + 1];   // exclusive prefix sum of the number of 8-sample passes per row
 };
 
-// Per-sample record staged in shared memory by the evaluating lane, laid out BY RESULT PARITY so that the lane of
-// parity class (pr, pc, po) picks its operands with fixed offsets: the cell with row parity pr / column parity
-// pc, the row weight of the row with parity pr, the column factor of the column with parity pc, the orientation
-// bin with parity po and its factor.
-struct DescRec {
-    uint32_t cells;   // byte (pr*2+pc): hist offset/4 of cell (r, c), or 0xff when that neighbour is outside the 4x4 grid
-    uint32_t obins;   // byte po: orientation bin of parity po; byte 2: 1 when both terms go to the same bin
-    float rwp[2];     // mag*(1-rfrac) / mag*rfrac, indexed by the parity of the row they go to
-    float cfp[2];     // (1-cfrac) / cfrac, indexed by the parity of the column
-    float ow[2];      // (1-ofrac) / ofrac, indexed by the parity of the orientation bin (in order when byte 2 set)
+// Staging area of one octet for one pass (8 samples): the evaluating lane s writes, for each of the 8 parity
+// classes p = (row&1)<<2 | (col&1)<<1 | (ori&1), the ONE contribution of sample s to a bin of that class as
+// (byte offset of the bin inside the octet's histogram, value).  A sample feeds at most 8 bins (2 rows x 2
+// columns x 2 orientations of the trilinear interpolation) and those always differ in all three parities, so
+// every class receives exactly one (possibly null) term per sample.  Null terms (neighbour cell outside the 4x4
+// grid, sample rejected by the reference's tests) are stored as value +0.0 on the class's home bin: every
+// histogram term is >= +0, so adding +0.0 is an exact no-op.
+// Rows are 10 float2 apart (80 B) and octets 704 B apart: the 8 lanes of an octet then store their 16-byte
+// chunks to 8 different bank quads, and the per-class 8-byte loads of two neighbouring octets do not collide.
+struct __align__(16) DescStage {
+    float2 e[8][10];
+    float2 pad[8];
 };
 
 // One warp, 4 keypoints (octet g handles kp[g] when act is true for that octet).
@@ -49,14 +51,13 @@ struct DescRec {
 // hist layout: bin (r, c, o) lives at 36*r + 8*c + o (rows padded by 4 floats), so that the 8 lanes of an octet
 // (2 rows x 2 columns x 2 orientations) always hit 8 different shared-memory banks.
 #define DESC_HIDX(i) ((i) + 4 * ((i) >> 5))  /* descriptor index i = (r*4+c)*8+o -> hist slot */
-__device__ __forceinline__ void describe_octets(float *__restrict__ hist, DescRows &rows, DescRec *__restrict__ recs,
+__device__ __forceinline__ void describe_octets(float *__restrict__ hist, DescRows &rows, DescStage &stage,
                                                 bool act, const float4 k,
                                                 const float *__restrict__ grad, const float *__restrict__ orim,
                                                 int pitch, int grad_width, int grad_height, int octsize,
                                                 uint8_t *out128) {
     const int lane = threadIdx.x & 31, l8 = lane & 7, obase = lane & 24;
     const unsigned omask = 0xffu << obase;  // lanes of my octet
-    const int pr = (l8 >> 2) & 1, pc = (l8 >> 1) & 1, po = l8 & 1;  // parity class of this lane
     for (int i = l8; i < 140; i += 8) hist[i] = 0.0f;
     // keypoints_cpu.cl:55-61
     const float row = k.y / (float)octsize, col = k.x / (float)octsize, angle = k.w;
@@ -146,12 +147,14 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ hist, DescRo
     };
     fetch(0);
     for (int p = 0; p < passes_max; p++) {
-        bool valid = false;
-        DescRec rec;
         const int i = n_i, j = n_j;
         const bool in_image = n_in;
         const float g_val = n_g, o_val = n_o;
         fetch(p + 1);
+        // terms of this lane's sample, indexed by the parity of the row / column / orientation bin they go to;
+        // the defaults describe a null sample
+        float rw_e = 0.0f, rw_o = 0.0f, cf_e = 0.0f, cf_o = 0.0f, ow_e = 0.0f, ow_o = 0.0f;
+        int ra_e = 0, ra_o = 4 * 36, ca_e = 0, ca_o = 4 * 8, oa_e = 0, oa_o = 4;  // byte offsets, home cell
         if (in_image) {
             const float rx = ((cosine * (float)i - sine * (float)j) - drow) / spacing + 1.5f;
             const float cx = ((sine * (float)i + cosine * (float)j) - dcol) / spacing + 1.5f;
@@ -167,64 +170,52 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ hist, DescRo
                 const int oi = (int)((oval >= 0.0f) ? oval : oval - 1.0f);
                 const float rfrac = rx - (float)ri, cfrac = cx - (float)ci, ofrac = oval - (float)oi;
                 if ((ri >= -1 && ri < 4 && oi >= 0 && oi <= 8 && rfrac >= 0.0f && rfrac <= 1.0f)) {
-                    valid = true;
-                    const int o0 = (oi >= 8) ? 0 : oi;  // oindex = oi + orr; if (oindex >= 8) oindex = 0
-                    const int o1 = (oi + 1 >= 8) ? 0 : oi + 1;
-                    const int rp = ri & 1, cpp = ci & 1;  // parity of row ri / column ci (ri = -1 -> 1)
-                    const float rw0 = mag * (1.0f - rfrac);  // rweight for r == 0 -> row ri
-                    const float rw1 = mag * rfrac;           // rweight for r == 1 -> row ri + 1
+                    // rows ri (weight mag*(1-rfrac)) and ri+1 (mag*rfrac): the even one and the odd one
+                    const float rw0 = mag * (1.0f - rfrac), rw1 = mag * rfrac;
+                    const int rodd = ri & 1, r_e = ri + rodd, r_o = ri + 1 - rodd;
+                    if ((unsigned)r_e < 4u) { rw_e = rodd ? rw1 : rw0; ra_e = 4 * 36 * r_e; }
+                    if ((unsigned)r_o < 4u) { rw_o = rodd ? rw0 : rw1; ra_o = 4 * 36 * r_o; }
                     const float cf0 = 1.0f - cfrac;
-                    rec.rwp[0] = rp ? rw1 : rw0;
-                    rec.rwp[1] = rp ? rw0 : rw1;
-                    rec.cfp[0] = cpp ? cfrac : cf0;
-                    rec.cfp[1] = cpp ? cf0 : cfrac;
-                    uint32_t cells = 0;
-#pragma unroll
-                    for (int d = 0; d < 4; d++) {
-                        const int rr = ri + (d >> 1), cc = ci + (d & 1);
-                        // stored as the hist offset / 4 of the cell: 9*rr + 2*cc (0..33), 0xff = outside
-                        const uint32_t cell = (rr >= 0 && rr < 4 && cc >= 0 && cc < 4) ? (uint32_t)(9 * rr + 2 * cc) : 0xffu;
-                        cells |= cell << (8 * (((rr & 1) << 1) | (cc & 1)));
-                    }
-                    rec.cells = cells;
-                    if (o0 != o1) {
-                        const float of0 = 1.0f - ofrac;
-                        const bool odd = o0 & 1;  // o0 and o1 have different parities
-                        rec.ow[0] = odd ? ofrac : of0;
-                        rec.ow[1] = odd ? of0 : ofrac;
-                        rec.obins = odd ? ((uint32_t)o1 | ((uint32_t)o0 << 8)) : ((uint32_t)o0 | ((uint32_t)o1 << 8));
-                    } else {  // ori == 2*pi exactly: both terms go to bin o0, first (1-ofrac) then ofrac
-                        rec.ow[0] = 1.0f - ofrac;
-                        rec.ow[1] = ofrac;
-                        rec.obins = (uint32_t)o0 | ((uint32_t)o0 << 8) | (1u << 16);
+                    const int codd = ci & 1, c_e = ci + codd, c_o = ci + 1 - codd;
+                    if ((unsigned)c_e < 4u) { cf_e = codd ? cfrac : cf0; ca_e = 4 * 8 * c_e; }
+                    if ((unsigned)c_o < 4u) { cf_o = codd ? cf0 : cfrac; ca_o = 4 * 8 * c_o; }
+                    const float of0 = 1.0f - ofrac;
+                    if (oi < 8) {
+                        const int o1 = (oi + 1) & 7;  // oindex = oi + orr; if (oindex >= 8) oindex = 0
+                        const bool oodd = oi & 1;
+                        ow_e = oodd ? ofrac : of0;
+                        ow_o = oodd ? of0 : ofrac;
+                        oa_e = 4 * (oodd ? o1 : oi);
+                        oa_o = 4 * (oodd ? oi : o1);
+                    } else {
+                        // oi == 8 <=> ori == 2*pi exactly (then oval == 8.0f and ofrac == 0): both terms go to
+                        // bin 0, cweight*(1-ofrac) then cweight*ofrac = +0 -- the second add is a no-op
+                        ow_e = of0;
+                        oa_e = 0;
                     }
                 }
             }
         }
-        // stage the valid samples of each octet, compacted in lane (= sample) order
-        const unsigned m = __ballot_sync(0xffffffffu, valid) & omask;
-        if (valid) recs[__popc(m & lanemask_lt())] = rec;
-        const int cnt = __popc(m);
-        const int cnt_max = __reduce_max_sync(0xffffffffu, cnt);
+        {
+            // (rweight * c-factor) * o-factor, in the reference's multiplication order (keypoints_cpu.cl:93-104)
+            const float cw_ee = rw_e * cf_e, cw_eo = rw_e * cf_o, cw_oe = rw_o * cf_e, cw_oo = rw_o * cf_o;
+            float4 *dst = reinterpret_cast<float4 *>(&stage.e[l8][0]);
+            dst[0] = make_float4(__int_as_float(ra_e + ca_e + oa_e), cw_ee * ow_e,
+                                 __int_as_float(ra_e + ca_e + oa_o), cw_ee * ow_o);
+            dst[1] = make_float4(__int_as_float(ra_e + ca_o + oa_e), cw_eo * ow_e,
+                                 __int_as_float(ra_e + ca_o + oa_o), cw_eo * ow_o);
+            dst[2] = make_float4(__int_as_float(ra_o + ca_e + oa_e), cw_oe * ow_e,
+                                 __int_as_float(ra_o + ca_e + oa_o), cw_oe * ow_o);
+            dst[3] = make_float4(__int_as_float(ra_o + ca_o + oa_e), cw_oo * ow_e,
+                                 __int_as_float(ra_o + ca_o + oa_o), cw_oo * ow_o);
+        }
         __syncwarp();
-        // commit them one at a time: lane (pr, pc, po) adds the one contribution of its parity class
-        // (fetching the operands of sample s+1 ahead of the add of sample s was measured slower: registers)
-        for (int sidx = 0; sidx < cnt_max; sidx++) {
-            if (sidx < cnt) {
-                const DescRec &r = recs[sidx];
-                const uint32_t cell = (r.cells >> (8 * ((pr << 1) | pc))) & 0xffu;
-                if (cell != 0xffu) {
-                    const float cweight = r.rwp[pr] * r.cfp[pc];
-                    const uint32_t ob = r.obins;
-                    float *hb = hist + cell * 4;
-                    if (!(ob >> 16)) {
-                        hb[(ob >> (8 * po)) & 0xffu] += cweight * r.ow[po];
-                    } else if (po == (int)(ob & 1u)) {
-                        hb[ob & 0xffu] += cweight * r.ow[0];
-                        hb[ob & 0xffu] += cweight * r.ow[1];
-                    }
-                }
-            }
+        // commit the 8 samples of the pass in sample order: lane (pr, pc, po) adds the one term of its class
+#pragma unroll
+        for (int sidx = 0; sidx < 8; sidx++) {
+            const float2 t = stage.e[sidx][l8];
+            float *bin = reinterpret_cast<float *>(reinterpret_cast<char *>(hist) + __float_as_int(t.x));
+            *bin += t.y;
         }
         __syncwarp();
     }
@@ -322,7 +313,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe(OctTable T, con
                                                                const int *__restrict__ order) {
     __shared__ float s_hist[DESC_WARPS * 4][DESC_HSTRIDE];
     __shared__ DescRows s_rows[DESC_WARPS * 4];
-    __shared__ DescRec s_recs[DESC_WARPS * 4][8];
+    __shared__ DescStage s_stage[DESC_WARPS * 4];
     const int lane = threadIdx.x & 31, l8 = lane & 7, obase = lane & 24;
     float *hist = s_hist[threadIdx.x >> 3];
     const int n = min(min(*n_base_p, cap) + *n_extra_p, cap);
@@ -351,7 +342,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe(OctTable T, con
         if (slot >= out_cap) act = false;
         KpRecord *o = out + (act ? slot : 0);
         if (act && l8 == 0) { o->x = k.x; o->y = k.y; o->scale = k.z; o->angle = k.w; }
-        describe_octets(hist, s_rows[threadIdx.x >> 3], s_recs[threadIdx.x >> 3], act, k, T.grad[oct][sc - 1],
+        describe_octets(hist, s_rows[threadIdx.x >> 3], s_stage[threadIdx.x >> 3], act, k, T.grad[oct][sc - 1],
                         T.ori[oct][sc - 1], T.pitch[oct], T.w[oct], T.h[oct], T.octsize[oct], o->desc);
     }
 }
@@ -363,7 +354,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 8) k_describe_rows(const floa
                                                                     int octsize, uint8_t *__restrict__ desc) {
     __shared__ float s_hist[DESC_WARPS * 4][DESC_HSTRIDE];
     __shared__ DescRows s_rows[DESC_WARPS * 4];
-    __shared__ DescRec s_recs[DESC_WARPS * 4][8];
+    __shared__ DescStage s_stage[DESC_WARPS * 4];
     float *hist = s_hist[threadIdx.x >> 3];
     const int noct = (gridDim.x * blockDim.x) >> 3;
     const int rounds = (n + noct - 1) / noct;
@@ -375,7 +366,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 8) k_describe_rows(const floa
             k = kp[gid0];
             act = k.y >= 0.0f;
         }
-        describe_octets(hist, s_rows[threadIdx.x >> 3], s_recs[threadIdx.x >> 3], act, k, grad, ori, pitch, w, h, octsize,
+        describe_octets(hist, s_rows[threadIdx.x >> 3], s_stage[threadIdx.x >> 3], act, k, grad, ori, pitch, w, h, octsize,
                         desc + 128L * (act ? gid0 : 0));
     }
 }

@@ -23,13 +23,13 @@
 #include "k_keypoint.cuh"
 
 #define DESC_WARPS 4  // warps per CTA -> 16 keypoints per CTA
-#define DESC_HSTRIDE 144  // floats between the histograms of two octets (140 used; 144 = 16 banks apart)
 
 #define DESC_MAXROWS 100  // window rows per keypoint handled by the interval table (iradius <= 49; default sigmas need 97)
 
-struct DescRows {          // per-octet table of the window rows: only the j-interval that can be valid
-    short jlo[DESC_MAXROWS];       // first candidate j of row i = r - iradius
-    short pfx[DESC_MAXROWS + 1];   // exclusive prefix sum of the number of 8-sample passes per row
+struct DescRows {          // per-octet table of the non-empty window rows: only the j-interval that can be valid
+    short i[DESC_MAXROWS];         // window row i (-iradius..iradius)
+    short jlo[DESC_MAXROWS];       // first candidate j of the row
+    short jhi[DESC_MAXROWS];       // last candidate j of the row
 };
 
 // Staging area of one octet for one pass (8 samples): the evaluating lane s writes, for each of the 8 parity
@@ -47,18 +47,22 @@ struct __align__(16) DescStage {
 };
 
 // One warp, 4 keypoints (octet g handles kp[g] when act is true for that octet).
-// hist: this octet's 128 floats in shared memory, index (r*4+c)*8 + o (the descriptor order).
-// hist layout: bin (r, c, o) lives at 36*r + 8*c + o (rows padded by 4 floats), so that the 8 lanes of an octet
-// (2 rows x 2 columns x 2 orientations) always hit 8 different shared-memory banks.
-#define DESC_HIDX(i) ((i) + 4 * ((i) >> 5))  /* descriptor index i = (r*4+c)*8+o -> hist slot */
-__device__ __forceinline__ void describe_octets(float *__restrict__ hist, DescRows &rows, DescStage &stage,
+// whist: the warp's 16 x 32 floats of histogram storage.  Octet g owns the bank group 8g..8g+7; bin (r, c, o)
+// lives in row (o>>1) + 4*(c>>1) + 8*(r>>1), bank 8g + 4*(r&1) + 2*(c&1) + (o&1): the 8 lanes of an octet (one
+// per parity class) and the 4 octets of the warp always hit 32 different banks -- every histogram access of the
+// commit loop is a single conflict-free wavefront.
+#define DESC_HOFF(i) /* descriptor index i = (r*4+c)*8+o -> float offset inside the octet's bank group */ \
+    (32 * ((((i) & 7) >> 1) + 4 * ((((i) >> 3) & 3) >> 1) + 8 * ((i) >> 6)) + 4 * (((i) >> 5) & 1) + 2 * (((i) >> 3) & 1) + ((i) & 1))
+__device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescRows &rows, DescStage &stage,
                                                 bool act, const float4 k,
                                                 const float *__restrict__ grad, const float *__restrict__ orim,
                                                 int pitch, int grad_width, int grad_height, int octsize,
                                                 uint8_t *out128) {
     const int lane = threadIdx.x & 31, l8 = lane & 7, obase = lane & 24;
     const unsigned omask = 0xffu << obase;  // lanes of my octet
-    for (int i = l8; i < 140; i += 8) hist[i] = 0.0f;
+    float *hist = whist + obase;            // bank group of my octet
+#pragma unroll
+    for (int r = 0; r < 16; r++) hist[32 * r + l8] = 0.0f;
     // keypoints_cpu.cl:55-61
     const float row = k.y / (float)octsize, col = k.x / (float)octsize, angle = k.w;
     const int irow = (int)(row + 0.5f), icol = (int)(col + 0.5f);
@@ -70,12 +74,18 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ hist, DescRo
     const int nrows = 2 * iradius + 1;  // 0 rows for an inactive octet
     const bool tabled = nrows <= DESC_MAXROWS;
     // ---- row table: the reference scans j = -R..R of every row and keeps the samples with rx, cx in (-1, 4)
-    // (keypoints_cpu.cl:66); those form one j-interval per row.  A conservative superset of it is computed
-    // here (real-valued bounds widened by a full sample on each side) so that only candidate samples are
-    // evaluated; every evaluated sample still goes through the reference's exact fp32 test.
-    int my_passes = 0;
+    // whose pixel is inside the image (keypoints_cpu.cl:66-67); those form one j-interval per row.  A
+    // conservative superset of it is computed here (real-valued bounds widened by a full sample on each side) so
+    // that only candidate samples are evaluated; every evaluated sample still goes through the reference's exact
+    // fp32 test.  Rows with an empty interval are dropped.
+    int my_passes = 0, nrc = 0;  // passes (8 samples each) of this octet, number of table rows
+    // untabled (enormous window, custom init_sigma): every row of the square that lies inside the image, full width
+    const int u_r0 = max(0, iradius - irow), u_r1 = min(nrows - 1, iradius + grad_height - 1 - irow);
+    const int u_jlo = max(-iradius, -icol), u_jhi = min(iradius, grad_width - 1 - icol);
     if (tabled) {
         const double L = 2.5 * (double)spacing, sn = (double)sine, cs = (double)cosine;
+        const bool use_sn = fabs(sn) > 1e-9, use_cs = fabs(cs) > 1e-9;
+        const double isn = 1.0 / sn, ics = 1.0 / cs;  // bounds are widened by a whole sample: 1 ulp is irrelevant
         for (int r = l8; r < nrows; r += 8) {
             const int i = r - iradius;
             double lo = -(double)iradius, hi = (double)iradius;
@@ -83,78 +93,94 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ hist, DescRo
             lo = fmax(lo, -(double)icol);
             hi = fmin(hi, (double)(grad_width - 1 - icol));
             const double A = cs * (double)i - (double)drow;  // |A - sn*j| < L
-            if (fabs(sn) > 1e-9) {
-                const double a = (A - L) / sn, b = (A + L) / sn;
+            if (use_sn) {
+                const double a = (A - L) * isn, b = (A + L) * isn;
                 lo = fmax(lo, fmin(a, b) - 1.0);
                 hi = fmin(hi, fmax(a, b) + 1.0);
             }
             const double B = sn * (double)i - (double)dcol;  // |B + cs*j| < L
-            if (fabs(cs) > 1e-9) {
-                const double a = (-L - B) / cs, b = (L - B) / cs;
+            if (use_cs) {
+                const double a = (-L - B) * ics, b = (L - B) * ics;
                 lo = fmax(lo, fmin(a, b) - 1.0);
                 hi = fmin(hi, fmax(a, b) + 1.0);
             }
             int jlo = (int)floor(lo), jhi = (int)ceil(hi);
-            jlo = max(jlo, -iradius);
-            jhi = min(jhi, iradius);
-            const int np = jhi >= jlo ? (jhi - jlo + 8) >> 3 : 0;
+            jlo = max(jlo, max(-iradius, -icol));
+            jhi = min(jhi, min(iradius, grad_width - 1 - icol));
+            if (jhi < jlo) { jlo = 1; jhi = 0; }  // empty (the real-valued bounds may not fit a short)
             rows.jlo[r] = (short)jlo;
-            rows.pfx[r + 1] = (short)np;  // counts first, scanned below
+            rows.jhi[r] = (short)jhi;
         }
         __syncwarp();
-        if (l8 == 0) {
-            int acc = 0;
-            rows.pfx[0] = 0;
-            for (int r = 0; r < nrows; r++) { acc += rows.pfx[r + 1]; rows.pfx[r + 1] = (short)acc; }
+        if (l8 == 0) {  // drop the empty rows (in place: the write index never overtakes the read index)
+            int n = 0, acc = 0;
+            for (int r = 0; r < nrows; r++) {
+                const int jlo = rows.jlo[r], jhi = rows.jhi[r];
+                if (jhi >= jlo) {
+                    rows.i[n] = (short)(r - iradius);
+                    rows.jlo[n] = (short)jlo;
+                    rows.jhi[n] = (short)jhi;
+                    n++;
+                    acc += (jhi - jlo + 8) >> 3;
+                }
+            }
+            nrc = n;
+            my_passes = acc;
         }
         __syncwarp();
-        my_passes = nrows > 0 ? rows.pfx[nrows] : 0;
-    } else {
-        my_passes = (nrows * nrows + 7) >> 3;  // enormous window: plain row-major scan of the whole square
+        nrc = __shfl_sync(0xffffffffu, nrc, obase);
+        my_passes = __shfl_sync(0xffffffffu, my_passes, obase);
+    } else if (u_r1 >= u_r0 && u_jhi >= u_jlo) {
+        nrc = u_r1 - u_r0 + 1;
+        my_passes = nrc * ((u_jhi - u_jlo + 8) >> 3);
     }
     // warp-uniform trip count: the longest of the 4 octets
     const int passes_max = __reduce_max_sync(0xffffffffu, my_passes);
-    int rcur = 0;
-    // Sample of this lane in pass pp: window coordinates and (if the pixel is inside the image) its gradient /
-    // orientation values.  The values of pass p+1 are requested before pass p is evaluated and committed, so the
-    // L2 / DRAM gather latency overlaps the commit loop (ncu: these loads were the top stall of the kernel).
-    int n_i = 0, n_j = 0;
+    // Octet-uniform cursor over the table: row rcur, next j of that row, last j of that row, pixel offset of
+    // (row, j = 0).  Sample of this lane in the next pass: window coordinates and (if it is a candidate) its
+    // gradient / orientation values.  The values of pass p+1 are requested before pass p is evaluated and
+    // committed, so the L2 / DRAM gather latency overlaps the commit loop.
+    int rcur = -1, jcur = 0, jend = -1, n_i = 0, n_j = 0;
+    long rowoff = 0;
     bool n_in = false;
     float n_g = 0.0f, n_o = 0.0f;
-    auto fetch = [&](int pp) {
-        n_in = false;
-        if (pp < my_passes) {
-            bool in_window;
-            if (tabled) {
-                while (pp >= rows.pfx[rcur + 1]) rcur++;
-                n_i = rcur - iradius;
-                n_j = rows.jlo[rcur] + ((pp - rows.pfx[rcur]) << 3) + l8;
-                in_window = n_j <= iradius;
-            } else {
-                const int t = pp * 8 + l8, ti = t / nrows;
-                n_i = ti - iradius;
-                n_j = (t - ti * nrows) - iradius;
-                in_window = t < nrows * nrows;
-            }
-            n_in = in_window && (irow + n_i) >= 0 && (irow + n_i) < grad_height && (icol + n_j) >= 0 &&
-                   (icol + n_j) < grad_width;
-            if (n_in) {
-                const long q = (long)(irow + n_i) * pitch + (icol + n_j);
-                n_g = grad[q];
-                n_o = orim[q];
+    auto fetch = [&]() {
+        if (jcur > jend) {  // next table row
+            rcur++;
+            if (rcur < nrc) {
+                if (tabled) {
+                    n_i = rows.i[rcur];
+                    jcur = rows.jlo[rcur];
+                    jend = rows.jhi[rcur];
+                } else {
+                    n_i = u_r0 + rcur - iradius;
+                    jcur = u_jlo;
+                    jend = u_jhi;
+                }
+                rowoff = (long)(irow + n_i) * pitch + icol;
+            } else {  // table exhausted: idle from now on
+                jcur = 0;
+                jend = -1;
             }
         }
+        n_j = jcur + l8;
+        n_in = n_j <= jend;
+        if (n_in) {
+            n_g = grad[rowoff + n_j];
+            n_o = orim[rowoff + n_j];
+        }
+        jcur += 8;
     };
-    fetch(0);
+    fetch();
     for (int p = 0; p < passes_max; p++) {
         const int i = n_i, j = n_j;
         const bool in_image = n_in;
         const float g_val = n_g, o_val = n_o;
-        fetch(p + 1);
+        fetch();
         // terms of this lane's sample, indexed by the parity of the row / column / orientation bin they go to;
         // the defaults describe a null sample
         float rw_e = 0.0f, rw_o = 0.0f, cf_e = 0.0f, cf_o = 0.0f, ow_e = 0.0f, ow_o = 0.0f;
-        int ra_e = 0, ra_o = 4 * 36, ca_e = 0, ca_o = 4 * 8, oa_e = 0, oa_o = 4;  // byte offsets, home cell
+        int ra_e = 0, ra_o = 16, ca_e = 0, ca_o = 8, oa_e = 0, oa_o = 4;  // byte offsets in the bank group, home cell
         if (in_image) {
             const float rx = ((cosine * (float)i - sine * (float)j) - drow) / spacing + 1.5f;
             const float cx = ((sine * (float)i + cosine * (float)j) - dcol) / spacing + 1.5f;
@@ -173,20 +199,20 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ hist, DescRo
                     // rows ri (weight mag*(1-rfrac)) and ri+1 (mag*rfrac): the even one and the odd one
                     const float rw0 = mag * (1.0f - rfrac), rw1 = mag * rfrac;
                     const int rodd = ri & 1, r_e = ri + rodd, r_o = ri + 1 - rodd;
-                    if ((unsigned)r_e < 4u) { rw_e = rodd ? rw1 : rw0; ra_e = 4 * 36 * r_e; }
-                    if ((unsigned)r_o < 4u) { rw_o = rodd ? rw0 : rw1; ra_o = 4 * 36 * r_o; }
+                    if ((unsigned)r_e < 4u) { rw_e = rodd ? rw1 : rw0; ra_e = 512 * r_e; }
+                    if ((unsigned)r_o < 4u) { rw_o = rodd ? rw0 : rw1; ra_o = 512 * r_o - 496; }
                     const float cf0 = 1.0f - cfrac;
                     const int codd = ci & 1, c_e = ci + codd, c_o = ci + 1 - codd;
-                    if ((unsigned)c_e < 4u) { cf_e = codd ? cfrac : cf0; ca_e = 4 * 8 * c_e; }
-                    if ((unsigned)c_o < 4u) { cf_o = codd ? cf0 : cfrac; ca_o = 4 * 8 * c_o; }
+                    if ((unsigned)c_e < 4u) { cf_e = codd ? cfrac : cf0; ca_e = 256 * c_e; }
+                    if ((unsigned)c_o < 4u) { cf_o = codd ? cf0 : cfrac; ca_o = 256 * c_o - 248; }
                     const float of0 = 1.0f - ofrac;
                     if (oi < 8) {
                         const int o1 = (oi + 1) & 7;  // oindex = oi + orr; if (oindex >= 8) oindex = 0
                         const bool oodd = oi & 1;
                         ow_e = oodd ? ofrac : of0;
                         ow_o = oodd ? of0 : ofrac;
-                        oa_e = 4 * (oodd ? o1 : oi);
-                        oa_o = 4 * (oodd ? oi : o1);
+                        oa_e = 64 * (oodd ? o1 : oi);
+                        oa_o = 64 * (oodd ? oi : o1) - 60;
                     } else {
                         // oi == 8 <=> ori == 2*pi exactly (then oval == 8.0f and ofrac == 0): both terms go to
                         // bin 0, cweight*(1-ofrac) then cweight*ofrac = +0 -- the second add is a no-op
@@ -221,16 +247,28 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ hist, DescRo
     }
     __syncwarp();
     // finish, keypoints_cpu.cl:127-160: each lane of the octet owns 16 consecutive descriptor entries
+    // i = 16*l8 + q, i.e. r = l8>>1, c = 2*(l8&1) + (q>>3), o = q&7
+    float *mine = hist + 32 * (4 * (l8 & 1) + 8 * (l8 >> 2)) + 4 * ((l8 >> 1) & 1);
+#define DESC_QOFF(q) (32 * (((q) & 7) >> 1) + 2 * ((q) >> 3) + ((q) & 1))
     float v[16];
 #pragma unroll
-    for (int q = 0; q < 16; q++) v[q] = hist[DESC_HIDX(l8 * 16 + q)];
+    for (int q = 0; q < 16; q++) v[q] = mine[DESC_QOFF(q)];
     __syncwarp();
 #pragma unroll
-    for (int q = 0; q < 16; q++) hist[l8 * 16 + q] = v[q] * v[q];
+    for (int q = 0; q < 16; q++) mine[DESC_QOFF(q)] = v[q] * v[q];
     __syncwarp();
+    // the sums of squares are sequential over i = 0..127 in the reference: one lane adds them in that order
+    auto ordered_sum = [&]() {
+        float acc = 0.0f;
+        for (int rc = 0; rc < 16; rc++) {
+            const float *cell = hist + 32 * (4 * ((rc & 3) >> 1) + 8 * (rc >> 3)) + 4 * ((rc >> 2) & 1) + 2 * (rc & 1);
+#pragma unroll
+            for (int o = 0; o < 8; o++) acc += cell[32 * (o >> 1) + (o & 1)];
+        }
+        return acc;
+    };
     float norm = 0.0f;
-    if (l8 == 0)
-        for (int i = 0; i < 128; i++) norm += hist[i];
+    if (l8 == 0) norm = ordered_sum();
     norm = cr_rsqrtf(__shfl_sync(0xffffffffu, norm, obase));
     bool changed = false;
     __syncwarp();
@@ -238,13 +276,12 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ hist, DescRo
     for (int q = 0; q < 16; q++) {
         v[q] *= norm;
         if (v[q] > 0.2f) { v[q] = 0.2f; changed = true; }
-        hist[l8 * 16 + q] = v[q] * v[q];
+        mine[DESC_QOFF(q)] = v[q] * v[q];
     }
     changed = (__ballot_sync(0xffffffffu, changed) & omask) != 0;
     __syncwarp();
     float norm2 = 0.0f;
-    if (l8 == 0 && changed)
-        for (int i = 0; i < 128; i++) norm2 += hist[i];
+    if (l8 == 0 && changed) norm2 = ordered_sum();
     norm2 = cr_rsqrtf(__shfl_sync(0xffffffffu, norm2, obase));
     if (changed) {
 #pragma unroll
@@ -311,11 +348,11 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe(OctTable T, con
                                                                const int *__restrict__ oct_offset,
                                                                int *__restrict__ oct_fill, int *__restrict__ queue,
                                                                const int *__restrict__ order) {
-    __shared__ float s_hist[DESC_WARPS * 4][DESC_HSTRIDE];
+    __shared__ float s_hist[DESC_WARPS][16 * 32];
     __shared__ DescRows s_rows[DESC_WARPS * 4];
     __shared__ DescStage s_stage[DESC_WARPS * 4];
     const int lane = threadIdx.x & 31, l8 = lane & 7, obase = lane & 24;
-    float *hist = s_hist[threadIdx.x >> 3];
+    float *hist = s_hist[threadIdx.x >> 5];
     const int n = min(min(*n_base_p, cap) + *n_extra_p, cap);
     // dynamic work queue: every warp fetches 4 keypoints at a time, so warps with small windows simply fetch
     // more often and the last wave is not quantised to the grid size
@@ -352,10 +389,10 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 8) k_describe_rows(const floa
                                                                     const float *__restrict__ ori, int pitch, int w,
                                                                     int h, const float4 *__restrict__ kp, int n,
                                                                     int octsize, uint8_t *__restrict__ desc) {
-    __shared__ float s_hist[DESC_WARPS * 4][DESC_HSTRIDE];
+    __shared__ float s_hist[DESC_WARPS][16 * 32];
     __shared__ DescRows s_rows[DESC_WARPS * 4];
     __shared__ DescStage s_stage[DESC_WARPS * 4];
-    float *hist = s_hist[threadIdx.x >> 3];
+    float *hist = s_hist[threadIdx.x >> 5];
     const int noct = (gridDim.x * blockDim.x) >> 3;
     const int rounds = (n + noct - 1) / noct;
     int gid0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;

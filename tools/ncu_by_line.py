@@ -43,7 +43,7 @@ for r in rows[hi + 1:]:
 tot = sum(v[0] for v in agg.values()); tots = sum(v[1] for v in agg.values())
 print("total warp-instr %.0f samples %.0f" % (tot, tots))
 src_cache = {}
-for key, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
+for key, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:int(__import__("os").environ.get("TOPN","45"))]:
     f, ln = key
     try:
         if f not in src_cache:

@@ -186,7 +186,7 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
             const float cx = ((sine * (float)i + cosine * (float)j) - dcol) / spacing + 1.5f;
             if (rx > -1.0f && rx < 4.0f && cx > -1.0f && cx < 4.0f) {
                 const float er = rx - 1.5f, ec = cx - 1.5f;
-                const float mag = g_val * cr_expf(-0.125f * (er * er + ec * ec));
+                const float mag = g_val * cr_expf_neg(-0.125f * (er * er + ec * ec));
                 float ori = o_val - angle;
                 while (ori > 2.0f * SIFTB_M_PI_F) ori -= 2.0f * SIFTB_M_PI_F;
                 while (ori < 0.0f) ori += 2.0f * SIFTB_M_PI_F;

@@ -106,28 +106,32 @@ __global__ void __launch_bounds__(256) k_orient(OctTable T, float4 *__restrict__
         if (lane < 4) hist[32 + lane] = 0.0f;
         __syncwarp();
         // the gradient / orientation values of chunk c+1 are requested before chunk c is evaluated and committed
-        // (L2 / DRAM gathers: ncu showed the warps mostly waiting on these loads)
+        // (L2 / DRAM gathers: ncu showed the warps mostly waiting on these loads).  idx -> (row, column) of the
+        // window: idx / ncols through an fp32 reciprocal, exact here because (idx + 0.5) / ncols is at least
+        // 0.5 / ncols away from an integer and idx < 2^20.
+        const float inv_ncols = 1.0f / (float)max(ncols, 1);
         float n_gval = 0.0f, n_ang = 0.0f;
-        if (lane < total) {
-            const int rr = lane / ncols;
-            const long q = (long)(rmin + rr) * Gpitch + cmin + (lane - rr * ncols);
-            n_gval = grad[q];
-            n_ang = ori[q];
-        }
-        for (int base = 0; base < total; base += 32) {
-            const int idx = base + lane;
-            const float gval = n_gval, angle = n_ang;
-            if (idx + 32 < total) {
-                const int rr = (idx + 32) / ncols;
-                const long q = (long)(rmin + rr) * Gpitch + cmin + ((idx + 32) - rr * ncols);
+        int n_r = 0, n_c = 0;
+        const bool big = total >= (1 << 20);  // warp-uniform; never with the default sigmas
+        auto locate = [&](int idx) {
+            const int rr = big ? idx / ncols : (int)(((float)idx + 0.5f) * inv_ncols);
+            n_r = rmin + rr;
+            n_c = cmin + (idx - rr * ncols);
+            if (idx < total) {
+                const long q = (long)n_r * Gpitch + n_c;
                 n_gval = grad[q];
                 n_ang = ori[q];
             }
+        };
+        locate(lane);
+        for (int base = 0; base < total; base += 32) {
+            const int idx = base + lane;
+            const float gval = n_gval, angle = n_ang;
+            const int r = n_r, c = n_c;
+            locate(idx + 32);
             int bin = -1;
             float w = 0.0f;
             if (idx < total) {
-                const int rr = idx / ncols;
-                const int r = rmin + rr, c = cmin + (idx - rr * ncols);
                 float dif = ((float)r - k.y);
                 float distsq = dif * dif;
                 dif = ((float)c - k.z);
@@ -136,7 +140,7 @@ __global__ void __launch_bounds__(256) k_orient(OctTable T, float4 *__restrict__
                     int b = (int)(36.0f * ((angle + SIFTB_M_PI_F) + 0.001f) / (2.0f * SIFTB_M_PI_F));
                     if (b >= 0 && b <= 36) {
                         bin = min(b, 35);
-                        w = cr_expf(-distsq / two_s2) * gval;
+                        w = cr_expf_neg(-distsq / two_s2) * gval;
                     }
                 }
             }
@@ -146,63 +150,89 @@ __global__ void __launch_bounds__(256) k_orient(OctTable T, float4 *__restrict__
                 const unsigned peers = __match_any_sync(0xffffffffu, bin);
                 const int rank = __popc(peers & lanemask_lt());
                 const int rounds = __reduce_max_sync(0xffffffffu, bin >= 0 ? rank : 0);
-                for (int r = 0; r <= rounds; r++) {
-                    if (bin >= 0 && rank == r) hist[bin] += w;
+                for (int rd = 0; rd <= rounds; rd++) {
+                    if (bin >= 0 && rank == rd) hist[bin] += w;
                     __syncwarp();
                 }
             }
         }
         // orientation_cpu.cl:100-108 -- six in-place smoothing passes.  In place means: bins 0..34 see
         // the OLD neighbours (prev is carried), bin 35 sees the NEW bin 0.  "/ 3.0" is a double division.
+        // x / 3.0 in double, rounded to fp32: q = x*(1/3) corrected once through the exact residual gives the same
+        // fp32 result as the IEEE division for EVERY fp32 x (exhaustive check, tools/div3_check.c)
+        auto third = [](float x) {
+            const double xd = (double)x, q0 = xd * (1.0 / 3.0);
+            return (float)fma(fma(-3.0, q0, xd), 1.0 / 3.0, q0);
+        };
         for (int j = 0; j < 6; j++) {
             const float a0 = hist[(lane + 35) % 36], b0 = hist[lane], c0 = hist[lane + 1];
             float a1 = 0.f, b1 = 0.f, c1 = 0.f;
             if (lane < 3) { a1 = hist[31 + lane], b1 = hist[32 + lane], c1 = hist[33 + lane]; }
             float o34 = hist[34], o35 = hist[35];
             __syncwarp();
-            const float n0 = (float)((double)((a0 + b0) + c0) / 3.0);
+            const float n0 = third((a0 + b0) + c0);
             hist[lane] = n0;
-            if (lane < 3) hist[32 + lane] = (float)((double)((a1 + b1) + c1) / 3.0);
+            if (lane < 3) hist[32 + lane] = third((a1 + b1) + c1);
             __syncwarp();
-            if (lane == 0) hist[35] = (float)((double)((o34 + o35) + n0) / 3.0);
+            if (lane == 0) hist[35] = third((o34 + o35) + n0);
             __syncwarp();
         }
-        if (lane == 0) {
-            float maxval = 0.0f;
-            int argmax = 0;
-            for (int i = 0; i < 36; i++)
-                if (maxval < hist[i]) { maxval = hist[i]; argmax = i; }
+        // orientation_cpu.cl:110-121 -- argmax = first bin holding the largest value > 0 (0 if there is none;
+        // NaN bins never win a comparison).  Lane i looks at bin i, lanes 0..3 also at bins 32..35.
+        const float h0 = hist[lane], h1 = lane < 4 ? hist[32 + lane] : 0.0f;
+        const float m0 = h0 > 0.0f ? h0 : 0.0f, m1 = h1 > 0.0f ? h1 : 0.0f;
+        float maxval = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(m0, m1))));
+        int argmax = 0;
+        if (maxval > 0.0f) {
+            const unsigned e0 = __ballot_sync(0xffffffffu, h0 == maxval);
+            const unsigned e1 = __ballot_sync(0xffffffffu, lane < 4 && h1 == maxval);
+            argmax = e0 ? __ffs(e0) - 1 : 31 + __ffs(e1);
+        }
+        float angle;
+        float4 o;
+        {
             const int prev = (argmax == 0 ? 35 : argmax - 1), next = (argmax == 35 ? 0 : argmax + 1);
             float hist_prev = hist[prev], hist_next = hist[next];
             if (maxval < 0.0f) { hist_prev = -hist_prev; maxval = -maxval; hist_next = -hist_next; }
             const float interp = 0.5f * (hist_prev - hist_next) / ((hist_prev - 2.0f * maxval) + hist_next);
-            const float angle = (2.0f * SIFTB_M_PI_F) * (((float)argmax + 0.5f) + interp) / 36.0f - SIFTB_M_PI_F;
-            float4 o;
+            angle = (2.0f * SIFTB_M_PI_F) * (((float)argmax + 0.5f) + interp) / 36.0f - SIFTB_M_PI_F;
             o.x = k.z * (float)octsize;
             o.y = k.y * (float)octsize;
             o.z = k.w * (float)octsize;
             o.w = angle;
-            kp[gid0] = o;
-            int added = 1;
-            for (int i = 0; i < 36; i++) {
-                const int pv = (i == 0 ? 35 : i - 1), nx = (i == 35 ? 0 : i + 1);
-                float hp = hist[pv], hc = hist[i], hn = hist[nx];
-                if (hc > hp && hc > hn && hc >= 0.8f * maxval && i != argmax) {
-                    if (hc < 0.0f) { hp = -hp; hc = -hc; hn = -hn; }
-                    const float itp = 0.5f * (hp - hn) / ((hp - 2.0f * hc) + hn);
-                    // orientation_cpu.cl:166: "/36.0" promotes the tail of the expression to double
-                    const float a2 = (float)((double)((2.0f * SIFTB_M_PI_F) * (((float)i + 0.5f) + itp)) / 36.0 -
-                                             (double)SIFTB_M_PI_F);
-                    if (a2 >= -SIFTB_M_PI_F && a2 <= SIFTB_M_PI_F) {
-                        const int old = n_base + atomicAdd(n_extra, 1);
-                        if (old < cap) {
-                            kp[old] = make_float4(o.x, o.y, o.z, a2);
-                            kp_tag[old] = tag;
-                        }
-                        added++;
-                    }
-                }
+            if (lane == 0) kp[gid0] = o;
+        }
+        // orientation_cpu.cl:131-172 -- every other local peak >= 0.8 max gives an extra keypoint
+        auto peak_angle = [&](int i, float &a2) {
+            const int pv = (i == 0 ? 35 : i - 1), nx = (i == 35 ? 0 : i + 1);
+            float hp = hist[pv], hc = hist[i], hn = hist[nx];
+            if (!(hc > hp && hc > hn && hc >= 0.8f * maxval && i != argmax)) return false;
+            if (hc < 0.0f) { hp = -hp; hc = -hc; hn = -hn; }
+            const float itp = 0.5f * (hp - hn) / ((hp - 2.0f * hc) + hn);
+            // orientation_cpu.cl:166: "/36.0" promotes the tail of the expression to double
+            a2 = (float)((double)((2.0f * SIFTB_M_PI_F) * (((float)i + 0.5f) + itp)) / 36.0 - (double)SIFTB_M_PI_F);
+            return a2 >= -SIFTB_M_PI_F && a2 <= SIFTB_M_PI_F;
+        };
+        float a2_0 = 0.0f, a2_1 = 0.0f;
+        const bool p0 = peak_angle(lane, a2_0);
+        const bool p1 = lane < 4 && peak_angle(32 + lane, a2_1);
+        const unsigned b0 = __ballot_sync(0xffffffffu, p0), b1 = __ballot_sync(0xffffffffu, p1);
+        const int n_extra_here = __popc(b0) + __popc(b1);
+        if (n_extra_here) {
+            int slot0 = 0;
+            if (lane == 0) slot0 = n_base + atomicAdd(n_extra, n_extra_here);
+            slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+            if (p0) {
+                const int old = slot0 + __popc(b0 & lanemask_lt());
+                if (old < cap) { kp[old] = make_float4(o.x, o.y, o.z, a2_0); kp_tag[old] = tag; }
             }
+            if (p1) {
+                const int old = slot0 + __popc(b0) + __popc(b1 & lanemask_lt());
+                if (old < cap) { kp[old] = make_float4(o.x, o.y, o.z, a2_1); kp_tag[old] = tag; }
+            }
+        }
+        if (lane == 0) {
+            const int added = 1 + n_extra_here;
             if (stage) atomicAdd(&stage[oct * 9 + (sc - 1) * 3 + 2], added);
             // rows whose angle is NaN (flat histogram) are dropped on output (plan.py:546-550)
             if (oct_valid) atomicAdd(&oct_valid[oct], added - ((angle != angle) ? 1 : 0));

@@ -52,6 +52,69 @@ __global__ void __launch_bounds__(256) k_gradient(GradArgs a) {
     }
 }
 
+// Vector form for planes whose pitch is a multiple of 4 floats and whose base is 16-byte aligned (every plane of
+// a SiftPlan): a thread owns 4 adjacent columns and walks GRAD4_ROWS rows.  One 128-bit load per row gives the
+// centre values; the horizontal neighbours come from the adjacent lanes (shuffles; the two edge lanes of a warp
+// read one extra value), the vertical neighbours are the previous / next row kept in registers, and the row after
+// next is requested before the current one is evaluated.  128-bit stores of both result planes.
+#define GRAD4_ROWS 16
+__device__ __forceinline__ void grad_one(float xgrad, float ygrad, float &gr, float &orv) {
+    gr = sqrtf(xgrad * xgrad + ygrad * ygrad);
+    orv = cr_atan2f_fast(-ygrad, xgrad);
+}
+__global__ void __launch_bounds__(128) k_gradient4(GradArgs a) {
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, z = blockIdx.z, lane = threadIdx.x & 31;
+    const int y0 = blockIdx.y * GRAD4_ROWS;
+    const float *g = a.g[z];
+    float *gradp = a.grad[z], *orip = a.ori[z];
+    const bool active = x4 < a.w;
+    const int xc = active ? x4 : 0;  // idle threads of a partly filled warp still take part in the shuffles
+    auto ldrow = [&](int y) {
+        y = max(0, min(y, a.h - 1));
+        return *reinterpret_cast<const float4 *>(g + (long)y * a.pitch + xc);
+    };
+    float4 up = ldrow(y0 - 1), cur = ldrow(y0), dn = ldrow(y0 + 1);
+    const int y_end = min(y0 + GRAD4_ROWS, a.h);
+    for (int y = y0; y < y_end; y++) {
+        const float4 nxt = ldrow(y + 2);
+        // horizontal neighbours of the 4-column group
+        float left = __shfl_up_sync(0xffffffffu, cur.w, 1), right = __shfl_down_sync(0xffffffffu, cur.x, 1);
+        if (lane == 0) left = x4 > 0 ? g[(long)y * a.pitch + xc - 1] : cur.x;
+        if (lane == 31) right = x4 + 4 < a.w ? g[(long)y * a.pitch + xc + 4] : cur.w;
+        // image.cl:58-66: xgrad = I[x+1]-I[x-1]; at the two image borders the one-sided difference, doubled
+        const int last = a.w - 1 - x4;  // element index of the last image column inside this group (or >= 4)
+        const float l0 = x4 == 0 ? cur.x : left, s0 = (x4 == 0 || last == 0) ? 2.0f : 1.0f;
+        const float xg0 = s0 * ((last == 0 ? cur.x : cur.y) - l0);
+        const float xg1 = (last == 1 ? 2.0f : 1.0f) * ((last == 1 ? cur.y : cur.z) - cur.x);
+        const float xg2 = (last == 2 ? 2.0f : 1.0f) * ((last == 2 ? cur.z : cur.w) - cur.y);
+        const float xg3 = (last == 3 ? 2.0f : 1.0f) * ((last == 3 ? cur.w : right) - cur.z);
+        // image.cl:67-72: ygrad = I[y-1]-I[y+1] ("up minus down"), doubled one-sided at the borders
+        float4 yg;
+        if (y == 0) yg = make_float4(2.0f * (cur.x - dn.x), 2.0f * (cur.y - dn.y), 2.0f * (cur.z - dn.z), 2.0f * (cur.w - dn.w));
+        else if (y == a.h - 1) yg = make_float4(2.0f * (up.x - cur.x), 2.0f * (up.y - cur.y), 2.0f * (up.z - cur.z), 2.0f * (up.w - cur.w));
+        else yg = make_float4(up.x - dn.x, up.y - dn.y, up.z - dn.z, up.w - dn.w);
+        float4 gr, orv;
+        grad_one(xg0, yg.x, gr.x, orv.x);
+        grad_one(xg1, yg.y, gr.y, orv.y);
+        grad_one(xg2, yg.z, gr.z, orv.z);
+        grad_one(xg3, yg.w, gr.w, orv.w);
+        if (active) {
+            const long pos = (long)y * a.pitch + x4;
+            if (last >= 3) {
+                *reinterpret_cast<float4 *>(gradp + pos) = gr;
+                *reinterpret_cast<float4 *>(orip + pos) = orv;
+            } else {  // ragged right edge: only the columns inside the image
+                gradp[pos] = gr.x; orip[pos] = orv.x;
+                if (last >= 1) { gradp[pos + 1] = gr.y; orip[pos + 1] = orv.y; }
+                if (last >= 2) { gradp[pos + 2] = gr.z; orip[pos + 2] = orv.z; }
+            }
+        }
+        up = cur;
+        cur = dn;
+        dn = nxt;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Gradient / orientation planes of EVERY octave of an image: orientation assignment and descriptors run once
 // per image over the keypoints of all octaves (a keypoint carries tag = octave << 8 | scale), so that the

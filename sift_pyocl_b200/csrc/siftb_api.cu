@@ -550,8 +550,8 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
             GradArgs ga;
             for (int i = 0; i < 3; i++) { ga.g[i] = p->G[i + 1]; ga.grad[i] = p->gradp[o][i]; ga.ori[i] = p->orip[o][i]; }
             ga.pitch = pitch; ga.w = w; ga.h = h;
-            dim3 grid((w + 255) / 256, (h + GRAD_ROWS - 1) / GRAD_ROWS, 3);
-            k_gradient<<<grid, 256, 0, st>>>(ga);
+            dim3 grid((w + 511) / 512, (h + GRAD4_ROWS - 1) / GRAD4_ROWS, 3);  // planes: pitch % 32 == 0, aligned
+            k_gradient4<<<grid, 128, 0, st>>>(ga);
             CKL();
             p->launches += 1;
         }
@@ -806,8 +806,13 @@ extern "C" int siftb_gradient(const float *image, int height, int width, float *
     GradArgs ga;
     for (int i = 0; i < 3; i++) { ga.g[i] = d.as<float>(); ga.grad[i] = g.as<float>(); ga.ori[i] = o.as<float>(); }
     ga.pitch = width; ga.w = width; ga.h = height;
-    dim3 grid((width + 255) / 256, (height + GRAD_ROWS - 1) / GRAD_ROWS, 1);
-    k_gradient<<<grid, 256>>>(ga);
+    if (width % 4 == 0) {  // the form the pipeline uses
+        dim3 grid((width + 511) / 512, (height + GRAD4_ROWS - 1) / GRAD4_ROWS, 1);
+        k_gradient4<<<grid, 128>>>(ga);
+    } else {
+        dim3 grid((width + 255) / 256, (height + GRAD_ROWS - 1) / GRAD_ROWS, 1);
+        k_gradient<<<grid, 256>>>(ga);
+    }
     CKL();
     CK(cudaMemcpy(grad, g.p, n * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(ori, o.p, n * 4, cudaMemcpyDeviceToHost));

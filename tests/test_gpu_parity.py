@@ -103,8 +103,9 @@ def test_pyramid_octave_bit_exact(stages, oracle, shape):  # plan.py:609-625, 73
     assert np.array_equal(nxt, oracle.shrink(Go[3]))
 
 
-def test_gradient(stages, oracle):  # test_image.py:91-129
-    img = oracle.blur(_img((301, 257), 6), oracle.gaussian_taps(1.5))
+@pytest.mark.parametrize("shape", [(301, 257), (301, 256), (37, 132), (16, 4)])  # scalar and 4-column kernels
+def test_gradient(stages, oracle, shape):  # test_image.py:91-129
+    img = oracle.blur(_img(shape, 6), oracle.gaussian_taps(1.5))
     grad, ori = stages.gradient(img)
     g0, o0 = oracle.gradient(img)
     assert np.array_equal(grad, g0)

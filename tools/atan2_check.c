@@ -4,11 +4,13 @@
 #include <stdint.h>
 #include <string.h>
 // CPU check of the fast atan2 used by k_gradient (sift_pyocl_b200/csrc/common.cuh: cr_atan2f_fast) against glibc:
-// gcc -O2 -mfma -o atan2_check tools/atan2_check.c -lm && ./atan2_check 200000000
+// gcc -O2 -mfma -ffp-contract=off -o tools/atan2_check tools/atan2_check.c -lm && tools/atan2_check 200000000 [t-perturbation, e.g. 1.000001]
 static const int NI = 16;
+// build with -ffp-contract=off (the device code is compiled with -fmad=false)
 static double C[17], ATC[17], TB[17];
 static void init(void){ for(int k=0;k<=NI;k++){ double a = (M_PI/4)*k/NI; C[k]=tan(a); ATC[k]=a; }
   for(int k=0;k<NI;k++){ TB[k]=tan((M_PI/4)*(k+0.5)/NI);} }
+static float TPERT = 1.0f;
 static inline double fast_atan2(float yf, float xf){
   double x=xf,y=yf; double ax=fabs(x), ay=fabs(y);
   double hi = ax>ay?ax:ay, lo = ax>ay?ay:ax;
@@ -16,9 +18,9 @@ static inline double fast_atan2(float yf, float xf){
   if (lo==0.0) a = 0.0; // includes (0,0)
   else {
     // interval: largest k with lo >= TB[k-1]*hi ... nearest breakpoint c_k = tan(k*pi/64)
-    int k=0; // binary search over TB (16 thresholds): k = number of thresholds with lo > TB*hi
-    { float lof=(float)lo, hif=(float)hi; /* fp32 search, as common.cuh (k <= 15) */
-      k = (lof > (float)TB[7]*hif) ? 8 : 0; k += (lof > (float)TB[k+3]*hif) ? 4 : 0; k += (lof > (float)TB[k+1]*hif) ? 2 : 0; k += (lof > (float)TB[k]*hif) ? 1 : 0; }
+    /* nearest breakpoint from a quadratic fit of atan, as common.cuh; the device computes t with __fdividef
+       (2 ulp), so a neighbouring k may be picked next to a boundary: KSHIFT = -1/0/+1 forces that here */
+    int k; { float lof=(float)lo, hif=(float)hi; float t = lof/hif; t = t*TPERT; k = (int)(t*(21.5615f + -5.5615f*t) + 0.5f); if(k>16)k=16; if(k<0)k=0; }
     double c=C[k];
     double r = fma(-c,hi,lo)/fma(c,lo,hi);
     double r2=r*r;
@@ -29,7 +31,7 @@ static inline double fast_atan2(float yf, float xf){
   if (signbit(x)) a = M_PI - a;
   return copysign(a, y);
 }
-int main(int argc,char**argv){ init(); long n = argc>1?atol(argv[1]):100000000; uint64_t s=88172645463325252ULL; long mism=0; double maxulp=0;
+int main(int argc,char**argv){ init(); if(argc>2) TPERT=(float)atof(argv[2]); long n = argc>1?atol(argv[1]):100000000; uint64_t s=88172645463325252ULL; long mism=0; double maxulp=0;
   for(long i=0;i<n;i++){ s^=s<<13; s^=s>>7; s^=s<<17; uint32_t a=(uint32_t)s, b=(uint32_t)(s>>32);
     float x,y; // mix of scales: gradients are differences of floats in [0,255]
     int mode = i&3;

@@ -83,28 +83,30 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
     const int u_r0 = max(0, iradius - irow), u_r1 = min(nrows - 1, iradius + grad_height - 1 - irow);
     const int u_jlo = max(-iradius, -icol), u_jhi = min(iradius, grad_width - 1 - icol);
     if (tabled) {
+        // rx in (-1, 4)  <=>  |cs*i - sn*j - drow| < L = 2.5*spacing in exact arithmetic; the fp32 evaluation of
+        // the reference (five roundings on magnitudes <= R + L) moves the left side by less than E.  Candidates
+        // therefore satisfy |A - sn*j| < L + E and |B + cs*j| < L + E: exact j-intervals, computed in double.
         const double L = 2.5 * (double)spacing, sn = (double)sine, cs = (double)cosine;
+        const double LE = L + 2e-6 * ((double)iradius + L + 2.0);
         const bool use_sn = fabs(sn) > 1e-9, use_cs = fabs(cs) > 1e-9;
-        const double isn = 1.0 / sn, ics = 1.0 / cs;  // bounds are widened by a whole sample: 1 ulp is irrelevant
+        const double isn = 1.0 / sn, ics = 1.0 / cs;
         for (int r = l8; r < nrows; r += 8) {
             const int i = r - iradius;
             double lo = -(double)iradius, hi = (double)iradius;
             if (irow + i < 0 || irow + i >= grad_height) hi = lo - 1.0;  // row outside the image
-            lo = fmax(lo, -(double)icol);
-            hi = fmin(hi, (double)(grad_width - 1 - icol));
-            const double A = cs * (double)i - (double)drow;  // |A - sn*j| < L
+            const double A = cs * (double)i - (double)drow;
             if (use_sn) {
-                const double a = (A - L) * isn, b = (A + L) * isn;
-                lo = fmax(lo, fmin(a, b) - 1.0);
-                hi = fmin(hi, fmax(a, b) + 1.0);
+                const double a = (A - LE) * isn, b = (A + LE) * isn;
+                lo = fmax(lo, fmin(a, b) - 1e-6);
+                hi = fmin(hi, fmax(a, b) + 1e-6);
             }
-            const double B = sn * (double)i - (double)dcol;  // |B + cs*j| < L
+            const double B = sn * (double)i - (double)dcol;
             if (use_cs) {
-                const double a = (-L - B) * ics, b = (L - B) * ics;
-                lo = fmax(lo, fmin(a, b) - 1.0);
-                hi = fmin(hi, fmax(a, b) + 1.0);
+                const double a = (-LE - B) * ics, b = (LE - B) * ics;
+                lo = fmax(lo, fmin(a, b) - 1e-6);
+                hi = fmin(hi, fmax(a, b) + 1e-6);
             }
-            int jlo = (int)floor(lo), jhi = (int)ceil(hi);
+            int jlo = (int)ceil(lo), jhi = (int)floor(hi);
             jlo = max(jlo, max(-iradius, -icol));
             jhi = min(jhi, min(iradius, grad_width - 1 - icol));
             if (jhi < jlo) { jlo = 1; jhi = 0; }  // empty (the real-valued bounds may not fit a short)
@@ -121,50 +123,48 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
                     rows.jlo[n] = (short)jlo;
                     rows.jhi[n] = (short)jhi;
                     n++;
-                    acc += (jhi - jlo + 8) >> 3;
+                    acc += jhi - jlo + 1;
                 }
             }
             nrc = n;
-            my_passes = acc;
+            my_passes = (acc + 7) >> 3;  // the candidates of all rows are packed back to back, 8 per pass
         }
         __syncwarp();
-        nrc = __shfl_sync(0xffffffffu, nrc, obase);
-        my_passes = __shfl_sync(0xffffffffu, my_passes, obase);
     } else if (u_r1 >= u_r0 && u_jhi >= u_jlo) {
         nrc = u_r1 - u_r0 + 1;
-        my_passes = nrc * ((u_jhi - u_jlo + 8) >> 3);
+        my_passes = (nrc * (u_jhi - u_jlo + 1) + 7) >> 3;
     }
+    nrc = __shfl_sync(0xffffffffu, nrc, obase);
+    my_passes = __shfl_sync(0xffffffffu, my_passes, obase);
     // warp-uniform trip count: the longest of the 4 octets
     const int passes_max = __reduce_max_sync(0xffffffffu, my_passes);
-    // Octet-uniform cursor over the table: row rcur, next j of that row, last j of that row, pixel offset of
-    // (row, j = 0).  Sample of this lane in the next pass: window coordinates and (if it is a candidate) its
-    // gradient / orientation values.  The values of pass p+1 are requested before pass p is evaluated and
-    // committed, so the L2 / DRAM gather latency overlaps the commit loop.
-    int rcur = -1, jcur = 0, jend = -1, n_i = 0, n_j = 0;
+    // Per-lane cursor over the candidate samples in row-major order: lane l8 takes candidates l8, l8 + 8, ... of
+    // the octet (table row rcur, column jcur, last column of that row jend, pixel offset of (row, j = 0)).  The
+    // gradient / orientation values of the lane's sample of pass p+1 are requested before pass p is evaluated
+    // and committed, so the L2 / DRAM gather latency overlaps the commit loop.
+    int rcur = -1, jcur = l8, jend = -1, n_i = 0, n_j = 0;
     long rowoff = 0;
     bool n_in = false;
     float n_g = 0.0f, n_o = 0.0f;
     auto fetch = [&]() {
-        if (jcur > jend) {  // next table row
+        while (jcur > jend && rcur < nrc) {  // into the next table row(s)
+            const int over = jcur - jend - 1;
             rcur++;
             if (rcur < nrc) {
                 if (tabled) {
                     n_i = rows.i[rcur];
-                    jcur = rows.jlo[rcur];
+                    jcur = rows.jlo[rcur] + over;
                     jend = rows.jhi[rcur];
                 } else {
                     n_i = u_r0 + rcur - iradius;
-                    jcur = u_jlo;
+                    jcur = u_jlo + over;
                     jend = u_jhi;
                 }
                 rowoff = (long)(irow + n_i) * pitch + icol;
-            } else {  // table exhausted: idle from now on
-                jcur = 0;
-                jend = -1;
             }
         }
-        n_j = jcur + l8;
-        n_in = n_j <= jend;
+        n_j = jcur;
+        n_in = rcur < nrc;
         if (n_in) {
             n_g = grad[rowoff + n_j];
             n_o = orim[rowoff + n_j];

@@ -13,20 +13,26 @@ struct DogStack {
     int pitch, w, h;
 };
 
-// image.cl:141-212 for one pixel and one scale, given the five DoG values c[0..4] at that pixel.
-// gate: smallest fp32 strictly above 0.8*peak_thresh evaluated in double (image.cl:152 compares in double:
-// fabs(val) > 0.8*peak_thresh  <=>  fabsf(val) >= gate for fp32 val); computed on the host.
-// Returns true when (gid0, gid1, scale) is a keypoint candidate.  Same decisions as the reference's flag loops
-// (strict comparisons, plateaus fire); the tests are ordered so that most pixels leave after a few compares on
-// values that are already in registers or L1.
-__device__ __forceinline__ bool maxmin_pixel(const DogStack &D, long pos, int scale, const float c[5], float gate,
-                                             float edthresh) {
+// image.cl:141-212 for one pixel and one scale, split in two steps with the same decisions as the reference's
+// flag loops (strict comparisons, plateaus fire):
+//  * maxmin_gate: contrast gate and the two neighbouring scales at the same pixel, from the five DoG values
+//    c[0..4] already in registers.  gate: smallest fp32 strictly above 0.8*peak_thresh evaluated in double
+//    (image.cl:152 compares in double: fabs(val) > 0.8*peak_thresh <=> fabsf(val) >= gate for fp32 val); computed
+//    on the host.  2-3.5 % of the pixels survive it.
+//  * maxmin_rest: the other 24 neighbours, ordered so that most pixels leave after a few compares, then the edge
+//    test (image.cl:180-186: H00/H11 in double (literal 2.0), H01 float differences then /4.0).
+__device__ __forceinline__ bool maxmin_gate(const float c[5], int scale, float gate) {
     const float val = c[scale];
     if (!(fabsf(val) >= gate)) return false;
     const float sgn = (val > 0.0f) ? 1.0f : -1.0f;  // maximum test for val > 0, minimum test otherwise
     const float sval = sgn * val;                   // sign flips are exact
-    if (sgn * c[scale - 1] > sval || sgn * c[scale + 1] > sval) return false;  // same pixel, neighbouring scales
+    return !(sgn * c[scale - 1] > sval || sgn * c[scale + 1] > sval);
+}
+__device__ __forceinline__ bool maxmin_rest(const DogStack &D, long pos, int scale, float edthresh) {
     const float *dc = D.d[scale];
+    const float val = dc[pos];
+    const float sgn = (val > 0.0f) ? 1.0f : -1.0f;
+    const float sval = sgn * val;
     if (sgn * dc[pos - 1] > sval || sgn * dc[pos + 1] > sval) return false;
 #pragma unroll
     for (int dr = -1; dr <= 1; dr += 2) {
@@ -43,7 +49,6 @@ __device__ __forceinline__ bool maxmin_pixel(const DogStack &D, long pos, int sc
             if (sgn * rowp[-1] > sval || sgn * rowp[0] > sval || sgn * rowp[1] > sval) return false;
         }
     }
-    // image.cl:180-186: H00/H11 in double (literal 2.0), H01 float differences then /4.0
     const long up = pos - D.pitch, dn_ = pos + D.pitch;
     float H00 = (float)(((double)dc[up] - 2.0 * (double)val) + (double)dc[dn_]);
     float H11 = (float)(((double)dc[pos - 1] - 2.0 * (double)val) + (double)dc[pos + 1]);
@@ -57,47 +62,87 @@ __device__ __forceinline__ bool maxmin_pixel(const DogStack &D, long pos, int sc
     return val != 0.0f;
 }
 
-#define EXT_ROWS 8
+#define EXT_ROWS 16
 // grid: (ceil(w/128), ceil((h-2*border)/EXT_ROWS)), block 128 threads along x; every thread walks EXT_ROWS rows
-// of its column and tests nscales scales per pixel from the five DoG values loaded together.
+// of its column and runs maxmin_gate on nscales scales per pixel from the five DoG values loaded together.  The
+// survivors of a warp are queued in shared memory and finished 32 at a time, one per lane (maxmin_rest is long and
+// would otherwise run for one or two lanes of a warp at a time).
 // cand rows: (val, row, col, scale).  n_cand = total candidates, stage[(s-1)*3] = per-scale count.
 __global__ void __launch_bounds__(128) k_extrema(DogStack D, int border, float gate, float edthresh,
                                                   float4 *__restrict__ cand, int cap, int *__restrict__ n_cand,
                                                   int *__restrict__ stage /* [3][3] or null */, int scale_lo,
                                                   int nscales) {
+    __shared__ unsigned short s_q[4][128];  // per warp: (row offset << 7) | (scale index << 5) | lane
     const int gid0 = blockIdx.x * blockDim.x + threadIdx.x;
     const int row0 = border + blockIdx.y * EXT_ROWS;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, col0 = gid0 - lane;
+    unsigned short *q = s_q[threadIdx.x >> 5];
     const bool col_ok = gid0 >= border && gid0 < D.w - border;
-    for (int r = 0; r < EXT_ROWS; r++) {
-        const int gid1 = row0 + r;
-        const bool in = col_ok && gid1 < D.h - border;
-        const long pos = (long)gid1 * D.pitch + gid0;
-        float c[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        if (in) {
+    int head = 0, qn = 0;  // warp-uniform ring state
+    auto finish = [&](int nb) {  // the first nb (<= 32) queued survivors, one per lane
+        bool hit = false;
+        int gid1 = 0, gcol = 0, scale = 1;
+        long pos = 0;
+        if (lane < nb) {
+            const unsigned e = q[(head + lane) & 127];
+            gid1 = row0 + (int)(e >> 7);
+            gcol = col0 + (int)(e & 31u);
+            scale = 1 + (int)((e >> 5) & 3u);
+            pos = (long)gid1 * D.pitch + gcol;
+            hit = maxmin_rest(D, pos, scale, edthresh);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(n_cand, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (hit) {
+                const int slot = base + __popc(m & lanemask_lt());
+                if (slot < cap) cand[slot] = make_float4(D.d[scale][pos], (float)gid1, (float)gcol, (float)scale);  // image.cl:202-208
+            }
+            if (stage) {
 #pragma unroll
-            for (int i = 0; i < 5; i++) c[i] = D.d[i][pos];
+                for (int sc = 1; sc <= 3; sc++) {
+                    const unsigned msc = __ballot_sync(0xffffffffu, hit && scale == sc);
+                    if (lane == 0 && msc) atomicAdd(&stage[(sc - 1) * 3 + 0], __popc(msc));
+                }
+            }
+        }
+        head = (head + nb) & 127;
+        qn -= nb;
+    };
+    const int r_end = min(EXT_ROWS, D.h - border - row0);
+    // the five values of the next two rows are requested before the current row is tested (bytes in flight)
+    float c1[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, c2[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (col_ok) {
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+            if (0 < r_end) c1[i] = D.d[i][(long)row0 * D.pitch + gid0];
+            if (1 < r_end) c2[i] = D.d[i][(long)(row0 + 1) * D.pitch + gid0];
+        }
+    }
+    for (int r = 0; r < r_end; r++) {
+        float c[5];
+#pragma unroll
+        for (int i = 0; i < 5; i++) { c[i] = c1[i]; c1[i] = c2[i]; }
+        if (col_ok && r + 2 < r_end) {
+#pragma unroll
+            for (int i = 0; i < 5; i++) c2[i] = D.d[i][(long)(row0 + r + 2) * D.pitch + gid0];
         }
 #pragma unroll
         for (int si = 0; si < 3; si++) {
             const int scale = 1 + si;
             if (scale < scale_lo || scale >= scale_lo + nscales) continue;  // block-uniform
-            const bool hit = in && maxmin_pixel(D, pos, scale, c, gate, edthresh);
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (m == 0) continue;
-            const int leader = __ffs(m) - 1;
-            int base = 0;
-            if (lane == leader) {
-                base = atomicAdd(n_cand, __popc(m));
-                if (stage) atomicAdd(&stage[(scale - 1) * 3 + 0], __popc(m));
-            }
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (hit) {
-                const int slot = base + __popc(m & lanemask_lt());
-                if (slot < cap) cand[slot] = make_float4(c[scale], (float)gid1, (float)gid0, (float)scale);  // image.cl:202-208
-            }
+            const bool surv = col_ok && maxmin_gate(c, scale, gate);
+            const unsigned m = __ballot_sync(0xffffffffu, surv);
+            if (surv) q[(head + qn + __popc(m & lanemask_lt())) & 127] = (unsigned short)((r << 7) | (si << 5) | lane);
+            qn += __popc(m);
         }
+        __syncwarp();
+        while (qn >= 32) { finish(32); __syncwarp(); }
     }
+    while (qn > 0) { finish(min(qn, 32)); __syncwarp(); }
 }
 
 // image.cl:249-366 for one candidate; returns true if kept, result (peak, row, col, sigma)

@@ -118,13 +118,14 @@ def _octave_fixture(oracle, shape=(240, 320), seed=9):
     return oracle.pyramid_octave(g0)
 
 
+@pytest.mark.parametrize("shape", [(240, 320), (161, 203)])  # 4-column kernel / scalar kernel
 @pytest.mark.parametrize("octsize", [1, 2])
-def test_local_maxmin(stages, oracle, octsize):  # test_image.py:141-191 (sorted compare)
-    G, D = _octave_fixture(oracle)
+def test_local_maxmin(stages, oracle, octsize, shape):  # test_image.py:141-191 (sorted compare)
+    G, D = _octave_fixture(oracle, shape)
     for s in (1, 2, 3):
         kp, n = stages.local_maxmin(D, s, octsize)
         ko, no = oracle.local_maxmin(D, s, octsize=octsize)
-        assert n == no and n > 30
+        assert n == no and n > 10
         assert np.array_equal(_sort_rows(kp), _sort_rows(ko[:no]))
 
 

@@ -16,12 +16,28 @@ __global__ void __launch_bounds__(256) k_extract_desc(const uint8_t *__restrict_
     desc[i] = *reinterpret_cast<const uint32_t *>(recs + row * 144 + 16 + 4 * wd);
 }
 
-#define MATCH_TILE 64
-// one thread per query row of list 1; list 2 streamed through shared memory in tiles
-__global__ void __launch_bounds__(128) k_match_l1(const uint32_t *__restrict__ d1, int n1,
-                                                   const uint32_t *__restrict__ d2, int n2, float ratio_th,
-                                                   int2 *__restrict__ pairs, int cap, int *__restrict__ counter) {
-    __shared__ uint4 tile[MATCH_TILE * 8];
+// acc + sum |a-b| over the 4 packed bytes, as ONE VABSDIFF4.U8.ACC (written in PTX so that the accumulation
+// stays a chain: with __vsadu4(a, b) + acc the compiler re-associates the sums into IADD3 trees, which costs
+// one extra ALU-pipe instruction per two SADs on the pipe that bounds the kernel)
+__device__ __forceinline__ unsigned sad4_acc(unsigned a, unsigned b, unsigned acc) {
+    unsigned d;
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(acc));
+    return d;
+}
+
+#define MATCH_TILE 64      // rows of list 2 per shared-memory stage (8 KB), two stages in flight
+#define MATCH_THREADS 64   // small CTAs: 100 000 queries -> 1563 CTAs, ~10.5 per SM (balance), all resident
+// One thread per query row of list 1 (its 128 bytes live in 32 registers); list 2 is streamed through shared
+// memory in double-buffered cp.async stages and every row is broadcast to the whole CTA (LDS.128, one wavefront).
+// sum |a-b| over 4 packed bytes = one VABSDIFF4.U8.ACC (64 lanes/clk/SM, measured with tools/sad_probe.cu: the
+// bound of this kernel); two rows are processed together with two accumulators each, so four independent
+// chains hide the latency of that pipe.  Distances stay integers (<= 32640); 0xffffffff stands for the
+// reference's initial 1e12f (matching_cpu.cl:71), so the integer compares decide exactly like the fp32 ones.
+__global__ void __launch_bounds__(MATCH_THREADS) k_match_l1(const uint32_t *__restrict__ d1, int n1,
+                                                             const uint32_t *__restrict__ d2, int n2, float ratio_th,
+                                                             int2 *__restrict__ pairs, int cap,
+                                                             int *__restrict__ counter) {
+    __shared__ uint4 tile[2][MATCH_TILE * 8];
     const int gid0 = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = gid0 < n1;
     uint32_t q[32];
@@ -33,29 +49,77 @@ __global__ void __launch_bounds__(128) k_match_l1(const uint32_t *__restrict__ d
             q[4 * i] = v.x; q[4 * i + 1] = v.y; q[4 * i + 2] = v.z; q[4 * i + 3] = v.w;
         }
     }
-    float dist1 = 1000000000000.0f, dist2 = 1000000000000.0f;  // matching_cpu.cl:71
-    int current_min = 0;
-    for (int base = 0; base < n2; base += MATCH_TILE) {
+    auto stage_load = [&](int st, int base) {  // rows [base, base + MATCH_TILE) of list 2 -> tile[st]
         const int rows = min(MATCH_TILE, n2 - base);
-        __syncthreads();
-        for (int i = threadIdx.x; i < rows * 8; i += blockDim.x)
-            tile[i] = __ldg(reinterpret_cast<const uint4 *>(d2) + (long)base * 8 + i);
-        __syncthreads();
-        for (int r = 0; r < rows; r++) {
-            unsigned dist = 0;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const uint4 v = tile[r * 8 + i];
-                dist = __vsadu4(q[4 * i], v.x) + dist;
-                dist = __vsadu4(q[4 * i + 1], v.y) + dist;
-                dist = __vsadu4(q[4 * i + 2], v.z) + dist;
-                dist = __vsadu4(q[4 * i + 3], v.w) + dist;
-            }
-            const float fd = (float)(int)dist;
-            if (fd < dist1) { dist2 = dist1; dist1 = fd; current_min = base + r; }
-            else if (fd < dist2) { dist2 = fd; }
+        for (int i = threadIdx.x; i < rows * 8; i += MATCH_THREADS) {
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tile[st][i]);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst),
+                         "l"(reinterpret_cast<const uint4 *>(d2) + (long)base * 8 + i) : "memory");
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // (distance << 17 | row index) keys: the two smallest keys give dist1 / dist2 with the reference's tie rules
+    // (strict '<': the first row wins a tie, the second-best value counts multiplicity) in three min/max
+    // operations per row.  Needs n2 <= 2^17; larger lists take the compare-and-select form.
+    const bool packed = n2 <= (1 << 17);
+    unsigned best1 = 0xffffffffu, best2 = 0xffffffffu;
+    int current_min = 0;
+    auto row_dist = [&](const uint4 *row) {
+        unsigned da = 0, db = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint4 v = row[i];
+            da = sad4_acc(q[4 * i], v.x, da);
+            db = sad4_acc(q[4 * i + 1], v.y, db);
+            da = sad4_acc(q[4 * i + 2], v.z, da);
+            db = sad4_acc(q[4 * i + 3], v.w, db);
+        }
+        return da + db;
+    };
+    auto update = [&](unsigned d, int idx) {
+        if (packed) {
+            const unsigned key = d * 131072u + (unsigned)idx;
+            best2 = min(best2, max(best1, key));
+            best1 = min(best1, key);
+        } else {  // matching_cpu.cl:92-97
+            if (d < best1) { best2 = best1; best1 = d; current_min = idx; }
+            else if (d < best2) { best2 = d; }
+        }
+    };
+    if (n2 > 0) stage_load(0, 0);
+    int st = 0;
+    for (int base = 0; base < n2; base += MATCH_TILE, st ^= 1) {
+        const int rows = min(MATCH_TILE, n2 - base);
+        if (base + MATCH_TILE < n2) {
+            stage_load(st ^ 1, base + MATCH_TILE);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const uint4 *t = tile[st];
+        if (rows == MATCH_TILE) {
+#pragma unroll 1
+            for (int r = 0; r < MATCH_TILE; r += 4) {
+                const uint4 *p4 = t + r * 8;
+                const unsigned dA = row_dist(p4), dB = row_dist(p4 + 8), dC = row_dist(p4 + 16), dD = row_dist(p4 + 24);
+                update(dA, base + r);
+                update(dB, base + r + 1);
+                update(dC, base + r + 2);
+                update(dD, base + r + 3);
+            }
+        } else {
+            for (int r = 0; r < rows; r++) update(row_dist(t + r * 8), base + r);
+        }
+        __syncthreads();  // everyone is done with tile[st] before it is refilled two iterations later
     }
+    if (packed) {
+        current_min = (int)(best1 & 131071u);
+        if (best1 != 0xffffffffu) best1 >>= 17;
+        if (best2 != 0xffffffffu) best2 >>= 17;
+    }
+    const float dist1 = best1 == 0xffffffffu ? 1000000000000.0f : (float)best1;
+    const float dist2 = best2 == 0xffffffffu ? 1000000000000.0f : (float)best2;
     const bool emit = active && (dist2 != 0.0f) && (dist1 / dist2 < ratio_th);  // matching_cpu.cl:100
     const int slot = warp_append(emit, counter);
     if (emit && slot < cap) pairs[slot] = make_int2(gid0, current_min);

@@ -686,6 +686,29 @@ struct DevBuf {
 };
 #define DALLOC(buf, bytes) CK((buf).alloc(bytes))
 
+// Scratch buffers of the stateless matcher entry point: taken from the device's stream-ordered memory pool, which
+// is told to keep freed memory (the reference's MatchPlan keeps its device buffers between calls, match.py:220-239),
+// so that repeated match() calls do not pay cudaMalloc / cudaFree.
+struct PoolBuf {
+    void *p = nullptr;
+    ~PoolBuf() { if (p) cudaFreeAsync(p, 0); }
+    cudaError_t alloc(size_t bytes) {
+        static bool configured[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!configured[dev & 63]) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                uint64_t keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            configured[dev & 63] = true;
+        }
+        return cudaMallocAsync(&p, bytes ? bytes : 1, 0);
+    }
+    template <typename T> T *as() { return (T *)p; }
+};
+
 extern "C" int siftb_gauss_taps(double sigma, float *taps, int cap, int *n) {
     if (!taps || !n || !(sigma > 0)) return fail(SIFTB_EINVAL, "bad argument");
     int size = kernel_size(sigma);
@@ -919,7 +942,7 @@ extern "C" int siftb_match_l1(const siftb_kp *kp1, int n1, const siftb_kp *kp2, 
     *n = 0;
     if (n1 == 0) return 0;
     CK(cudaSetDevice(device));
-    DevBuf R1, R2, D1, D2, P, C;
+    PoolBuf R1, R2, D1, D2, P, C;
     const uint8_t *r1 = (const uint8_t *)kp1, *r2 = (const uint8_t *)kp2;
     if (!on_device) {
         DALLOC(R1, (size_t)n1 * 144); DALLOC(R2, (size_t)n2 * 144);
@@ -932,7 +955,7 @@ extern "C" int siftb_match_l1(const siftb_kp *kp1, int n1, const siftb_kp *kp2, 
     k_extract_desc<<<(int)(((long)n1 * 32 + 255) / 256), 256>>>(r1, n1, D1.as<uint32_t>());
     if (n2) k_extract_desc<<<(int)(((long)n2 * 32 + 255) / 256), 256>>>(r2, n2, D2.as<uint32_t>());
     CKL();
-    k_match_l1<<<(n1 + 127) / 128, 128>>>(D1.as<uint32_t>(), n1, D2.as<uint32_t>(), n2, ratio_th, P.as<int2>(), cap,
+    k_match_l1<<<(n1 + MATCH_THREADS - 1) / MATCH_THREADS, MATCH_THREADS>>>(D1.as<uint32_t>(), n1, D2.as<uint32_t>(), n2, ratio_th, P.as<int2>(), cap,
                                           C.as<int>());
     CKL();
     CK(cudaMemcpy(n, C.p, 4, cudaMemcpyDeviceToHost));

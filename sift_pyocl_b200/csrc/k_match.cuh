@@ -60,10 +60,12 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match_l1(const uint32_t *__re
     };
     // (distance << 17 | row index) keys: the two smallest keys give dist1 / dist2 with the reference's tie rules
     // (strict '<': the first row wins a tie, the second-best value counts multiplicity) in three min/max
-    // operations per row.  Needs n2 <= 2^17; larger lists take the compare-and-select form.
-    const bool packed = n2 <= (1 << 17);
-    unsigned best1 = 0xffffffffu, best2 = 0xffffffffu;
+    // operations per row.  17 index bits: list 2 is walked in chunks of 2^17 rows whose results are folded, in
+    // order, into the running (dist1, index, dist2) with the reference's compare-and-select (matching_cpu.cl:92-97).
+    constexpr int CHUNK = 1 << 17;
+    unsigned best1 = 0xffffffffu, best2 = 0xffffffffu;  // running result, plain distances
     int current_min = 0;
+    unsigned key1 = 0xffffffffu, key2 = 0xffffffffu;    // current chunk, packed keys
     auto row_dist = [&](const uint4 *row) {
         unsigned da = 0, db = 0;
 #pragma unroll
@@ -76,18 +78,25 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match_l1(const uint32_t *__re
         }
         return da + db;
     };
-    auto update = [&](unsigned d, int idx) {
-        if (packed) {
-            const unsigned key = d * 131072u + (unsigned)idx;
-            best2 = min(best2, max(best1, key));
-            best1 = min(best1, key);
-        } else {  // matching_cpu.cl:92-97
-            if (d < best1) { best2 = best1; best1 = d; current_min = idx; }
+    auto update = [&](unsigned d, int idx_in_chunk) {
+        const unsigned key = d * (unsigned)CHUNK + (unsigned)idx_in_chunk;
+        key2 = min(key2, max(key1, key));
+        key1 = min(key1, key);
+    };
+    auto fold = [&](int chunk_base) {
+        if (key1 != 0xffffffffu) {
+            const unsigned d = key1 >> 17;
+            if (d < best1) { best2 = best1; best1 = d; current_min = chunk_base + (int)(key1 & (CHUNK - 1)); }
             else if (d < best2) { best2 = d; }
         }
+        if (key2 != 0xffffffffu) {
+            const unsigned d = key2 >> 17;
+            if (d < best2) best2 = d;  // d >= best1 here
+        }
+        key1 = key2 = 0xffffffffu;
     };
     if (n2 > 0) stage_load(0, 0);
-    int st = 0;
+    int st = 0, chunk_base = 0;
     for (int base = 0; base < n2; base += MATCH_TILE, st ^= 1) {
         const int rows = min(MATCH_TILE, n2 - base);
         if (base + MATCH_TILE < n2) {
@@ -97,27 +106,25 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match_l1(const uint32_t *__re
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
+        if (base - chunk_base >= CHUNK) { fold(chunk_base); chunk_base = base; }  // CHUNK is a multiple of the tile
         const uint4 *t = tile[st];
+        const int loc = base - chunk_base;
         if (rows == MATCH_TILE) {
 #pragma unroll 1
             for (int r = 0; r < MATCH_TILE; r += 4) {
                 const uint4 *p4 = t + r * 8;
                 const unsigned dA = row_dist(p4), dB = row_dist(p4 + 8), dC = row_dist(p4 + 16), dD = row_dist(p4 + 24);
-                update(dA, base + r);
-                update(dB, base + r + 1);
-                update(dC, base + r + 2);
-                update(dD, base + r + 3);
+                update(dA, loc + r);
+                update(dB, loc + r + 1);
+                update(dC, loc + r + 2);
+                update(dD, loc + r + 3);
             }
         } else {
-            for (int r = 0; r < rows; r++) update(row_dist(t + r * 8), base + r);
+            for (int r = 0; r < rows; r++) update(row_dist(t + r * 8), loc + r);
         }
         __syncthreads();  // everyone is done with tile[st] before it is refilled two iterations later
     }
-    if (packed) {
-        current_min = (int)(best1 & 131071u);
-        if (best1 != 0xffffffffu) best1 >>= 17;
-        if (best2 != 0xffffffffu) best2 >>= 17;
-    }
+    fold(chunk_base);
     const float dist1 = best1 == 0xffffffffu ? 1000000000000.0f : (float)best1;
     const float dist2 = best2 == 0xffffffffu ? 1000000000000.0f : (float)best2;
     const bool emit = active && (dist2 != 0.0f) && (dist1 / dist2 < ratio_th);  // matching_cpu.cl:100

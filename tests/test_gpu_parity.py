@@ -382,6 +382,29 @@ def test_match_l1(sift, oracle):  # test_matching.py (assert commented out in th
                           oracle.match(one, np.concatenate([one, one])))
 
 
+def test_match_long_second_list(sift, oracle):
+    """List 2 longer than the 2^17-row chunks of the packed (distance, row) keys: ties and best / second-best
+    pairs that straddle a chunk boundary must resolve like the sequential scan (first row wins, '<' strict)."""
+    rng = np.random.default_rng(11)
+    n1, n2 = 300, (1 << 17) + 9000
+    k1, _, _ = _desc_sets(n1, 10, seed=5)
+    from sift_pyocl_b200._lib import dtype_kp
+    k2 = np.zeros(n2, dtype_kp)
+    k2["desc"] = np.minimum(rng.gamma(1.0, 28.0, (n2, 128)), 255).astype(np.uint8)
+    near = lambda d: np.clip(d.astype(np.int32) + rng.integers(-1, 2, 128), 0, 255).astype(np.uint8)
+    for i in range(0, 100):        # exact copy in chunk 1 only -> dist1 = 0
+        k2["desc"][(1 << 17) + 10 + i] = k1.desc[i]
+    for i in range(100, 200):      # identical copies in both chunks: the first one must win; dist2 == dist1 -> no match
+        k2["desc"][500 + i] = k2["desc"][(1 << 17) + 500 + i] = near(k1.desc[i])
+    for i in range(200, 300):      # best in chunk 1, a slightly worse one in chunk 0
+        k2["desc"][(1 << 17) + 2000 + i] = near(k1.desc[i])
+        k2["desc"][3000 + i] = np.clip(k1.desc[i].astype(np.int32) + 40, 0, 255).astype(np.uint8)
+    k2 = k2.view(np.recarray)
+    raw = sift.MatchPlan().match(k1, k2, raw_results=True)
+    want = oracle.match(k1, k2)
+    assert np.array_equal(_sort_rows(raw), _sort_rows(want)) and len(want) >= 100
+
+
 def test_match_from_real_keypoints(sift, oracle):
     img = _ms(512, 21)
     shifted = np.roll(img, (3, 5), axis=(0, 1))

@@ -93,6 +93,16 @@ __device__ __forceinline__ float cr_atan2f_fast(float yf, float xf) {
     return copysignf((float)a, yf);
 }
 
+// ---- correctly rounded fp32 division by a loop-invariant divisor -------------------------------------------
+// a / b == (float)((double)a * inv) with inv = 1.0 / (double)b: the double product is within 2^-52 (relative) of
+// the exact quotient, while a quotient of two 24-bit significands is either at least 2^-49 (relative) away from
+// every rounding boundary of fp32 (the midpoints have 25 significant bits: |a - m*b| >= 1 in integer units) or
+// exactly representable, and it can never sit exactly on a midpoint.  So the final rounding to fp32 sees the
+// same side of every boundary as the exact quotient: bit-identical to IEEE division, for finite non-tiny values
+// (all uses here are O(1) magnitudes).  3 instructions instead of ~10 per division.
+__device__ __forceinline__ double div_prepare(float b) { return 1.0 / (double)b; }
+__device__ __forceinline__ float div_by(float a, double inv) { return (float)((double)a * inv); }
+
 // reference mirror rule, convolution.cl:41-50: p<0 -> -p-1 ; p>=dim -> 2*dim-1-p
 __device__ __forceinline__ int mirror_index(int p, int dim) {
     if (p < 0) p = -p - 1;

@@ -68,6 +68,7 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
     const int irow = (int)(row + 0.5f), icol = (int)(col + 0.5f);
     const float sine = cr_sinf(angle), cosine = cr_cosf(angle);
     const float spacing = k.z / (float)octsize * 3.0f;
+    const double inv_spacing = div_prepare(spacing);  // x / spacing == div_by(x, inv_spacing), see common.cuh
     int iradius = (int)(((1.414f * spacing) * 2.5f) + 0.5f);
     const float drow = row - (float)irow, dcol = col - (float)icol;
     if (!(act && iradius >= 0)) iradius = -1;
@@ -182,8 +183,8 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
         float rw_e = 0.0f, rw_o = 0.0f, cf_e = 0.0f, cf_o = 0.0f, ow_e = 0.0f, ow_o = 0.0f;
         int ra_e = 0, ra_o = 16, ca_e = 0, ca_o = 8, oa_e = 0, oa_o = 4;  // byte offsets in the bank group, home cell
         if (in_image) {
-            const float rx = ((cosine * (float)i - sine * (float)j) - drow) / spacing + 1.5f;
-            const float cx = ((sine * (float)i + cosine * (float)j) - dcol) / spacing + 1.5f;
+            const float rx = div_by((cosine * (float)i - sine * (float)j) - drow, inv_spacing) + 1.5f;
+            const float cx = div_by((sine * (float)i + cosine * (float)j) - dcol, inv_spacing) + 1.5f;
             if (rx > -1.0f && rx < 4.0f && cx > -1.0f && cx < 4.0f) {
                 const float er = rx - 1.5f, ec = cx - 1.5f;
                 const float mag = g_val * cr_expf_neg(-0.125f * (er * er + ec * ec));
@@ -191,8 +192,10 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
                 while (ori > 2.0f * SIFTB_M_PI_F) ori -= 2.0f * SIFTB_M_PI_F;
                 while (ori < 0.0f) ori += 2.0f * SIFTB_M_PI_F;
                 const float oval = (4.0f * ori) * SIFTB_M_1_PI_F;
-                const int ri = (int)((rx >= 0.0f) ? rx : rx - 1.0f);
-                const int ci = (int)((cx >= 0.0f) ? cx : cx - 1.0f);
+                // keypoints_cpu.cl:77-79 `(int)((v >= 0.0f) ? v : v - 1.0f)`: for v in (-1, 4) that is floor(v)
+                // (v - 1 lies in (-2, -1) for negative v, so the truncation gives -1); oval >= 0 always
+                const int ri = __float2int_rd(rx);
+                const int ci = __float2int_rd(cx);
                 const int oi = (int)((oval >= 0.0f) ? oval : oval - 1.0f);
                 const float rfrac = rx - (float)ri, cfrac = cx - (float)ci, ofrac = oval - (float)oi;
                 if ((ri >= -1 && ri < 4 && oi >= 0 && oi <= 8 && rfrac >= 0.0f && rfrac <= 1.0f)) {

@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(256) k_orient(OctTable T, float4 *__restrict__
         const int rmin = max(0, row - radius), cmin = max(0, col - radius);
         const int rmax = min(row + radius, Gh - 2), cmax = min(col + radius, Gw - 2);
         const float two_s2 = (2.0f * sigma) * sigma;
+        const double inv_two_s2 = div_prepare(two_s2), inv_two_pi = div_prepare(2.0f * SIFTB_M_PI_F);
         const float rad2 = ((float)(radius * radius)) + 0.5f;
         const int ncols = cmax - cmin + 1, nrows = rmax - rmin + 1;
         const int total = (ncols > 0 && nrows > 0) ? ncols * nrows : 0;
@@ -200,10 +201,10 @@ __global__ void __launch_bounds__(256) k_orient(OctTable T, float4 *__restrict__
                 dif = ((float)c - k.z);
                 distsq += dif * dif;
                 if (gval > 0.0f && distsq < rad2) {
-                    int b = (int)(36.0f * ((angle + SIFTB_M_PI_F) + 0.001f) / (2.0f * SIFTB_M_PI_F));
+                    int b = (int)div_by(36.0f * ((angle + SIFTB_M_PI_F) + 0.001f), inv_two_pi);
                     if (b >= 0 && b <= 36) {
                         bin = min(b, 35);
-                        w = cr_expf_neg(-distsq / two_s2) * gval;
+                        w = cr_expf_neg(div_by(-distsq, inv_two_s2)) * gval;
                     }
                 }
             }

@@ -97,7 +97,8 @@ SIFTB_API int siftb_plan_keypoints(siftb_plan *plan, const void *image, int flag
 
 /* The same path split in two so that callers can overlap the copy of image k+1 with the kernels of
  * image k: submit() enqueues copy + all kernels on the plan's stream and returns immediately;
- * collect() waits and copies the records to the host.  One submit may be in flight per plan. */
+ * collect() waits for the oldest submitted image and copies its records to the host.  Up to three submits may be
+ * in flight per plan (results come back in submission order). */
 SIFTB_API int siftb_plan_submit(siftb_plan *plan, const void *image, int flags);
 SIFTB_API int siftb_plan_collect(siftb_plan *plan, siftb_kp *out, int cap, int *n_out, int *n_per_octave,
                        float *minmax);   /* out == NULL: wait and return the counts only (records stay on the device) */

@@ -31,6 +31,7 @@
 #define SIFTB_VERSION 100
 #define MAX_OCT 32
 #define AUX_INTS (8 + 3 * SIFTB_KOCT + 3 * DESC_CLASSES)
+#define NSLOT 3  // images in flight per plan
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) {
@@ -124,10 +125,11 @@ struct siftb_plan {
     int ntaps[6];
     bool has_init = false;
     size_t raw_bytes = 0, dev_bytes = 0;
-    // Two image slots so that submit(k+1) (H->D copy on the copy stream) and collect(k) (D->H of the records)
-    // overlap the kernels of the other image; the planes and keypoint lists are shared (kernels of successive
-    // images are serialised on the compute stream).
-    void *d_raws[2] = {nullptr, nullptr};  // staging for host input (plan dtype)
+    // NSLOT image slots so that submit(k+1), submit(k+2) (H->D copies on the copy stream) and collect(k) (D->H of
+    // the records, host-side handling of the result) overlap the kernels of another image: with three slots the
+    // compute stream always has the next image queued, input already resident, when an image finishes.  The planes
+    // and keypoint lists are shared (kernels of successive images are serialised on the compute stream).
+    void *d_raws[NSLOT] = {};  // staging for host input (plan dtype)
     float *d_img = nullptr;    // dense fp32 plane for converted integer/RGB/f64 input
     float *G[6] = {}, *D[5] = {};
     float *gradp[SIFTB_KOCT][3] = {}, *orip[SIFTB_KOCT][3] = {};  // gradient planes of every octave (k_keypoint.cuh)
@@ -136,15 +138,15 @@ struct siftb_plan {
     int *kp_tag = nullptr;  // octave << 8 | scale
     int *kp_order = nullptr;  // keypoint indices by descending descriptor-window size
     int kp_cap = 0;         // keypoints of one image over all octaves
-    KpRecord *outs[2] = {nullptr, nullptr};
+    KpRecord *outs[NSLOT] = {};
     // device counters: [0]=n_out, [1..]: per octave {n_cand, n_kp, n_extra, n_out_oct}; then stage[n_oct][3][3]; then mm[2]
     // per slot AUX_INTS ints: [0] describe work-queue head, [1] refined keypoints (all octaves), [2] extra
     // orientations, [8..8+KOCT) records per octave, [8+KOCT..) first record slot per octave, [8+2KOCT..) fill
     int *d_queue = nullptr;
-    int *d_cnts[2] = {nullptr, nullptr};
-    int *h_cnts[2] = {nullptr, nullptr};  // pinned mirrors
+    int *d_cnts[NSLOT] = {};
+    int *h_cnts[NSLOT] = {};  // pinned mirrors
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_h2d[2] = {}, ev_done[2] = {}, ev_d2h[2] = {};
+    cudaEvent_t ev_h2d[NSLOT] = {}, ev_done[NSLOT] = {}, ev_d2h[NSLOT] = {};
     int head = 0, n_flight = 0;  // slots [head, head + n_flight) are submitted and not yet collected
     int last = 0;                // slot of the most recently collected image
     int cnt_ints = 0;
@@ -152,7 +154,7 @@ struct siftb_plan {
     uint64_t launches = 0;
     TbMaps tmaps[MAX_OCT][5];  // source G[s] of octave o, boxes for taps[s]
     bool tmaps_ok[MAX_OCT][5] = {};
-    TbMaps tmap_raws[2], tmap_img;  // first blur: from the host-staging buffers / the converted fp32 plane
+    TbMaps tmap_raws[NSLOT], tmap_img;  // first blur: from the host-staging buffers / the converted fp32 plane
     bool tmap_raw_ok = false, tmap_img_ok = false;
     int force_generic = 0;
     std::vector<Event> events;
@@ -205,14 +207,14 @@ extern "C" int siftb_plan_destroy(siftb_plan *p) {
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
-    for (int s = 0; s < 2; s++) { cudaFree(p->d_raws[s]); cudaFree(p->outs[s]); cudaFree(p->d_cnts[s]); }
+    for (int s = 0; s < NSLOT; s++) { cudaFree(p->d_raws[s]); cudaFree(p->outs[s]); cudaFree(p->d_cnts[s]); }
     cudaFree(p->d_img);
     for (auto q : p->G) cudaFree(q);
     for (auto q : p->D) cudaFree(q);
     for (int o = 0; o < SIFTB_KOCT; o++)
         for (int i = 0; i < 3; i++) { cudaFree(p->gradp[o][i]); cudaFree(p->orip[o][i]); }
     cudaFree(p->cand); cudaFree(p->kp); cudaFree(p->kp_tag); cudaFree(p->kp_order); cudaFree(p->d_queue);
-    for (int s = 0; s < 2; s++) {
+    for (int s = 0; s < NSLOT; s++) {
         if (p->h_cnts[s]) cudaFreeHost(p->h_cnts[s]);
         if (p->ev_h2d[s]) cudaEventDestroy(p->ev_h2d[s]);
         if (p->ev_done[s]) cudaEventDestroy(p->ev_done[s]);
@@ -229,7 +231,7 @@ static int plan_create_impl(siftb_plan *p) {
     CK(cudaSetDevice(p->device));
     CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
-    for (int s = 0; s < 2; s++) {
+    for (int s = 0; s < NSLOT; s++) {
         CK(cudaEventCreateWithFlags(&p->ev_h2d[s], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&p->ev_done[s], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&p->ev_d2h[s], cudaEventDisableTiming));
@@ -275,7 +277,7 @@ static int plan_create_impl(siftb_plan *p) {
     const size_t plane = (size_t)p->opitch[0] * p->oh[0] * sizeof(float);
     p->raw_bytes = N * (dtype_bytes(p->dtype) > 4 ? dtype_bytes(p->dtype) : 4);  // fp32 input is always accepted
     int rc;
-    for (int s = 0; s < 2; s++) if ((rc = dalloc(p, &p->d_raws[s], p->raw_bytes))) return rc;
+    for (int s = 0; s < NSLOT; s++) if ((rc = dalloc(p, &p->d_raws[s], p->raw_bytes))) return rc;
     if (p->dtype != SIFTB_F32 && (rc = dalloc(p, &p->d_img, N * sizeof(float)))) return rc;
     for (int i = 0; i < 6; i++) if ((rc = dalloc(p, &p->G[i], plane))) return rc;
     for (int i = 0; i < 5; i++) if ((rc = dalloc(p, &p->D[i], plane))) return rc;
@@ -299,22 +301,24 @@ static int plan_create_impl(siftb_plan *p) {
     if ((rc = dalloc(p, &p->kp, (size_t)p->kp_cap * sizeof(float4)))) return rc;
     if ((rc = dalloc(p, &p->kp_tag, (size_t)p->kp_cap * sizeof(int)))) return rc;
     if ((rc = dalloc(p, &p->kp_order, (size_t)p->kp_cap * sizeof(int)))) return rc;
-    if ((rc = dalloc(p, &p->d_queue, 2 * AUX_INTS * sizeof(int)))) return rc;
+    if ((rc = dalloc(p, &p->d_queue, NSLOT * AUX_INTS * sizeof(int)))) return rc;
     p->out_cap = 2 * p->kpsize;
-    for (int s = 0; s < 2; s++) if ((rc = dalloc(p, &p->outs[s], (size_t)p->out_cap * sizeof(KpRecord)))) return rc;
+    for (int s = 0; s < NSLOT; s++) if ((rc = dalloc(p, &p->outs[s], (size_t)p->out_cap * sizeof(KpRecord)))) return rc;
     if (tb_get_encode()) {
         for (int o = 0; o < p->n_oct; o++)
             for (int s = 0; s < 5; s++)
                 if (tb_supported(p->ntaps[s], s == kScales - 1 && o + 1 < p->n_oct ? TB_DOG_HALF : TB_DOG))
                     p->tmaps_ok[o][s] = tb_encode_pair(&p->tmaps[o][s], p->G[s], p->ow[o], p->oh[o], p->opitch[o], p->ntaps[s] >> 1) == 0;
         if (tb_supported(p->ntaps[5], TB_NORM) && p->w % 4 == 0) {
-            p->tmap_raw_ok = tb_encode_pair(&p->tmap_raws[0], (const float *)p->d_raws[0], p->w, p->h, p->w, p->ntaps[5] >> 1) == 0 &&
-                             tb_encode_pair(&p->tmap_raws[1], (const float *)p->d_raws[1], p->w, p->h, p->w, p->ntaps[5] >> 1) == 0;
+            p->tmap_raw_ok = true;
+            for (int s = 0; s < NSLOT; s++)
+                p->tmap_raw_ok = p->tmap_raw_ok && tb_encode_pair(&p->tmap_raws[s], (const float *)p->d_raws[s], p->w, p->h,
+                                                                  p->w, p->ntaps[5] >> 1) == 0;
             if (p->d_img) p->tmap_img_ok = tb_encode_pair(&p->tmap_img, p->d_img, p->w, p->h, p->w, p->ntaps[5] >> 1) == 0;
         }
     }
     p->cnt_ints = 1 + 13 * p->n_oct + 2 + 2;  // ... + min/max + {refined, extra} totals
-    for (int s = 0; s < 2; s++) {
+    for (int s = 0; s < NSLOT; s++) {
         if ((rc = dalloc(p, &p->d_cnts[s], p->cnt_ints * sizeof(int)))) return rc;
         CK(cudaHostAlloc((void **)&p->h_cnts[s], p->cnt_ints * sizeof(int), cudaHostAllocDefault));
         memset(p->h_cnts[s], 0, p->cnt_ints * sizeof(int));
@@ -467,7 +471,7 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
     p->events.clear();
     const long N = (long)p->h * p->w;
     const void *src = image;
-    const int slot = (p->head + p->n_flight) & 1;
+    const int slot = (p->head + p->n_flight) % NSLOT;
     if (!on_device) {
         // H->D on the copy stream: overlaps the kernels of the previous image (pinned host memory)
         CK(cudaMemcpyAsync(p->d_raws[slot], image, (size_t)N * dtype_bytes(dtype), cudaMemcpyHostToDevice,
@@ -587,7 +591,7 @@ static int collect_impl(siftb_plan *p, siftb_kp *out, int cap, int *n_out, int *
     CK(cudaSetDevice(p->device));
     const int slot = p->head;
     CK(cudaEventSynchronize(p->ev_done[slot]));
-    p->head ^= 1;
+    p->head = (p->head + 1) % NSLOT;
     p->n_flight--;
     p->last = slot;
     const int *h_cnt = p->h_cnts[slot];
@@ -627,7 +631,7 @@ static int collect_impl(siftb_plan *p, siftb_kp *out, int cap, int *n_out, int *
 extern "C" int siftb_plan_submit(siftb_plan *p, const void *image, int flags) {
     if (!p || !image) return fail(SIFTB_EINVAL, "null argument");
     std::lock_guard<std::mutex> lk(p->mtx);
-    if (p->n_flight >= 2) return fail(SIFTB_EINVAL, "two submits are already in flight on this plan");
+    if (p->n_flight >= NSLOT) return fail(SIFTB_EINVAL, "three submits are already in flight on this plan");
     return submit_impl(p, image, flags);
 }
 extern "C" int siftb_plan_collect(siftb_plan *p, siftb_kp *out, int cap, int *n_out, int *n_per_octave,

@@ -278,7 +278,7 @@ def test_plan_reuse_and_device_input(sift, oracle):
     assert np.array_equal(_sort_kp(plan.collect()), _sort_kp(k1))
 
 
-def test_pipelined_two_in_flight(sift, oracle):
+def test_pipelined_images_in_flight(sift, oracle):
     imgs = [_ms(320, 40 + i) for i in range(5)]
     plan = sift.SiftPlan(shape=imgs[0].shape, dtype=np.float32)
     pinned = []
@@ -292,10 +292,12 @@ def test_pipelined_two_in_flight(sift, oracle):
         assert np.array_equal(_sort_kp(kp), _sort_kp(oracle.keypoints(im)))
     plan.submit(pinned[0])
     plan.submit(pinned[1])
+    plan.submit(pinned[2])
     with pytest.raises(AssertionError):
-        plan.submit(pinned[2])  # at most two images in flight
-    a, b = plan.collect(), plan.collect()
+        plan.submit(pinned[3])  # at most three images in flight
+    a, b, c = plan.collect(), plan.collect(), plan.collect()
     assert np.array_equal(_sort_kp(a), _sort_kp(got[0])) and np.array_equal(_sort_kp(b), _sort_kp(got[1]))
+    assert np.array_equal(_sort_kp(c), _sort_kp(got[2]))
     with pytest.raises(AssertionError):
         plan.collect()
 

@@ -36,8 +36,8 @@ SIZE = 4096
 OCTAVES = 3
 N_IMAGES = 2  # distinct images cycled per rank (working set per image ~1.2 GB >> 126 MB L2)
 # dram__bytes_read.sum + dram__bytes_write.sum per octave-0 blur+DoG launch from the committed ncu --set full
-# capture (profiles/r01_blur_ncu_full.csv), averaged over the five tap counts; None until measured
-TRAFFIC_PER_LAUNCH = 148.6e6
+# capture (profiles/r01c_ncu_full_final.csv), averaged over the five tap counts; None until measured
+TRAFFIC_PER_LAUNCH = 164.3e6
 
 
 def _peaks():

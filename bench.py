@@ -163,9 +163,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
+    # stdout carries exactly one JSON line: libraries that chat on fd 1 (NCCL prints its version banner there at
+    # any NCCL_DEBUG level >= VERSION) are sent to stderr, the line itself goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import sift_pyocl_b200 as sift
@@ -213,8 +216,15 @@ def main():
     nkp, blur_ms, blur0_ms, stage_ms = 0, 0.0, 0.0, {}
     ev0.record(stream)
     t0 = time.perf_counter()
+    # K steps, software-pipelined: the kernels of step i+1 are enqueued before step i is collected, so the
+    # all-gather of step i's records (N > 1) and the host-side bookkeeping overlap the next image's kernels
+    plan.submit(dev_imgs[0])
     for i in range(args.steps):
-        nkp += device_step(i)
+        if i + 1 < args.steps:
+            plan.submit(dev_imgs[(i + 1) % N_IMAGES])
+        n = plan.collect(records=False)
+        gather(n)
+        nkp += n
         for name, ms in plan.fetch_events():
             key = name.split(" octave")[0]
             stage_ms[key] = stage_ms.get(key, 0.0) + ms
@@ -238,11 +248,17 @@ def main():
         pass
     barrier()
     e2e_kp, d2h, t0 = 0, 0, time.perf_counter()
+    pending = None  # N > 1: the all-gather of step i is completed while step i+1 runs (counts first, then payload)
     for kp in plan.keypoints_many(host_imgs[i % N_IMAGES] for i in range(args.steps)):
         e2e_kp += kp.size
         d2h += kp.size * 144 + 4 * (1 + 13 * plan.octave_max + 2)
         if world > 1:
-            gather(kp.size)
+            started = sdist.allgather_records_begin(sdist.device_records_tensor(plan, kp.size))
+            if pending is not None:
+                pending.finish()
+            pending = started
+    if pending is not None:
+        pending.finish()
     barrier()
     e2e_s = time.perf_counter() - t0
     # the same, strictly one image at a time (SiftPlan.keypoints, the reference's call)
@@ -312,7 +328,8 @@ def main():
         line["cpu_baseline"] = {"value": n_cpu / dt, "unit": "keypoints/s", "cores": siftref.num_threads(),
                                 "kind": "port", "ms_per_image": 1e3 * dt,
                                 "sample": "%d x one %dx%d image (seed 1234), oracle/libsiftref.so OpenMP" % (reps, SIZE, SIZE)}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0

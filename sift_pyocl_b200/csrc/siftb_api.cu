@@ -157,7 +157,8 @@ struct siftb_plan {
     TbMaps tmap_raws[NSLOT], tmap_img;  // first blur: from the host-staging buffers / the converted fp32 plane
     bool tmap_raw_ok = false, tmap_img_ok = false;
     int force_generic = 0;
-    std::vector<Event> events;
+    std::vector<Event> events_s[NSLOT];  // profiling events of the image in each slot
+    int cur = 0;                         // slot being submitted (ProfScope)
     std::vector<const char *> ev_names;
     std::vector<float> ev_ms;
 
@@ -221,7 +222,7 @@ extern "C" int siftb_plan_destroy(siftb_plan *p) {
         if (p->ev_d2h[s]) cudaEventDestroy(p->ev_d2h[s]);
     }
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
-    for (auto &e : p->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (auto &ev : p->events_s) for (auto &e : ev) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
     return 0;
@@ -453,11 +454,11 @@ struct ProfScope {
         cudaEventCreate(&e.a);
         cudaEventCreate(&e.b);
         cudaEventRecord(e.a, p->stream);
-        p->events.push_back(e);
-        idx = (int)p->events.size() - 1;
+        p->events_s[p->cur].push_back(e);
+        idx = (int)p->events_s[p->cur].size() - 1;
     }
     ~ProfScope() {
-        if (idx >= 0) cudaEventRecord(p->events[idx].b, p->stream);
+        if (idx >= 0) cudaEventRecord(p->events_s[p->cur][idx].b, p->stream);
     }
 };
 
@@ -467,11 +468,12 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
     const int dtype = (flags & SIFTB_IS_F32) ? SIFTB_F32 : p->dtype;
     CK(cudaSetDevice(p->device));
     cudaStream_t st = p->stream;
-    for (auto &e : p->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-    p->events.clear();
     const long N = (long)p->h * p->w;
     const void *src = image;
     const int slot = (p->head + p->n_flight) % NSLOT;
+    p->cur = slot;
+    for (auto &e : p->events_s[slot]) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    p->events_s[slot].clear();
     if (!on_device) {
         // H->D on the copy stream: overlaps the kernels of the previous image (pinned host memory)
         CK(cudaMemcpyAsync(p->d_raws[slot], image, (size_t)N * dtype_bytes(dtype), cudaMemcpyHostToDevice,
@@ -659,10 +661,12 @@ extern "C" int siftb_plan_events(siftb_plan *p, const char *const **names, const
     if (!p) return fail(SIFTB_EINVAL, "null plan");
     std::lock_guard<std::mutex> lk(p->mtx);
     CK(cudaSetDevice(p->device));
-    CK(cudaStreamSynchronize(p->stream));
+    // the events of the most recently collected image: all recorded before its ev_done, which collect() waited for
+    // (no stream synchronisation here: the next images may already be running)
+    auto &events = p->events_s[p->last];
     p->ev_names.clear();
     p->ev_ms.clear();
-    for (auto &e : p->events) {
+    for (auto &e : events) {
         float t = 0.f;
         cudaEventElapsedTime(&t, e.a, e.b);
         p->ev_names.push_back(e.name.c_str());
@@ -670,7 +674,7 @@ extern "C" int siftb_plan_events(siftb_plan *p, const char *const **names, const
     }
     if (names) *names = p->ev_names.data();
     if (ms) *ms = p->ev_ms.data();
-    if (n) *n = (int)p->events.size();
+    if (n) *n = (int)events.size();
     return 0;
 }
 extern "C" int siftb_plan_stage_counts(siftb_plan *p, int *counts) {

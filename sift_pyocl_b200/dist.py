@@ -34,25 +34,46 @@ def device_records_tensor(plan, n):
     return t.view(n, 144)
 
 
+class _PendingGather(object):
+    """All-gather of ragged records split in two so that the host never waits for the exchange of the counts:
+    begin (constructor) copies the local records and starts the all-gather of the counts asynchronously;
+    ``finish()`` -- typically called one pipeline step later -- reads the counts and runs the all-gather of the
+    records padded to the largest count."""
+
+    def __init__(self, local, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.local = local.clone()  # the plan's record buffer is recycled by a later submit()
+        dev = local.device
+        self.cnt = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
+        self.counts = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        self.work = dist.all_gather_into_tensor(self.counts, self.cnt, group=group, async_op=True)
+
+    def finish(self):
+        self.work.wait()
+        counts_h = self.counts.cpu()
+        nmax = max(int(counts_h.max()), 1)
+        dev = self.local.device
+        padded = torch.zeros((nmax, 144), dtype=torch.uint8, device=dev)
+        padded[:self.local.shape[0]] = self.local
+        gathered = torch.empty((self.world * nmax, 144), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(gathered, padded, group=self.group)
+        gathered = gathered.view(self.world, nmax, 144)
+        return [gathered[r, :int(counts_h[r])] for r in range(self.world)], counts_h
+
+
+def allgather_records_begin(local, group=None):
+    """Start the all-gather of ragged record tensors; returns a handle whose ``finish()`` completes it."""
+    return _PendingGather(local, group)
+
+
 def allgather_records(local, group=None):
     """All-gather ragged record tensors.
 
     :param local: uint8 tensor [n_local, 144] (CUDA for nccl, CPU for gloo)
     :return: (list of per-rank uint8 tensors [n_r, 144], int64 tensor of counts)
     """
-    world = dist.get_world_size(group)
-    dev = local.device
-    cnt = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
-    counts = torch.zeros(world, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(counts, cnt, group=group)
-    counts_h = counts.cpu()
-    nmax = int(counts_h.max())
-    padded = torch.zeros((max(nmax, 1), 144), dtype=torch.uint8, device=dev)
-    padded[:local.shape[0]] = local
-    gathered = torch.empty((world * max(nmax, 1), 144), dtype=torch.uint8, device=dev)
-    dist.all_gather_into_tensor(gathered, padded, group=group)
-    gathered = gathered.view(world, max(nmax, 1), 144)
-    return [gathered[r, :int(counts_h[r])] for r in range(world)], counts_h
+    return _PendingGather(local, group).finish()
 
 
 def records_to_numpy(t):

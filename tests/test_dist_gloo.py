@@ -63,6 +63,42 @@ def test_sharded_batch_allgather_world2(n_images):
     assert res == [(0, True), (1, True)]
 
 
+def _pipelined_worker(rank, world, port, q):
+    """Two-phase all-gather as the pipelined e2e loop uses it: begin(step i+1) before finish(step i)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sift_pyocl_b200 import dist as sdist
+    steps = [torch.full((3 * i + rank, 144), 10 * i + rank, dtype=torch.uint8) for i in range(4)]
+    pending, ok = None, True
+    results = []
+    for t in steps:
+        started = sdist.allgather_records_begin(t)
+        t.fill_(255)  # the source buffer is recycled right away, like a plan slot
+        if pending is not None:
+            results.append(pending.finish())
+        pending = started
+    results.append(pending.finish())
+    for i, (per_rank, counts) in enumerate(results):
+        for r in range(world):
+            ok = ok and int(counts[r]) == 3 * i + r and per_rank[r].shape == (3 * i + r, 144)
+            ok = ok and bool((per_rank[r] == 10 * i + r).all())
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_pipelined_allgather_world2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_pipelined_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert res == [(0, True), (1, True)]
+
+
 class _StubMatch(object):
     device = 0
 

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(128) k_gradient4(GradArgs a) {
         const float4 nxt = ldrow(y + 2);
         // horizontal neighbours of the 4-column group
         float left = __shfl_up_sync(0xffffffffu, cur.w, 1), right = __shfl_down_sync(0xffffffffu, cur.x, 1);
-        if (lane == 0) left = x4 > 0 ? g[(long)y * a.pitch + xc - 1] : cur.x;
+        if (lane == 0) left = (active && x4 > 0) ? g[(long)y * a.pitch + xc - 1] : cur.x;
         if (lane == 31) right = x4 + 4 < a.w ? g[(long)y * a.pitch + xc + 4] : cur.w;
         // image.cl:58-66: xgrad = I[x+1]-I[x-1]; at the two image borders the one-sided difference, doubled
         const int last = a.w - 1 - x4;  // element index of the last image column inside this group (or >= 4)

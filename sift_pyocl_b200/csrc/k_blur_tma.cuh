@@ -186,8 +186,10 @@ k_blur_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
         }
         if (cont || left || right) __syncthreads();     // halo carry / patches done before the row pass
         // ---- horizontal pass: task q -> (row = q % nrows, segment = q / nrows) --------------------------
+        // q / nrows by multiply-shift (exact for q < 2^10: the error of the scaled reciprocal is < q / 2^20)
+        const int rdiv = cont ? (1 << 20) / TB_TH + 1 : (1 << 20) / BH + 1;
         for (int q = tid; q < nrows * NSEG; q += TB_THREADS) {
-            const int seg = q / nrows, row = q - seg * nrows;
+            const int seg = (q * rdiv) >> 20, row = q - seg * nrows;
             tb_row_task<C, RH, DELTA>(tile + row * BW + seg * RH, hbuf + (hrow0 + row) * TB_HP + seg * RH, taps);
         }
         __syncthreads();

@@ -68,28 +68,38 @@ __device__ double c_atan_a[17] = {0x0.0p+0, 0x1.921fb54442d18p-5, 0x1.921fb54442
 // (thresholds of the former breakpoint search; kept for reference)
 __device__ double c_atan_t[17] = {0x1.92346247a91f0p-6, 0x1.2e239ccff3831p-4, 0x1.f93183a8db9e9p-4, 0x1.635c990ce0d36p-3, 0x1.cbe4ceb4b4cf2p-3, 0x1.1b6103d3597e8p-2, 0x1.5248ae1701b18p-2, 0x1.8b00196b3d021p-2, 0x1.c5e87185e67b6p-2, 0x1.01b819b5a7cf7p-1, 0x1.220b5ef047825p-1, 0x1.44386db9ce5dap-1, 0x1.6897514751db6p-1, 0x1.8f9197bf85eeap-1, 0x1.b9a77c18c1af2p-1, 0x1.e776eafc91705p-1, 1e300};
 
-__device__ __forceinline__ float cr_atan2f_fast(float yf, float xf) {
+// The double constants of the polynomial and of the quadrant fix-up live in the constant bank, where DFMA / DADD
+// read them as a direct operand: as literals ptxas re-materialises each of them with two moves at every use (a
+// tenth of the instructions of the gradient kernel).
+__constant__ double c_atan_k[7] = {-1.0 / 11.0, 1.0 / 9.0, -1.0 / 7.0, 1.0 / 5.0, -1.0 / 3.0, 1.5707963267948966,
+                                   3.141592653589793};
+struct AtanConsts {
+    double c11, c9, c7, c5, c3, pio2, pi;
+    __device__ __forceinline__ AtanConsts()
+        : c11(c_atan_k[0]), c9(c_atan_k[1]), c7(c_atan_k[2]), c5(c_atan_k[3]), c3(c_atan_k[4]), pio2(c_atan_k[5]),
+          pi(c_atan_k[6]) {}
+};
+
+__device__ __forceinline__ float cr_atan2f_fast(float yf, float xf, const AtanConsts &K) {
     const float axf = fabsf(xf), ayf = fabsf(yf);
     const float hif = fmaxf(axf, ayf), lof = fminf(axf, ayf);
-    double a = 0.0;
-    if (lof != 0.0f) {
-        // tables live in global memory and are read through L1 (__ldg): the index differs per lane, which the
-        // constant cache would serialise
-        const float t = __fdividef(lof, hif);
-        const int k = min((int)(t * (21.5615f + -5.5615f * t) + 0.5f), 16);
-        const double hi = (double)hif, lo = (double)lof;
-        const double c = __ldg(&c_atan_c[k]);
-        const double r = __ddiv_rn(fma(-c, hi, lo), fma(c, lo, hi));
-        const double r2 = r * r;
-        double p = fma(r2, -1.0 / 11.0, 1.0 / 9.0);
-        p = fma(r2, p, -1.0 / 7.0);
-        p = fma(r2, p, 1.0 / 5.0);
-        p = fma(r2, p, -1.0 / 3.0);
-        p = p * r2;
-        a = __ldg(&c_atan_a[k]) + fma(r, p, r);
-    }
-    if (ayf > axf) a = 1.5707963267948966 - a;
-    if (signbit(xf)) a = 3.141592653589793 - a;
+    // tables live in global memory and are read through L1 (__ldg): the index differs per lane, which the
+    // constant cache would serialise.  Branch-free: lof == 0 (including 0/0) is selected to a = 0 at the end.
+    const float t = __fdividef(lof, hif);
+    const int k = max(min((int)(t * (21.5615f + -5.5615f * t) + 0.5f), 16), 0);
+    const double hi = (double)hif, lo = (double)lof;
+    const double c = __ldg(&c_atan_c[k]);
+    const double r = __ddiv_rn(fma(-c, hi, lo), fma(c, lo, hi));
+    const double r2 = r * r;
+    double p = fma(r2, K.c11, K.c9);
+    p = fma(r2, p, K.c7);
+    p = fma(r2, p, K.c5);
+    p = fma(r2, p, K.c3);
+    p = p * r2;
+    double a = __ldg(&c_atan_a[k]) + fma(r, p, r);
+    if (lof == 0.0f) a = 0.0;
+    if (ayf > axf) a = K.pio2 - a;
+    if (signbit(xf)) a = K.pi - a;
     return copysignf((float)a, yf);
 }
 

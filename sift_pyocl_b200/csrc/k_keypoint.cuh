@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(256) k_gradient(GradArgs a) {
     const int xm = x == 0 ? 0 : x - 1, xp = x == a.w - 1 ? x : x + 1;
     const float xs = (x == 0 || x == a.w - 1) ? 2.0f : 1.0f;  // one-sided differences are doubled (image.cl:61-66)
     // sliding window of the centre column: up, cur, down
+    const AtanConsts K;
     float up = g[(long)(y0 > 0 ? y0 - 1 : 0) * a.pitch + x];
     float cur = g[(long)y0 * a.pitch + x];
 #pragma unroll
@@ -46,7 +47,7 @@ __global__ void __launch_bounds__(256) k_gradient(GradArgs a) {
         else if (y == a.h - 1) ygrad = 2.0f * (up - cur);
         else ygrad = up - dn;
         gradp[pos] = sqrtf(xgrad * xgrad + ygrad * ygrad);
-        orip[pos] = cr_atan2f_fast(-ygrad, xgrad);
+        orip[pos] = cr_atan2f_fast(-ygrad, xgrad, K);
         up = cur;
         cur = dn;
     }
@@ -58,9 +59,9 @@ __global__ void __launch_bounds__(256) k_gradient(GradArgs a) {
 // read one extra value), the vertical neighbours are the previous / next row kept in registers, and the row after
 // next is requested before the current one is evaluated.  128-bit stores of both result planes.
 #define GRAD4_ROWS 16
-__device__ __forceinline__ void grad_one(float xgrad, float ygrad, float &gr, float &orv) {
+__device__ __forceinline__ void grad_one(float xgrad, float ygrad, float &gr, float &orv, const AtanConsts &K) {
     gr = sqrtf(xgrad * xgrad + ygrad * ygrad);
-    orv = cr_atan2f_fast(-ygrad, xgrad);
+    orv = cr_atan2f_fast(-ygrad, xgrad, K);
 }
 __global__ void __launch_bounds__(128) k_gradient4(GradArgs a) {
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, z = blockIdx.z, lane = threadIdx.x & 31;
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(128) k_gradient4(GradArgs a) {
         y = max(0, min(y, a.h - 1));
         return *reinterpret_cast<const float4 *>(g + (long)y * a.pitch + xc);
     };
+    const AtanConsts K;
     float4 up = ldrow(y0 - 1), cur = ldrow(y0), dn = ldrow(y0 + 1);
     const int y_end = min(y0 + GRAD4_ROWS, a.h);
     for (int y = y0; y < y_end; y++) {
@@ -94,10 +96,10 @@ __global__ void __launch_bounds__(128) k_gradient4(GradArgs a) {
         else if (y == a.h - 1) yg = make_float4(2.0f * (up.x - cur.x), 2.0f * (up.y - cur.y), 2.0f * (up.z - cur.z), 2.0f * (up.w - cur.w));
         else yg = make_float4(up.x - dn.x, up.y - dn.y, up.z - dn.z, up.w - dn.w);
         float4 gr, orv;
-        grad_one(xg0, yg.x, gr.x, orv.x);
-        grad_one(xg1, yg.y, gr.y, orv.y);
-        grad_one(xg2, yg.z, gr.z, orv.z);
-        grad_one(xg3, yg.w, gr.w, orv.w);
+        grad_one(xg0, yg.x, gr.x, orv.x, K);
+        grad_one(xg1, yg.y, gr.y, orv.y, K);
+        grad_one(xg2, yg.z, gr.z, orv.z, K);
+        grad_one(xg3, yg.w, gr.w, orv.w, K);
         if (active) {
             const long pos = (long)y * a.pitch + x4;
             if (last >= 3) {

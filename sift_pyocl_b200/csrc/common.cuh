@@ -65,8 +65,6 @@ __device__ __forceinline__ float cr_rsqrtf(float x) { return (float)(1.0 / sqrt(
 // the same guarantee class as libdevice's atan2 at a fraction of its cost.  Signed zeros follow C99.
 __device__ double c_atan_c[17] = {0x0.0p+0, 0x1.927278a3b1162p-5, 0x1.936bb8c5b2da2p-4, 0x1.2fcac73a60640p-3, 0x1.975f5e0553158p-3, 0x1.007fa758626aep-2, 0x1.36a08355c63dcp-2, 0x1.6e649f7d78649p-2, 0x1.a827999fcef32p-2, 0x1.e450e0d273e7ap-2, 0x1.11ab7190834ebp-1, 0x1.32e1889047ffcp-1, 0x1.561b82ab7f990p-1, 0x1.7bb99ed2990cfp-1, 0x1.a43002ae4284fp-1, 0x1.d00cbc7384d2dp-1, 0x1.fffffffffffffp-1};
 __device__ double c_atan_a[17] = {0x0.0p+0, 0x1.921fb54442d18p-5, 0x1.921fb54442d18p-4, 0x1.2d97c7f3321d2p-3, 0x1.921fb54442d18p-3, 0x1.f6a7a2955385ep-3, 0x1.2d97c7f3321d2p-2, 0x1.5fdbbe9bba775p-2, 0x1.921fb54442d18p-2, 0x1.c463abeccb2bbp-2, 0x1.f6a7a2955385ep-2, 0x1.1475cc9eedf00p-1, 0x1.2d97c7f3321d2p-1, 0x1.46b9c347764a4p-1, 0x1.5fdbbe9bba775p-1, 0x1.78fdb9effea46p-1, 0x1.921fb54442d18p-1};
-// (thresholds of the former breakpoint search; kept for reference)
-__device__ double c_atan_t[17] = {0x1.92346247a91f0p-6, 0x1.2e239ccff3831p-4, 0x1.f93183a8db9e9p-4, 0x1.635c990ce0d36p-3, 0x1.cbe4ceb4b4cf2p-3, 0x1.1b6103d3597e8p-2, 0x1.5248ae1701b18p-2, 0x1.8b00196b3d021p-2, 0x1.c5e87185e67b6p-2, 0x1.01b819b5a7cf7p-1, 0x1.220b5ef047825p-1, 0x1.44386db9ce5dap-1, 0x1.6897514751db6p-1, 0x1.8f9197bf85eeap-1, 0x1.b9a77c18c1af2p-1, 0x1.e776eafc91705p-1, 1e300};
 
 // The double constants of the polynomial and of the quadrant fix-up live in the constant bank, where DFMA / DADD
 // read them as a direct operand: as literals ptxas re-materialises each of them with two moves at every use (a

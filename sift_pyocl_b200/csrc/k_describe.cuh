@@ -5,16 +5,17 @@
 // fp32 addition is not associative, so every bin must see its contributions in exactly that order.
 //
 // Parallel scheme: 8 lanes (an "octet") per keypoint, 4 keypoints per warp.
-//   * evaluation: the 8 lanes evaluate 8 consecutive window samples (row-major); rows are clipped to the
-//     j-interval that can pass the reference's (rx, cx) test, so almost every evaluated sample is valid;
-//   * commit: the valid samples of the pass are committed ONE AT A TIME in sample order.  A sample
-//     feeds up to 8 bins (2 rows x 2 columns x 2 orientations of the trilinear interpolation) and
-//     those 8 bins always differ in the parities (row&1, col&1, ori&1) -- so lane p of the octet owns
-//     parity class p, computes exactly the one contribution of its class from the broadcast sample and
-//     adds it to shared memory.  All 8 lanes work on every committed sample, bins of one sample
-//     never collide, and each bin receives its contributions in the reference's order.
-//     (The only exception, ori == 2*pi exactly, puts both orientation terms into bin 0; the lane of
-//     the even class then adds both, in order.)
+//   * candidates: per window row, the j-interval that can pass the reference's (rx, cx) test is computed in
+//     double with a rigorous bound on the fp32 evaluation error folded in; the candidates of all rows are
+//     packed back to back and lane l of the octet takes candidates l, l + 8, ... (8 per pass);
+//   * evaluation: each lane evaluates its candidate with the reference's exact fp32 expressions and stages, for
+//     each of the 8 parity classes (row&1, col&1, ori&1), ONE (bin address, value) term: a sample feeds up to 8
+//     bins (2 rows x 2 columns x 2 orientations of the trilinear interpolation) and those always differ in all
+//     three parities.  Missing terms are +0.0 on the class's home bin (an exact no-op: every term is >= +0);
+//   * commit: lane p owns parity class p and performs 8 unconditional `hist[addr] += value` steps per pass, in
+//     sample order: all lanes busy, bins of one sample never collide, and each bin receives its contributions
+//     in the reference's order.  (ori == 2*pi exactly puts both orientation terms into bin 0; the second one is
+//     cweight * 0 = +0 there, so one add suffices.)
 //   * finish: L2 normalisation / 0.2 clamp / renormalisation / x512 -> uint8; the two
 //     sums of squares are accumulated sequentially by one lane of the octet (order matters).
 // Also performs the host-side NaN filtering and record assembly of plan.py:546-565.
@@ -51,8 +52,6 @@ struct __align__(16) DescStage {
 // lives in row (o>>1) + 4*(c>>1) + 8*(r>>1), bank 8g + 4*(r&1) + 2*(c&1) + (o&1): the 8 lanes of an octet (one
 // per parity class) and the 4 octets of the warp always hit 32 different banks -- every histogram access of the
 // commit loop is a single conflict-free wavefront.
-#define DESC_HOFF(i) /* descriptor index i = (r*4+c)*8+o -> float offset inside the octet's bank group */ \
-    (32 * ((((i) & 7) >> 1) + 4 * ((((i) >> 3) & 3) >> 1) + 8 * ((i) >> 6)) + 4 * (((i) >> 5) & 1) + 2 * (((i) >> 3) & 1) + ((i) & 1))
 __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescRows &rows, DescStage &stage,
                                                 bool act, const float4 k,
                                                 const float *__restrict__ grad, const float *__restrict__ orim,

@@ -44,4 +44,4 @@ int main(int argc,char**argv){ init(); if(argc>2) TPERT=(float)atof(argv[2]); lo
     if(ref!=0){ double u=fabs(got-ref)/ (fabs(ref)*2.220446049250313e-16); if(u>maxulp) maxulp=u; }
     else if (got!=0 || signbit(got)!=signbit(ref)) {mism++;}
   }
-  printf("n=%ld float mismatches=%ld max err=%.2f double-ulps\n",n,mism,maxulp); return 0; }
+  printf("n=%ld float mismatches=%ld max err=%.2f double-ulps\n",n,mism,maxulp); return mism!=0; }

@@ -28,9 +28,9 @@
 #define DESC_MAXROWS 100  // window rows per keypoint handled by the interval table (iradius <= 49; default sigmas need 97)
 
 struct DescRows {          // per-octet table of the non-empty window rows: only the j-interval that can be valid
-    short i[DESC_MAXROWS];         // window row i (-iradius..iradius)
-    short jlo[DESC_MAXROWS];       // first candidate j of the row
-    short jhi[DESC_MAXROWS];       // last candidate j of the row
+    signed char i[DESC_MAXROWS];   // window row i (-iradius..iradius; |.| <= 49 for tabled windows)
+    signed char jlo[DESC_MAXROWS]; // first candidate j of the row
+    signed char jhi[DESC_MAXROWS]; // last candidate j of the row
 };
 
 // Staging area of one octet for one pass (8 samples): the evaluating lane s writes, for each of the 8 parity
@@ -109,9 +109,9 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
             int jlo = (int)ceil(lo), jhi = (int)floor(hi);
             jlo = max(jlo, max(-iradius, -icol));
             jhi = min(jhi, min(iradius, grad_width - 1 - icol));
-            if (jhi < jlo) { jlo = 1; jhi = 0; }  // empty (the real-valued bounds may not fit a short)
-            rows.jlo[r] = (short)jlo;
-            rows.jhi[r] = (short)jhi;
+            if (jhi < jlo) { jlo = 1; jhi = 0; }  // empty (the real-valued bounds may not fit the table's type)
+            rows.jlo[r] = (signed char)jlo;
+            rows.jhi[r] = (signed char)jhi;
         }
         __syncwarp();
         if (l8 == 0) {  // drop the empty rows (in place: the write index never overtakes the read index)
@@ -119,9 +119,9 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
             for (int r = 0; r < nrows; r++) {
                 const int jlo = rows.jlo[r], jhi = rows.jhi[r];
                 if (jhi >= jlo) {
-                    rows.i[n] = (short)(r - iradius);
-                    rows.jlo[n] = (short)jlo;
-                    rows.jhi[n] = (short)jhi;
+                    rows.i[n] = (signed char)(r - iradius);
+                    rows.jlo[n] = (signed char)jlo;
+                    rows.jhi[n] = (signed char)jhi;
                     n++;
                     acc += jhi - jlo + 1;
                 }
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(256) k_size_order(const float4 *__restrict__ k
 // Pipeline form: octets fetch keypoints of ALL octaves from a work queue; rows with NaN are dropped
 // (plan.py:546-550); the survivors of octave o go to out[oct_offset[o] + ...], i.e. the output is grouped by
 // octave in octave order like the reference's concatenation (plan.py:555-565).
-__global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe(OctTable T, const float4 *__restrict__ kp,
+__global__ void __launch_bounds__(DESC_WARPS * 32, 7) k_describe(OctTable T, const float4 *__restrict__ kp,
                                                                const int *__restrict__ kp_tag,
                                                                const int *__restrict__ n_base_p,
                                                                const int *__restrict__ n_extra_p, int cap,

@@ -578,7 +578,7 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
         k_octave_offsets<<<1, 1, 0, st>>>(oct_valid, p->n_oct, oct_offset, p->c_nout(slot), p->c_oct(slot, 0) + 3,
                                           size_hist, size_start);
         k_size_order<<<148, 256, 0, st>>>(p->kp, p->kp_tag, n_kp, n_extra, p->kp_cap, size_start, size_fill, p->kp_order);
-        k_describe<<<148 * 6, DESC_WARPS * 32, 0, st>>>(p->table, p->kp, p->kp_tag, n_kp, n_extra, p->kp_cap,
+        k_describe<<<148 * 7, DESC_WARPS * 32, 0, st>>>(p->table, p->kp, p->kp_tag, n_kp, n_extra, p->kp_cap,
                                                         p->outs[slot], p->out_cap, oct_offset, oct_fill, q_head,
                                                         p->kp_order);
         CKL();

@@ -139,6 +139,7 @@ __device__ __forceinline__ int desc_size_class(float sigma_oct, int octsize) {
     return min(max(iradius, 0), DESC_CLASSES - 1);
 }
 
+#define ORI_MAXROWS 96  // window rows handled by the chord table (radius <= 47; the default sigmas need 41)
 // One warp per keypoint (grid-stride).  kp rows in: (peak, row, col, sigma); out: (x, y, sigma*oct, angle).
 // Extra-orientation keypoints are appended at n_base + atomicAdd(n_extra).
 // stage: [octave][3 scales][3] counters (may be null); oct_valid[o]: records octave o will emit (non-NaN rows).
@@ -147,7 +148,9 @@ __global__ void __launch_bounds__(256) k_orient(OctTable T, float4 *__restrict__
                                                  float OriSigma, int *__restrict__ stage, int *__restrict__ oct_valid,
                                                  int *__restrict__ size_hist) {
     __shared__ float s_hist[8][36];
+    __shared__ int s_clo[8][ORI_MAXROWS], s_chi[8][ORI_MAXROWS];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    int *clo = s_clo[wib], *chi = s_chi[wib];
     const int n_base = min(*n_base_p, cap);
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     float *hist = s_hist[wib];
@@ -167,37 +170,70 @@ __global__ void __launch_bounds__(256) k_orient(OctTable T, float4 *__restrict__
         const double inv_two_s2 = div_prepare(two_s2), inv_two_pi = div_prepare(2.0f * SIFTB_M_PI_F);
         const float rad2 = ((float)(radius * radius)) + 0.5f;
         const int ncols = cmax - cmin + 1, nrows = rmax - rmin + 1;
-        const int total = (ncols > 0 && nrows > 0) ? ncols * nrows : 0;
         hist[lane] = 0.0f;
         if (lane < 4) hist[32 + lane] = 0.0f;
+        // Candidate columns of every window row: the reference scans the square [rmin, rmax] x [cmin, cmax] and
+        // keeps the samples with distsq < rad2 (orientation_cpu.cl:78-85); per row those lie on the chord
+        // |c - k.z| < sqrt(rad2 - dr^2).  The chord is computed in double with margins (1e-5 relative, 1e-3
+        // absolute) far above the fp32 evaluation error of distsq (< 3e-7 relative), so it is a superset; every
+        // candidate still goes through the reference's exact fp32 test.  Windows with more than ORI_MAXROWS rows
+        // (never with the default sigmas) scan the full square.
+        const bool chord = nrows <= ORI_MAXROWS;  // warp-uniform
+        int total = (ncols > 0 && nrows > 0) ? ncols * nrows : 0;
+        if (chord && total > 0) {
+            int mine = 0;
+            for (int rr = lane; rr < nrows; rr += 32) {
+                const double drd = (double)(rmin + rr) - (double)k.y;
+                const double hw2 = (double)rad2 * 1.00001 - drd * drd * 0.99999 + 1e-3;
+                int lo = 1, hi = 0;  // empty
+                if (hw2 > 0.0) {
+                    const double hw = sqrt(hw2);
+                    lo = max(cmin, (int)ceil((double)k.z - hw));
+                    hi = min(cmax, (int)floor((double)k.z + hw));
+                    if (hi < lo) { lo = 1; hi = 0; }
+                }
+                clo[rr] = lo;
+                chi[rr] = hi;
+                mine += hi - lo + 1;
+            }
+            total = __reduce_add_sync(0xffffffffu, mine);
+        }
         __syncwarp();
-        // the gradient / orientation values of chunk c+1 are requested before chunk c is evaluated and committed
-        // (L2 / DRAM gathers: ncu showed the warps mostly waiting on these loads).  idx -> (row, column) of the
-        // window: idx / ncols through an fp32 reciprocal, exact here because (idx + 0.5) / ncols is at least
-        // 0.5 / ncols away from an integer and idx < 2^20.
-        const float inv_ncols = 1.0f / (float)max(ncols, 1);
+        // Per-lane cursor over the candidates in row-major order: lane l takes candidates l, l + 32, ...  The
+        // gradient / orientation values of chunk c+1 are requested before chunk c is evaluated and committed
+        // (L2 / DRAM gathers: ncu showed the warps mostly waiting on these loads).
         float n_gval = 0.0f, n_ang = 0.0f;
-        int n_r = 0, n_c = 0;
-        const bool big = total >= (1 << 20);  // warp-uniform; never with the default sigmas
-        auto locate = [&](int idx) {
-            const int rr = big ? idx / ncols : (int)(((float)idx + 0.5f) * inv_ncols);
-            n_r = rmin + rr;
-            n_c = cmin + (idx - rr * ncols);
-            if (idx < total) {
+        int rcur = -1, ccur = lane, cend = -1, n_r = 0, n_c = 0;
+        bool n_ok = false;
+        auto locate = [&]() {
+            while (ccur > cend && rcur < nrows) {  // into the next row(s); empty rows are stepped over
+                const int over = ccur - cend - 1;
+                rcur++;
+                if (rcur < nrows) {
+                    const int lo = chord ? clo[rcur] : cmin;
+                    cend = chord ? chi[rcur] : cmax;
+                    ccur = lo + over;
+                }
+            }
+            n_ok = rcur < nrows && total > 0;
+            n_r = rmin + rcur;
+            n_c = ccur;
+            if (n_ok) {
                 const long q = (long)n_r * Gpitch + n_c;
                 n_gval = grad[q];
                 n_ang = ori[q];
             }
+            ccur += 32;
         };
-        locate(lane);
+        locate();
         for (int base = 0; base < total; base += 32) {
-            const int idx = base + lane;
             const float gval = n_gval, angle = n_ang;
             const int r = n_r, c = n_c;
-            locate(idx + 32);
+            const bool ok = n_ok;
+            locate();
             int bin = -1;
             float w = 0.0f;
-            if (idx < total) {
+            if (ok) {
                 float dif = ((float)r - k.y);
                 float distsq = dif * dif;
                 dif = ((float)c - k.z);

@@ -63,7 +63,7 @@ __device__ __forceinline__ void grad_one(float xgrad, float ygrad, float &gr, fl
     gr = sqrtf(xgrad * xgrad + ygrad * ygrad);
     orv = cr_atan2f_fast(-ygrad, xgrad, K);
 }
-__global__ void __launch_bounds__(128) k_gradient4(GradArgs a) {
+__global__ void __launch_bounds__(128, 8) k_gradient4(GradArgs a) {
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, z = blockIdx.z, lane = threadIdx.x & 31;
     const int y0 = blockIdx.y * GRAD4_ROWS;
     const float *g = a.g[z];

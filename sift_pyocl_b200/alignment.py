@@ -100,13 +100,11 @@ class LinearAlign(object):
             kp = self.sift.keypoints(data)
             logger.debug("mod image keypoints: %s" % kp.size)
             raw_matching = self.match.match(self.ref_kp, kp, raw_results=True)
-            matching = numpy.recarray(shape=raw_matching.shape, dtype=MatchPlan.dtype_kp)
             len_match = raw_matching.shape[0]
             if len_match == 0:
                 logger.warning("No matching keypoints")
                 return
-            matching[:, 0] = self.ref_kp[raw_matching[:, 0]]
-            matching[:, 1] = kp[raw_matching[:, 1]]
+            matching = _lib.pair_records(self.ref_kp, raw_matching[:, 0], kp, raw_matching[:, 1])
             if orsa:
                 logger.warning("feature is not available. No ORSA filtering")  # alignment.py:260-264
             if (len_match < 3 * 6) or (shift_only):  # 3 points per DOF

@@ -75,9 +75,7 @@ class MatchPlan(object):
             if raw_results:
                 result = match
             else:
-                result = numpy.recarray(shape=(size, 2), dtype=self.dtype_kp)
-                result[:, 0] = nkp1[match[:size, 0]]
-                result[:, 1] = nkp2[match[:size, 1]]
+                result = _lib.pair_records(nkp1, match[:size, 0], nkp2, match[:size, 1])
         return result
 
     __call__ = match

@@ -95,3 +95,25 @@ def test_utils_host_logic():
     m[:, 1].x = a * m[:, 0].x + b * m[:, 0].y + c
     m[:, 1].y = d * m[:, 0].x + e * m[:, 0].y + f
     assert np.allclose(matching_correction(m), [a, b, c, d, e, f], atol=1e-4)
+
+
+def test_pair_records_equals_structured_indexing():
+    """_lib.pair_records (raw 144-byte row gather) == the reference's field-wise result[:, 0] = kp1[idx] form
+    (match.py:267-270), including empty results and non-contiguous inputs."""
+    import numpy as np
+    from sift_pyocl_b200._lib import dtype_kp, pair_records
+    rng = np.random.default_rng(2)
+    k1, k2 = np.zeros(50, dtype_kp), np.zeros(80, dtype_kp)
+    for k in (k1, k2):
+        k["x"], k["y"] = rng.random(k.size), rng.random(k.size)
+        k["scale"], k["angle"] = rng.random(k.size), rng.random(k.size)
+        k["desc"] = rng.integers(0, 256, (k.size, 128))
+    i1, i2 = rng.integers(0, 50, 33).astype(np.int32), rng.integers(0, 80, 33).astype(np.int32)
+    want = np.recarray((33, 2), dtype_kp)
+    want[:, 0], want[:, 1] = k1[i1], k2[i2]
+    got = pair_records(k1.view(np.recarray), i1, k2[::1], i2)
+    assert got.dtype == dtype_kp and got.shape == (33, 2) and got.tobytes() == want.tobytes()
+    assert np.array_equal(got[:, 1].desc, k2["desc"][i2]) and np.array_equal(got[:, 0].x, k1["x"][i1])
+    strided = np.concatenate([k2, k2])[::2]  # non-contiguous view
+    assert pair_records(k1, i1, strided, i2 % strided.size).shape == (33, 2)
+    assert pair_records(k1, i1[:0], k2, i2[:0]).shape == (0, 2)

@@ -95,11 +95,11 @@ def keypoints_batch(plan, images, group=None, gather=True):
     n_images = len(images)
     mine = shard_indices(n_images, rank, world)
     get = images if callable(images) else images.__getitem__
-    local, sizes = [], []
-    for i in mine:
-        kp = plan.keypoints(get(i))
-        local.append(kp)
-        sizes.append(kp.size)
+    # the rank's images go through the plan's pipelined form when it has one (copies of one image overlap the
+    # kernels of the others), else one at a time
+    many = getattr(plan, "keypoints_many", None)
+    local = list(many(get(i) for i in mine)) if many is not None else [plan.keypoints(get(i)) for i in mine]
+    sizes = [kp.size for kp in local]
     out = [None] * n_images
     if not gather:
         for i, kp in zip(mine, local):

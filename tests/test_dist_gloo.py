@@ -32,6 +32,16 @@ class _StubPlan(object):
         return kp.view(np.recarray)
 
 
+class _StubPipelinedPlan(_StubPlan):
+    """A plan with the pipelined generator form (SiftPlan.keypoints_many)."""
+    calls = 0
+
+    def keypoints_many(self, images):
+        for im in images:
+            type(self).calls += 1
+            yield self.keypoints(im)
+
+
 def _worker(rank, world, port, n_images, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -43,6 +53,9 @@ def _worker(rank, world, port, n_images, q):
         want = _StubPlan().keypoints(images[i])
         ok = ok and kp.size == want.size and np.array_equal(kp.x, want.x) and np.array_equal(kp.desc, want.desc)
     mine = sdist.shard_indices(n_images, rank, world)
+    piped = sdist.keypoints_batch(_StubPipelinedPlan(), images)  # same result through keypoints_many
+    ok = ok and _StubPipelinedPlan.calls == len(mine)
+    ok = ok and all(a.size == b.size and np.array_equal(a.desc, b.desc) for a, b in zip(out, piped))
     local_only = sdist.keypoints_batch(_StubPlan(), images, gather=False)
     ok = ok and all((local_only[i] is not None) == (i in mine) for i in range(n_images))
     q.put((rank, bool(ok)))

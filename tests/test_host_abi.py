@@ -117,3 +117,25 @@ def test_pair_records_equals_structured_indexing():
     strided = np.concatenate([k2, k2])[::2]  # non-contiguous view
     assert pair_records(k1, i1, strided, i2 % strided.size).shape == (33, 2)
     assert pair_records(k1, i1[:0], k2, i2[:0]).shape == (0, 2)
+
+
+def test_matching_correction_equals_pinv_form():
+    """utils.matching_correction (two decoupled 3-parameter least-squares problems) == the pinv(X).y completion of
+    the reference's 2N x 6 system (utils.py:156-189 + test/test_transform.py:118-133)."""
+    import numpy as np
+    from sift_pyocl_b200._lib import dtype_kp
+    from sift_pyocl_b200.utils import matching_correction
+    rng = np.random.default_rng(4)
+    for n in (3, 18, 500):
+        m = np.zeros((n, 2), dtype_kp).view(np.recarray)
+        m.x[:, 0], m.y[:, 0] = rng.random(n) * 900, rng.random(n) * 700
+        m.x[:, 1] = 1.02 * m.x[:, 0] - 0.03 * m.y[:, 0] + 4 + rng.normal(0, 0.2, n)
+        m.y[:, 1] = 0.02 * m.x[:, 0] + 0.97 * m.y[:, 0] - 3 + rng.normal(0, 0.2, n)
+        X = np.zeros((2 * n, 6))
+        X[::2, 0], X[::2, 1], X[::2, 2] = m.x[:, 0], m.y[:, 0], 1
+        X[1::2, 3], X[1::2, 4], X[1::2, 5] = m.x[:, 0], m.y[:, 0], 1
+        y = np.zeros((2 * n, 1))
+        y[::2, 0], y[1::2, 0] = m.x[:, 1], m.y[:, 1]
+        want = np.dot(np.linalg.pinv(X), y).ravel()
+        got = matching_correction(m)
+        assert got.shape == (6,) and np.allclose(got, want, rtol=1e-9, atol=1e-9)

@@ -35,9 +35,10 @@ if ROOT not in sys.path:
 SIZE = 4096
 OCTAVES = 3
 N_IMAGES = 2  # distinct images cycled per rank (working set per image ~1.2 GB >> 126 MB L2)
-# dram__bytes_read.sum + dram__bytes_write.sum per octave-0 blur+DoG launch from the committed ncu --set full
-# capture (profiles/r01c_ncu_full_final.csv), averaged over the five tap counts; None until measured
-TRAFFIC_PER_LAUNCH = 164.3e6
+# dram__bytes_read.sum + dram__bytes_write.sum of all blur launches of one step, summed from the committed
+# ncu --set full capture of the final kernels of the round (profiles/, see TRAFFIC_NOTE); None until measured
+TRAFFIC_PER_STEP = None
+TRAFFIC_NOTE = "not captured yet for this kernel revision"
 
 
 def _peaks():
@@ -107,6 +108,25 @@ def _workload_name():
     return "SiftPlan %dx%d float32, %d octaves x 3 scales" % (SIZE, SIZE, OCTAVES)
 
 
+def _config(world):
+    """The workload description: IDENTICAL in both arms (the driver compares the dicts)."""
+    return {"workload": _workload_name(), "images_per_step_per_gpu": 1,
+            "image": "multiscale noise (sift_pyocl_b200.utils.multiscale_image), seeds 1234+",
+            "l2": "inputs larger than L2: %d distinct 67 MB images cycled per GPU, ~1.2 GB of planes rewritten per step"
+                  % N_IMAGES,
+            "gather": "NCCL all-gather of the keypoint records every step" if world > 1 else "none (1 GPU)"}
+
+
+def _cpu_leg(siftref, img, threads, reps):
+    """keypoints/s of the oracle port on ``threads`` host threads (bounded sample: ``reps`` images)."""
+    siftref.set_num_threads(threads)
+    n, t0 = 0, time.perf_counter()
+    for _ in range(reps):
+        n += siftref.keypoints(img, octave_max=OCTAVES).size
+    dt = time.perf_counter() - t0
+    return n / dt, 1e3 * dt / reps
+
+
 def run_reference(args):
     """CPU arm: the oracle port of the reference's kernels on all host threads (the reference's own
     OpenCL path cannot run: no PyOpenCL / ICD in the image)."""
@@ -128,9 +148,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "keypoints/sec on 4096x4096 float32", "value": v, "unit": "keypoints/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": _workload_name(), "image": "multiscale noise seed 1234"},
+            "config": _config(int(os.environ.get("WORLD_SIZE", "1"))),
             "cpu_baseline": {"value": v, "unit": "keypoints/s", "cores": cores, "kind": "port",
-                             "sample": "%d x one %dx%d image, OpenMP on %d threads" % (args.steps, SIZE, SIZE, cores)},
+                             "sample": "%d x one %dx%d image (seed 1234), OpenMP on %d threads" % (args.steps, SIZE, SIZE, cores)},
             "e2e": {"value": v, "unit": "keypoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -148,9 +168,11 @@ def blur_bytes_per_step(plan):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--repeats", type=int, default=5, help="the K-step timed region is measured this many times; "
+                    "the line reports the median region (every region times exactly K steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
@@ -190,144 +212,184 @@ def main():
         dev_imgs.append(torch.from_numpy(img).cuda())
     torch.cuda.synchronize()
 
-    def gather(n):
-        if world > 1:
-            sdist.allgather_records(sdist.device_records_tensor(plan, n))
-
-    def device_step(i):
-        plan.submit(dev_imgs[i % N_IMAGES])
-        n = plan.collect(records=False)
-        gather(n)
-        return n
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # warm-up; at N > 1 the ranks also agree on the slab size of the per-step record exchange
+    n_max = 0
     for i in range(args.warmup):
-        device_step(i)
-    plan.set_profile(True)
+        plan.submit(dev_imgs[i % N_IMAGES])
+        n_max = max(n_max, plan.collect(records=False))
+    exchange = None
+    if world > 1:
+        cap = torch.tensor([n_max], dtype=torch.int64, device="cuda")
+        dist.all_reduce(cap, op=dist.ReduceOp.MAX)
+        exchange = sdist.RecordExchange(int(int(cap.item()) * 1.3) + 1024, "cuda:%d" % local_rank)
+        for i in range(2):  # NCCL warm-up of the exchange itself
+            plan.submit(dev_imgs[i % N_IMAGES])
+            n = plan.collect(records=False)
+            exchange.begin(sdist.device_records_tensor(plan, n), plan).finish()
+
+    def device_region(profile):
+        """K steps, device-resident input, records left on the device; software-pipelined: step i+1 is enqueued
+        before step i is collected, the exchange of step i (N > 1) is completed one step later."""
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nkp, blur_ms, blur0_ms, first_ms, stage_ms = 0, 0.0, 0.0, 0.0, {}
+        barrier()
+        ev0.record(stream)
+        t0 = time.perf_counter()
+        pending = None
+        plan.submit(dev_imgs[0])
+        for i in range(args.steps):
+            if i + 1 < args.steps:
+                plan.submit(dev_imgs[(i + 1) % N_IMAGES])
+            n = plan.collect(records=False)
+            nkp += n
+            if exchange is not None:
+                started = exchange.begin(sdist.device_records_tensor(plan, n), plan)
+                if pending is not None:
+                    pending.finish()
+                pending = started
+            if profile:
+                for name, ms in plan.fetch_events():
+                    key = name.split(" octave")[0]
+                    stage_ms[key] = stage_ms.get(key, 0.0) + ms
+                    if "blur" in name:
+                        blur_ms += ms
+                    if name == "blur + DoG octave 0":
+                        blur0_ms += ms
+                    if name == "normalize + init blur":
+                        first_ms += ms
+        cur = torch.cuda.current_stream()
+        cur.wait_stream(stream)
+        if exchange is not None:
+            cur.wait_stream(exchange.stream)  # the last exchange belongs to the timed region
+        ev1.record(cur)
+        if pending is not None:
+            pending.finish()
+        barrier()
+        wall = time.perf_counter() - t0
+        return ev0.elapsed_time(ev1) / 1e3, nkp, wall, blur_ms, blur0_ms, first_ms, stage_ms
+
+    def e2e_region():
+        """K steps through the public API with HOST buffers: pinned image -> H2D -> kernels -> D2H records ->
+        numpy recarray every step (SiftPlan.keypoints_many keeps three images in flight)."""
+        barrier()
+        e2e_kp, d2h, t0 = 0, 0, time.perf_counter()
+        pending = None
+        for kp in plan.keypoints_many(host_imgs[i % N_IMAGES] for i in range(args.steps)):
+            e2e_kp += kp.size
+            d2h += kp.size * 144 + 4 * (1 + 13 * plan.octave_max + 4)
+            if exchange is not None:
+                started = exchange.begin(sdist.device_records_tensor(plan, kp.size), plan)
+                if pending is not None:
+                    pending.finish()
+                pending = started
+        if pending is not None:
+            pending.finish()
+        barrier()
+        return time.perf_counter() - t0, e2e_kp, d2h
+
+    def sync_region():
+        """the same, strictly one image at a time: SiftPlan.keypoints(host image), the reference's call"""
+        barrier()
+        n, t0 = 0, time.perf_counter()
+        for i in range(args.steps):
+            n += plan.keypoints(host_imgs[i % N_IMAGES]).size
+        barrier()
+        return time.perf_counter() - t0, n
+
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = plan.launches
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    nkp, blur_ms, blur0_ms, stage_ms = 0, 0.0, 0.0, {}
-    ev0.record(stream)
-    t0 = time.perf_counter()
-    # K steps, software-pipelined: the kernels of step i+1 are enqueued before step i is collected, so the
-    # all-gather of step i's records (N > 1) and the host-side bookkeeping overlap the next image's kernels
-    plan.submit(dev_imgs[0])
-    for i in range(args.steps):
-        if i + 1 < args.steps:
-            plan.submit(dev_imgs[(i + 1) % N_IMAGES])
-        n = plan.collect(records=False)
-        gather(n)
-        nkp += n
-        for name, ms in plan.fetch_events():
-            key = name.split(" octave")[0]
-            stage_ms[key] = stage_ms.get(key, 0.0) + ms
-            if "blur" in name:
-                blur_ms += ms
-            if name == "blur + DoG octave 0":
-                blur0_ms += ms
-    cur = torch.cuda.current_stream()
-    cur.wait_stream(stream)  # the gather (if any) runs on torch's stream after the plan's stream
-    ev1.record(cur)
-    barrier()
-    wall = time.perf_counter() - t0
-    dev_s = ev0.elapsed_time(ev1) / 1e3
-    launches = plan.launches - launches0
+    regions = [device_region(False) for _ in range(max(args.repeats, 1))]
+    launches = (plan.launches - launches0) // max(args.repeats, 1)
+    plan.set_profile(True)   # stage breakdown + roofline launches: a separate region (event pairs cost ~1 %)
+    prof = device_region(True)
     plan.set_profile(False)
-
-    # end to end through the public API with host buffers: every step copies its image from pinned host
-    # memory to the device and its records back into host memory.  SiftPlan.keypoints_many keeps three images in
-    # flight so the copies of one image overlap the kernels of the others (all of it inside the timed region).
     for kp in plan.keypoints_many(host_imgs[i % N_IMAGES] for i in range(3)):
         pass
-    barrier()
-    e2e_kp, d2h, t0 = 0, 0, time.perf_counter()
-    pending = None  # N > 1: the all-gather of step i is completed while step i+1 runs (counts first, then payload)
-    for kp in plan.keypoints_many(host_imgs[i % N_IMAGES] for i in range(args.steps)):
-        e2e_kp += kp.size
-        d2h += kp.size * 144 + 4 * (1 + 13 * plan.octave_max + 2)
-        if world > 1:
-            started = sdist.allgather_records_begin(sdist.device_records_tensor(plan, kp.size))
-            if pending is not None:
-                pending.finish()
-            pending = started
-    if pending is not None:
-        pending.finish()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    # the same, strictly one image at a time (SiftPlan.keypoints, the reference's call)
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        plan.keypoints(host_imgs[i % N_IMAGES])
-    barrier()
-    e2e_sync_s = time.perf_counter() - t0
+    e2e_regions = [e2e_region() for _ in range(max(min(args.repeats, 3), 1))]
+    sync_s, sync_kp = sync_region()
     sampler.stop_flag = True
 
+    def median_by(rs, key):
+        rs = sorted(rs, key=key)
+        return rs[len(rs) // 2]
+    dev_s, nkp, wall = median_by(regions, lambda r: r[0])[:3]
+    e2e_s, e2e_kp, d2h = median_by(e2e_regions, lambda r: r[0])
+    all_dev_s = [r[0] for r in regions]
     if world > 1:
-        t = torch.tensor([dev_s, e2e_s, float(nkp), float(e2e_kp), float(launches)], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dev_s, e2e_s, sync_s, float(nkp), float(e2e_kp), float(launches), float(sync_kp)],
+                         dtype=torch.float64, device="cuda")
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        dev_s, e2e_s = float(tmax[0]), float(tmax[1])
-        nkp, e2e_kp, launches = float(t[2]), float(t[3]), int(t[4])
+        dev_s, e2e_s, sync_s = float(tmax[0]), float(tmax[1]), float(tmax[2])
+        nkp, e2e_kp, launches, sync_kp = float(t[3]), float(t[4]), int(t[5]), float(t[6])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
     peak, peak_src = _peaks()
-    bbytes = blur_bytes_per_step(plan) * args.steps
-    achieved_all = bbytes / (blur_ms / 1e3) / 1e9 if blur_ms > 0 else None
-    # dominant kernel: the five blur+DoG launches on the full-resolution planes (octave 0), 12*W*H bytes each
+    _, _, _, blur_ms, blur0_ms, first_ms, stage_ms = prof
+    bbytes = blur_bytes_per_step(plan)
+    n_blur = 1 + 5 * plan.octave_max
+    achieved_all = bbytes * args.steps / (blur_ms / 1e3) / 1e9 if blur_ms > 0 else None
     b0bytes = 5 * 12 * SIZE * SIZE
-    achieved = b0bytes * args.steps / (blur0_ms / 1e3) / 1e9 if blur0_ms > 0 else None
+    achieved0 = b0bytes * args.steps / (blur0_ms / 1e3) / 1e9 if blur0_ms > 0 else None
+    achieved_first = 8 * SIZE * SIZE * args.steps / (first_ms / 1e3) / 1e9 if first_ms > 0 else None
     line = {
         "metric": "keypoints/sec on 4096x4096 float32", "value": nkp / dev_s, "unit": "keypoints/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": _workload_name(), "images_per_step_per_gpu": 1,
-                   "image": "multiscale noise, seeds 1234+", "keypoints_per_image": nkp / args.steps / world,
-                   "l2": "inputs larger than L2: %d distinct 67 MB images cycled, ~1.2 GB of planes rewritten per step"
-                         % N_IMAGES,
-                   "gather": "NCCL all-gather of records per step" if world > 1 else "none (1 GPU)"},
+        "config": _config(world),
+        "keypoints_per_image": nkp / args.steps / world,
+        "timed_regions": {"repeats": len(regions), "reported": "median", "ms_per_step_each":
+                          [1e3 * x / args.steps for x in all_dev_s]},
         "e2e": {"value": e2e_kp / e2e_s, "unit": "keypoints/s", "h2d_bytes_per_step": SIZE * SIZE * 4,
                 "d2h_bytes_per_step": int(d2h / args.steps), "ms_per_step": 1e3 * e2e_s / args.steps,
-                "api": "SiftPlan.keypoints_many (3 images in flight)",
-                "ms_per_step_one_at_a_time": 1e3 * e2e_sync_s / args.steps},
+                "api": "SiftPlan.keypoints_many (three images in flight; pinned host image in, numpy recarray out)",
+                "one_at_a_time": {"api": "SiftPlan.keypoints(host image), the reference's call", "value":
+                                  sync_kp / sync_s, "ms_per_step": 1e3 * sync_s / args.steps}},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm",
-                     "kernel": "k_blur_tma: the 5 blur+DoG launches on the 4096x4096 planes (octave 0), 11..27 taps",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                     "traffic": TRAFFIC_PER_LAUNCH, "peak_source": peak_src + " (burst copy figure)",
-                     "algorithmic_bytes_per_launch": 12 * SIZE * SIZE, "launches_per_step": 5,
-                     "avg_launch_ms": blur0_ms / args.steps / 5,
-                     "all_blur_launches": {"note": "all %d blur launches of the step incl. first blur and octaves >= 1"
-                                                   % (1 + 5 * plan.octave_max),
-                                           "achieved": achieved_all, "frac": (achieved_all / peak) if achieved_all else None,
-                                           "algorithmic_bytes_per_step": bbytes // args.steps,
-                                           "ms_per_step": blur_ms / args.steps}},
+                     "kernel": "k_blur_tma, the whole Gaussian pyramid: all %d blur launches of a step "
+                               "(normalise + first blur, then 5 blur+DoG per octave on %s planes)"
+                               % (n_blur, " / ".join("%dx%d" % (int(w), int(h)) for w, h in plan.scales)),
+                     "achieved": achieved_all, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved_all / peak) if achieved_all else None,
+                     "traffic": TRAFFIC_PER_STEP, "traffic_note": TRAFFIC_NOTE,
+                     "peak_source": peak_src + " (burst copy figure)",
+                     "algorithmic_bytes_per_step": bbytes, "launches_per_step": n_blur,
+                     "avg_launch_ms": blur_ms / args.steps / n_blur, "ms_per_step": blur_ms / args.steps,
+                     "octave0_launches": {"note": "the 5 blur+DoG launches on the 4096x4096 planes, 12*W*H bytes each",
+                                          "achieved": achieved0, "frac": (achieved0 / peak) if achieved0 else None,
+                                          "avg_launch_ms": blur0_ms / args.steps / 5},
+                     "first_blur": {"note": "normalise fused into the first blur, 8*W*H bytes", "achieved": achieved_first,
+                                    "frac": (achieved_first / peak) if achieved_first else None,
+                                    "avg_launch_ms": first_ms / args.steps}},
         "stage_ms_per_step": {k: v / args.steps for k, v in sorted(stage_ms.items())},
+        "stage_ms_note": "CUDA events on the plan's stream in a separate K-step region with profiling on",
         "wall_ms_per_step": 1e3 * wall / args.steps,
         "clocks": sampler.summary(),
     }
     if not args.no_cpu_baseline and world == 1:
         from oracle import siftref
-        siftref.set_num_threads(os.cpu_count())
         img = np.array(host_imgs[0])
-        siftref.keypoints(img, octave_max=OCTAVES)
-        reps, t0 = 3, time.perf_counter()
-        for _ in range(reps):
-            n_cpu = siftref.keypoints(img, octave_max=OCTAVES).size
-        dt = (time.perf_counter() - t0) / reps
-        line["cpu_baseline"] = {"value": n_cpu / dt, "unit": "keypoints/s", "cores": siftref.num_threads(),
-                                "kind": "port", "ms_per_image": 1e3 * dt,
-                                "sample": "%d x one %dx%d image (seed 1234), oracle/libsiftref.so OpenMP" % (reps, SIZE, SIZE)}
+        siftref.set_num_threads(os.cpu_count())
+        cores = siftref.num_threads()
+        siftref.keypoints(img, octave_max=OCTAVES)  # warm-up
+        v_all, ms_all = _cpu_leg(siftref, img, cores, 3)
+        v_one, ms_one = _cpu_leg(siftref, img, 1, 1)
+        line["cpu_baseline"] = {"value": v_all, "unit": "keypoints/s", "cores": cores, "kind": "port",
+                                "ms_per_image": ms_all,
+                                "single_thread": {"value": v_one, "ms_per_image": ms_one, "cores": 1},
+                                "sample": "3 x one %dx%d image (seed 1234) on all %d host threads + 1 x the same image "
+                                          "on one thread, oracle/libsiftref.so (OpenMP)" % (SIZE, SIZE, cores)}
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:

@@ -79,6 +79,13 @@ SIFTB_API int siftb_plan_octave_shape(const siftb_plan *plan, int octave, int *w
 SIFTB_API uint64_t siftb_plan_device_bytes(const siftb_plan *plan);   /* plan.py:226 _calc_memory */
 SIFTB_API void *siftb_plan_stream(const siftb_plan *plan);            /* cudaStream_t of the plan's queue */
 SIFTB_API int siftb_plan_set_profile(siftb_plan *plan, int enable);   /* plan.py:185-186 PROFILING_ENABLE */
+SIFTB_API int siftb_plan_device(const siftb_plan *plan);               /* CUDA ordinal the plan lives on */
+/* Orders the plan's queue after everything enqueued so far on `stream` (a cudaStream_t of the plan's device; the
+ * handles 0x1 / 0x2 are CUDA's legacy / per-thread default streams): call it before handing a device-resident
+ * image to keypoints()/submit() when that image is produced asynchronously on another stream, and after an
+ * external stream has been asked to read siftb_plan_result_dev() memory.  Replaces the implicit ordering of the
+ * reference's single in-order command queue shared with its pyopencl.array inputs (plan.py:185-188,451). */
+SIFTB_API int siftb_plan_wait_stream(siftb_plan *plan, void *stream);
 /* number of CUDA kernels this plan has launched since it was created (bench.py's gpu_launches) */
 SIFTB_API uint64_t siftb_plan_launches(const siftb_plan *plan);
 
@@ -104,6 +111,9 @@ SIFTB_API int siftb_plan_collect(siftb_plan *plan, siftb_kp *out, int cap, int *
                        float *minmax);   /* out == NULL: wait and return the counts only (records stay on the device) */
 /* results left on the device (valid until the next submit): records, count */
 SIFTB_API int siftb_plan_result_dev(const siftb_plan *plan, const siftb_kp **dev_records, const int **dev_count);
+
+/* host copy of the records of the most recently collected run (for callers that collected with out == NULL) */
+SIFTB_API int siftb_plan_fetch_records(siftb_plan *plan, siftb_kp *out, int cap, int *n_out);
 
 /* profile=True event list, plan.py:826-847 log_profile: names[i] ran for ms[i] on the device.
  * Pointers stay valid until the next keypoints()/submit() on the plan. */
@@ -143,12 +153,43 @@ SIFTB_API int siftb_orientation(const float *kp4_in, int n, const float *grad, c
 SIFTB_API int siftb_descriptor(const float *kp4, int n, const float *grad, const float *ori, int height, int width,
                      int octsize, uint8_t *desc);
 
-/* ---- MatchPlan.match (match.py:200-272, matching_{cpu,gpu}.cl:matching) ---------------------- */
+/* ---- MatchPlan (match.py:52-272, matching_{cpu,gpu}.cl:matching) ----------------------------- */
+/* The matcher owns persistent device buffers like the reference's buffers["Kp_1"], ["Kp_2"], ["match"], ["cnt"]
+ * (match.py:129-160).  Keypoint lists are copied into it from host OR device memory (the reference accepts
+ * pyopencl arrays, match.py:216-239) and stay resident until replaced, so a caller that matches many frames
+ * against one reference list (LinearAlign, alignment.py:157) sends that list once. */
+typedef struct siftb_matcher siftb_matcher;
+SIFTB_API int siftb_matcher_create(int device, siftb_matcher **out);          /* match.py:77-127 __init__ */
+SIFTB_API int siftb_matcher_destroy(siftb_matcher *m);
+SIFTB_API int siftb_matcher_set_profile(siftb_matcher *m, int enable);
+SIFTB_API void *siftb_matcher_stream(const siftb_matcher *m);
+/* which = 0 / 1: first / second list of match(); records: n dtype_kp records in host (on_device = 0) or device
+ * memory of the matcher's device (on_device = 1, e.g. siftb_plan_result_dev) -- match.py:216-239 */
+SIFTB_API int siftb_matcher_set_list(siftb_matcher *m, int which, const siftb_kp *records, int n, int on_device);
+/* match.py:241-263: pairs_host (may be NULL): int[cap][2] = (index in list 0, index in list 1); n_found = value of
+ * the device counter (may exceed cap; at most cap pairs are stored) */
+SIFTB_API int siftb_matcher_run(siftb_matcher *m, float ratio_th, int cap, int *pairs_host, int *n_found);
+/* the matched keypoints of the last run, gathered on the device (replaces the host-side fancy indexing of
+ * match.py:267-270): out8 = float[m][8] = (x, y, scale, angle) of list 0 then of list 1;
+ * out = siftb_kp[m][2], the reference's result recarray.  m = min(n_found, cap) of the last run. */
+SIFTB_API int siftb_matcher_pairs(siftb_matcher *m, int *pairs_host);   /* int[m][2], the index pairs again */
+SIFTB_API int siftb_matcher_pair_coords(siftb_matcher *m, float *out8);
+SIFTB_API int siftb_matcher_pair_records(siftb_matcher *m, siftb_kp *out);
+/* profile=True event list (match.py:226-263): names[i] ran for ms[i]; accumulates until reset != 0 */
+SIFTB_API int siftb_matcher_events(siftb_matcher *m, const char *const **names, const float **ms, int *n, int reset);
+
+/* stateless form of the above (create, load both lists, run, destroy) */
 /* pairs: int[cap][2] = (index in kp1, index in kp2); n = number found (counter, may exceed cap) */
 SIFTB_API int siftb_match_l1(const siftb_kp *kp1, int n1, const siftb_kp *kp2, int n2, float ratio_th, int on_device,
                    int device, int *pairs, int cap, int *n);
 
 /* ---- LinearAlign's warp (alignment.py:329-349, transform.cl:22 transform) -------------------- */
+/* Warp of the image of the plan's most recent keypoints() run, which is still resident on the device (the
+ * reference uploads a frame once into buffers["input"] for both SIFT and the warp, alignment.py:242-246).
+ * The image must be float32 or RGB8.  out: out_height*out_width floats (or *3 bytes), host or device memory. */
+SIFTB_API int siftb_plan_warp_last(siftb_plan *plan, const float matrix[4], const float offset[2], float fill, int mode,
+                                   void *out, int out_height, int out_width, int out_on_device);
+/* stateless, host in / host out */
 SIFTB_API int siftb_transform(const float *image, int height, int width, float *out, int out_height, int out_width,
                     const float matrix[4], const float offset[2], float fill, int mode, int device);
 
@@ -156,6 +197,19 @@ SIFTB_API int siftb_transform(const float *image, int height, int width, float *
 SIFTB_API int siftb_transform_rgb(const uint8_t *image, int height, int width, uint8_t *out, int out_height,
                                   int out_width, const float matrix[4], const float offset[2], float fill, int mode,
                                   int device);
+
+/* ---- multi-GPU helpers (no reference equivalent: the reference is single-device) ---------------
+ * One communicator per process / GPU over NCCL.  Images of a batch are independent, so ranks only exchange
+ * results: the ragged keypoint arrays are all-gathered (counts, then records padded to the largest count). */
+#define SIFTB_COMM_ID_BYTES 128
+typedef struct siftb_comm siftb_comm;
+SIFTB_API int siftb_comm_unique_id(char id[SIFTB_COMM_ID_BYTES]);   /* rank 0 creates it, ships it to the others */
+SIFTB_API int siftb_comm_init(int rank, int nranks, const char id[SIFTB_COMM_ID_BYTES], int device, siftb_comm **out);
+SIFTB_API int siftb_comm_destroy(siftb_comm *comm);
+/* dev_records: this rank's n_local records in device memory; counts: int[nranks] (host); out_host (may be NULL):
+ * all records grouped by rank, rank 0 first; n_total = sum of counts (> cap_out -> SIFTB_EOVERFLOW) */
+SIFTB_API int siftb_allgather_kp(siftb_comm *comm, const siftb_kp *dev_records, int n_local, int *counts,
+                                 siftb_kp *out_host, int cap_out, int *n_total);
 
 #ifdef __cplusplus
 }

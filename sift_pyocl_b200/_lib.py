@@ -47,10 +47,13 @@ SIGNATURES = {
     "siftb_plan_stream": (c_void_p, [c_void_p]),
     "siftb_plan_set_profile": (c_int, [c_void_p, c_int]),
     "siftb_plan_launches": (c_u64, [c_void_p]),
+    "siftb_plan_device": (c_int, [c_void_p]),
+    "siftb_plan_wait_stream": (c_int, [c_void_p, c_void_p]),
     "siftb_plan_keypoints": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int_p, c_int_p, c_float_p]),
     "siftb_plan_submit": (c_int, [c_void_p, c_void_p, c_int]),
     "siftb_plan_collect": (c_int, [c_void_p, c_void_p, c_int, c_int_p, c_int_p, c_float_p]),
     "siftb_plan_result_dev": (c_int, [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]),
+    "siftb_plan_fetch_records": (c_int, [c_void_p, c_void_p, c_int, c_int_p]),
     "siftb_plan_events": (c_int, [c_void_p, ctypes.POINTER(ctypes.POINTER(ctypes.c_char_p)),
                                   ctypes.POINTER(c_float_p), c_int_p]),
     "siftb_plan_stage_counts": (c_int, [c_void_p, c_int_p]),
@@ -66,6 +69,22 @@ SIGNATURES = {
     "siftb_orientation": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
                                   c_int_p]),
     "siftb_descriptor": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "siftb_matcher_create": (c_int, [c_int, ctypes.POINTER(c_void_p)]),
+    "siftb_matcher_destroy": (c_int, [c_void_p]),
+    "siftb_matcher_set_profile": (c_int, [c_void_p, c_int]),
+    "siftb_matcher_stream": (c_void_p, [c_void_p]),
+    "siftb_matcher_set_list": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int]),
+    "siftb_matcher_run": (c_int, [c_void_p, c_float, c_int, c_void_p, c_int_p]),
+    "siftb_matcher_pairs": (c_int, [c_void_p, c_void_p]),
+    "siftb_matcher_pair_coords": (c_int, [c_void_p, c_void_p]),
+    "siftb_matcher_pair_records": (c_int, [c_void_p, c_void_p]),
+    "siftb_matcher_events": (c_int, [c_void_p, ctypes.POINTER(ctypes.POINTER(ctypes.c_char_p)),
+                                     ctypes.POINTER(c_float_p), c_int_p, c_int]),
+    "siftb_plan_warp_last": (c_int, [c_void_p, c_float_p, c_float_p, c_float, c_int, c_void_p, c_int, c_int, c_int]),
+    "siftb_comm_unique_id": (c_int, [c_void_p]),
+    "siftb_comm_init": (c_int, [c_int, c_int, c_void_p, c_int, ctypes.POINTER(c_void_p)]),
+    "siftb_comm_destroy": (c_int, [c_void_p]),
+    "siftb_allgather_kp": (c_int, [c_void_p, c_void_p, c_int, c_int_p, c_void_p, c_int, c_int_p]),
     "siftb_match_l1": (c_int, [c_void_p, c_int, c_void_p, c_int, c_float, c_int, c_int, c_void_p, c_int, c_int_p]),
     "siftb_transform": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_float_p, c_float_p, c_float,
                                 c_int, c_int]),
@@ -127,12 +146,29 @@ def pair_records(kp1, idx1, kp2, idx2):
 
 def device_pointer(obj):
     """Device pointer of a CUDA-resident array (torch tensor / __cuda_array_interface__), else None."""
+    if hasattr(obj, "is_cuda") and hasattr(obj, "data_ptr"):
+        return int(obj.data_ptr()) if obj.is_cuda else None
     cai = getattr(obj, "__cuda_array_interface__", None)
     if cai is not None:
         return int(cai["data"][0])
-    if hasattr(obj, "is_cuda") and obj.is_cuda and hasattr(obj, "data_ptr"):
-        return int(obj.data_ptr())
     return None
+
+
+def device_info(obj):
+    """(device ordinal or None if unknown, producer stream handle or None) of a CUDA-resident array.
+
+    torch tensors: the tensor's device and torch's current stream on it (work enqueued there may still be
+    writing the tensor).  ``__cuda_array_interface__`` v3: the optional ``stream`` entry (None = already
+    synchronised, 1 = legacy default stream, 2 = per-thread default stream, else a cudaStream_t)."""
+    if hasattr(obj, "is_cuda") and hasattr(obj, "data_ptr"):
+        import torch
+        return obj.device.index, int(torch.cuda.current_stream(obj.device).cuda_stream)
+    cai = getattr(obj, "__cuda_array_interface__", None)
+    if cai is not None:
+        stream = cai.get("stream", None)
+        dev = getattr(getattr(obj, "device", None), "id", None)  # cupy
+        return dev, (int(stream) if stream is not None else None)
+    return None, None
 
 
 def pinned_empty(shape, dtype):

@@ -1,5 +1,13 @@
 """LinearAlign: align images on a reference image with an affine transformation -- same public
-surface as the reference's sift-src/alignment.py (keypoints + match + host least squares + warp)."""
+surface as the reference's sift-src/alignment.py (keypoints + match + host least squares + warp).
+
+Data flow per frame (everything between the two copies stays on the device, like the reference's
+``buffers["input"]`` / ``ref_kp_gpu``, alignment.py:157,242-249):
+
+    frame --H2D--> SiftPlan (records stay in HBM) --D2D--> MatchPlan (reference list resident)
+          --> 32 bytes per matched pair --D2H--> host: shift / affine least squares / 4-sigma rejection
+          --> 6 numbers --> warp of the still-resident frame --D2H--> aligned image
+"""
 import ctypes
 import logging
 from threading import Semaphore
@@ -9,33 +17,83 @@ import numpy
 from . import _lib
 from .match import MatchPlan
 from .plan import SiftPlan
-from .utils import matching_correction
+from .utils import affine_lstsq
 
 logger = logging.getLogger("sift.alignment")
+
+MIN_MATCHES_AFFINE = 3 * 6  # three points per degree of freedom (alignment.py:266)
+OUTLIER_SIGMAS = 4.0         # alignment.py:294-296
 
 
 def transform(image, matrix, offset, fill, out_shape=None, mode=1, device=0):
     """Inverse-mapped affine warp, bilinear (mode 1) or nearest (mode 0): transform.cl:22-108; an (H, W, 3)
-    uint8 image goes through transform_RGB (transform.cl:116-203)."""
+    uint8 image goes through transform_RGB (transform.cl:116-203).  Host in, host out."""
     m = numpy.ascontiguousarray(numpy.asarray(matrix, numpy.float32).reshape(4))
     o = numpy.ascontiguousarray(numpy.asarray(offset, numpy.float32).reshape(2))
-    if numpy.ndim(image) == 3:
-        image = numpy.ascontiguousarray(image, numpy.uint8)
-        h, w = image.shape[:2]
-        oh, ow = (h, w) if out_shape is None else out_shape
-        out = numpy.empty((oh, ow, 3), numpy.uint8)
-        _lib.check(_lib.load().siftb_transform_rgb(_lib.ptr(image), h, w, _lib.ptr(out), oh, ow,
-                                                   m.ctypes.data_as(_lib.c_float_p), o.ctypes.data_as(_lib.c_float_p),
-                                                   ctypes.c_float(fill), int(mode), int(device)))
-        return out
-    image = numpy.ascontiguousarray(image, numpy.float32)
-    h, w = image.shape
+    colour = numpy.ndim(image) == 3
+    image = numpy.ascontiguousarray(image, numpy.uint8 if colour else numpy.float32)
+    h, w = image.shape[:2]
     oh, ow = (h, w) if out_shape is None else out_shape
-    out = numpy.empty((oh, ow), numpy.float32)
-    _lib.check(_lib.load().siftb_transform(_lib.ptr(image), h, w, _lib.ptr(out), oh, ow,
-                                           m.ctypes.data_as(_lib.c_float_p), o.ctypes.data_as(_lib.c_float_p),
-                                           ctypes.c_float(fill), int(mode), int(device)))
+    out = numpy.empty((oh, ow, 3) if colour else (oh, ow), image.dtype)
+    fn = _lib.load().siftb_transform_rgb if colour else _lib.load().siftb_transform
+    _lib.check(fn(_lib.ptr(image), h, w, _lib.ptr(out), oh, ow, m.ctypes.data_as(_lib.c_float_p),
+                  o.ctypes.data_as(_lib.c_float_p), ctypes.c_float(fill), int(mode), int(device)))
     return out
+
+
+# ---- geometry on the matched pairs: float32 [m, 8] = (x, y, scale, angle) of the reference keypoint, then of
+# ---- its match in the frame (MatchPlan.match_coords).  Small pure functions, unit-tested on the CPU.
+def pairs_from_matching(matching):
+    """The [m, 8] pair array of a reference-style (m, 2) recarray of matched keypoints."""
+    out = numpy.empty((matching.shape[0], 8), numpy.float32)
+    for col, field in enumerate(("x", "y", "scale", "angle")):
+        out[:, col] = matching[:, 0][field]
+        out[:, 4 + col] = matching[:, 1][field]
+    return out
+
+
+def median_shift(pairs):
+    """Pure translation (alignment.py:266-274): identity matrix, offset = median displacement as (dy, dx)."""
+    dx = pairs[:, 4] - pairs[:, 0]
+    dy = pairs[:, 5] - pairs[:, 1]
+    return numpy.identity(2, dtype=numpy.float32), numpy.array([numpy.median(dy), numpy.median(dx)], numpy.float32)
+
+
+def affine_from_pairs(pairs):
+    """Least-squares affine map reference -> frame (alignment.py:278-282 + utils.matching_correction) in the
+    warp's convention: frame (y, x) = matrix . reference (y, x) + offset."""
+    a, b, c, d, e, f = affine_lstsq(pairs[:, 0], pairs[:, 1], pairs[:, 4], pairs[:, 5])
+    return numpy.array([[e, d], [b, a]], numpy.float32), numpy.array([f, c], numpy.float32)
+
+
+def inlier_mask(pairs, nsigma=OUTLIER_SIGMAS):
+    """True for the pairs kept by the reference's validation (alignment.py:283-297): a pair is an outlier when its
+    displacement length, its rotation or its log scale ratio lies more than ``nsigma`` standard deviations from
+    the mean over all pairs."""
+    dx = pairs[:, 4] - pairs[:, 0]
+    dy = pairs[:, 5] - pairs[:, 1]
+    quantities = (numpy.sqrt(dx * dx + dy * dy), pairs[:, 7] - pairs[:, 3], numpy.log(pairs[:, 6] / pairs[:, 2]))
+    keep = numpy.ones(pairs.shape[0], bool)
+    with numpy.errstate(divide="ignore", invalid="ignore"):
+        for q in quantities:
+            keep &= ~(numpy.abs((q - q.mean()) / q.std()) > nsigma)  # NaN (zero spread) counts as inlier, like the reference
+    return keep
+
+
+def chain_transform(previous, matrix, offset):
+    """3x3 homogeneous form of (matrix, offset) composed onto ``previous`` (alignment.py:303-320, relative mode)."""
+    step = numpy.identity(3, dtype=numpy.float64)
+    step[:2, :2] = matrix
+    step[:2, 2] = offset
+    return step if previous is None else numpy.dot(step, previous)
+
+
+def residual_rms(pairs, matrix, offset):
+    """RMS distance between the mapped reference keypoints and their matches (alignment.py:353-356)."""
+    ref_yx = numpy.stack((pairs[:, 1], pairs[:, 0]))
+    img_yx = numpy.stack((pairs[:, 5], pairs[:, 4]))
+    corr = (numpy.dot(matrix, ref_yx).T + numpy.asarray(offset).T) - img_yx.T
+    return numpy.sqrt((corr * corr).sum(axis=-1).mean())
 
 
 class LinearAlign(object):
@@ -47,130 +105,103 @@ class LinearAlign(object):
         self.profile = bool(profile)
         self.events = []
         self.program = None
-        self.ref = numpy.ascontiguousarray(image, numpy.float32)
         self.buffers = {}
-        self.shape = image.shape
-        if len(self.shape) == 3:
-            self.RGB = True
-            self.shape = self.shape[:2]
-        elif len(self.shape) == 2:
-            self.RGB = False
-        else:
-            raise RuntimeError("Unable to process image of shape %s" % (tuple(self.shape),))
-        if "__len__" not in dir(extra):
-            self.extra = (int(extra), int(extra))
-        else:
-            self.extra = extra[:2]
-        self.outshape = tuple(i + 2 * j for i, j in zip(self.shape, self.extra))
+        shape = tuple(image.shape)
+        if len(shape) not in (2, 3):
+            raise RuntimeError("Unable to process image of shape %s" % (shape,))
+        self.RGB = len(shape) == 3
+        self.shape = shape[:2]
+        self.ref = numpy.ascontiguousarray(image, numpy.uint8 if self.RGB else numpy.float32)
+        pad = tuple(extra[:2]) if "__len__" in dir(extra) else (int(extra), int(extra))
+        self.extra = pad
+        self.outshape = tuple(int(n) + 2 * int(e) for n, e in zip(self.shape, pad))
         self.ROI = ROI
         self.ctx = context
         self.device = device
-        self.sift = SiftPlan(template=image, context=context, profile=self.profile, device=device,
+        self.sift = SiftPlan(template=self.ref, context=context, profile=self.profile, device=device,
                              max_workgroup_size=max_workgroup_size, init_sigma=init_sigma)
-        self.ref_kp = self.sift.keypoints(image)
-        if self.ROI is not None:
-            self.ref_kp = self._apply_roi(self.ref_kp)
         self.match = MatchPlan(context=context, profile=self.profile, device=device,
                                max_workgroup_size=max_workgroup_size)
+        self._set_reference(self.sift.keypoints(self.ref))
         self.fill_value = 0
         self.sem = Semaphore()
         self.relative_transfo = None
 
-    def _apply_roi(self, kp):  # alignment.py:149-154
-        kpx = numpy.round(kp.x).astype(numpy.int32)
-        kpy = numpy.round(kp.y).astype(numpy.int32)
-        masked = self.ROI[(kpy, kpx)].astype(bool)
-        logger.warning("Reducing keypoint list from %i to %i because of the ROI" % (kp.size, masked.sum()))
-        return kp[masked]
+    def _set_reference(self, kp):
+        """New reference keypoints: ROI filter on the host (alignment.py:149-154), then resident in the matcher
+        (alignment.py:157 ``ref_kp_gpu``)."""
+        if self.ROI is not None:
+            inside = numpy.asarray(self.ROI)[(numpy.round(kp.y).astype(numpy.int32),
+                                              numpy.round(kp.x).astype(numpy.int32))].astype(bool)
+            logger.warning("Reducing keypoint list from %i to %i because of the ROI" % (kp.size, inside.sum()))
+            kp = kp[inside]
+        self.ref_kp = kp
+        self.match.hold(0, self.ref_kp)
 
     def align(self, img, shift_only=False, return_all=False, double_check=False, relative=False, orsa=False):
         """Align image on reference image (reference alignment.py:227-360).
 
         :param img: numpy array containing the image to align to reference
+        :param shift_only: fit a translation only (median displacement of the matched keypoints)
         :param return_all: return in addition to the image, keypoints, matching keypoints and transformations as a dict
+        :param double_check: re-fit after dropping the matches more than 4 sigma away in displacement, rotation or scale
         :param relative: update reference keypoints with those from current image to perform relative alignment
         :return: aligned image, or all information, or None when no keypoint matches
         """
         logger.debug("ref_keypoints: %s" % self.ref_kp.size)
-        if self.RGB:
-            data = numpy.ascontiguousarray(img, numpy.uint8)  # alignment.py:237-238
-        else:
-            data = numpy.ascontiguousarray(img, numpy.float32)
+        frame = numpy.ascontiguousarray(img, numpy.uint8 if self.RGB else numpy.float32)  # alignment.py:237-240
         with self.sem:
-            kp = self.sift.keypoints(data)
-            logger.debug("mod image keypoints: %s" % kp.size)
-            raw_matching = self.match.match(self.ref_kp, kp, raw_results=True)
-            len_match = raw_matching.shape[0]
-            if len_match == 0:
+            self.sift.submit(frame)               # one upload: keypoints now, the warp below
+            n_kp = self.sift.collect(records=False)
+            logger.debug("mod image keypoints: %s" % n_kp)
+            pairs = self.match.match_coords(self.ref_kp, self.sift.device_keypoints(n_kp))
+            n_match = pairs.shape[0]
+            if n_match == 0:
                 logger.warning("No matching keypoints")
-                return
-            matching = _lib.pair_records(self.ref_kp, raw_matching[:, 0], kp, raw_matching[:, 1])
+                return None
             if orsa:
                 logger.warning("feature is not available. No ORSA filtering")  # alignment.py:260-264
-            if (len_match < 3 * 6) or (shift_only):  # 3 points per DOF
-                if shift_only:
-                    logger.debug("Shift Only mode: Common keypoints: %s" % len_match)
-                else:
-                    logger.warning("Shift Only mode: Common keypoints: %s" % len_match)
-                dx = matching[:, 1].x - matching[:, 0].x
-                dy = matching[:, 1].y - matching[:, 0].y
-                matrix = numpy.identity(2, dtype=numpy.float32)
-                offset = numpy.array([+numpy.median(dy), +numpy.median(dx)], numpy.float32)
+            enough = n_match >= MIN_MATCHES_AFFINE
+            if shift_only or not enough:
+                (logger.debug if shift_only else logger.warning)("Shift Only mode: Common keypoints: %s" % n_match)
+                matrix, offset = median_shift(pairs)
             else:
-                logger.debug("Common keypoints: %s" % len_match)
-                matrix, offset = self._fit(matching)
-            if double_check and (len_match >= 3 * 6):
+                logger.debug("Common keypoints: %s" % n_match)
+                matrix, offset = affine_from_pairs(pairs)
+            if double_check and enough:
                 logger.warning("Validating keypoints, %s,%s" % (matrix, offset))
-                dx = matching[:, 1].x - matching[:, 0].x
-                dy = matching[:, 1].y - matching[:, 0].y
-                dangle = matching[:, 1].angle - matching[:, 0].angle
-                dscale = numpy.log(matching[:, 1].scale / matching[:, 0].scale)
-                distance = numpy.sqrt(dx * dx + dy * dy)
-                outlayer = numpy.zeros(distance.shape, numpy.int8)
-                outlayer += abs((distance - distance.mean()) / distance.std()) > 4
-                outlayer += abs((dangle - dangle.mean()) / dangle.std()) > 4
-                outlayer += abs((dscale - dscale.mean()) / dscale.std()) > 4
-                outlayersum = outlayer.sum()
-                if outlayersum > 0 and not numpy.isinf(outlayersum):
-                    matching2 = matching[outlayer == 0]
-                    matrix, offset = self._fit(matching2)
-            if relative:  # update stable part to perform a relative alignment
-                self.ref_kp = kp
-                if self.ROI is not None:
-                    self.ref_kp = self._apply_roi(self.ref_kp)
-                transfo = numpy.zeros((3, 3), dtype=numpy.float64)
-                transfo[:2, :2] = matrix
-                transfo[0, 2] = offset[0]
-                transfo[1, 2] = offset[1]
-                transfo[2, 2] = 1
-                if self.relative_transfo is None:
-                    self.relative_transfo = transfo
-                else:
-                    self.relative_transfo = numpy.dot(transfo, self.relative_transfo)
+                keep = inlier_mask(pairs)
+                if not keep.all():
+                    matrix, offset = affine_from_pairs(pairs[keep])
+            kp = matching = None
+            if return_all or relative:
+                kp = self.sift.fetch_keypoints()
+            if return_all:
+                matching = self.match.last_pairs()
+            if relative:  # the current frame becomes the reference of the next one; transforms accumulate
+                self._set_reference(kp)
+                self.relative_transfo = chain_transform(self.relative_transfo, matrix, offset)
                 matrix = numpy.ascontiguousarray(self.relative_transfo[:2, :2], dtype=numpy.float32)
                 offset = numpy.ascontiguousarray(self.relative_transfo[:2, 2], dtype=numpy.float32)
             fill = self.sift.buffers["min"].get()[0]  # alignment.py:345
-            result = transform(data, matrix, offset, float(fill), self.outshape, 1, self.sift.device)
+            result = self.sift.warp_last(matrix, offset, float(fill), self.outshape, 1)
+            if self.profile:
+                self.events += [(name, ms) for name, ms in self.sift.fetch_events()
+                                if name.startswith("transform") or name.startswith("copy D->H transformed")]
         if return_all:
-            corr = numpy.dot(matrix, numpy.vstack((matching[:, 0].y, matching[:, 0].x))).T + offset.T - \
-                numpy.vstack((matching[:, 1].y, matching[:, 1].x)).T
-            rms = numpy.sqrt((corr * corr).sum(axis=-1).mean())
             return {"result": result, "keypoint": kp, "matching": matching, "offset": offset, "matrix": matrix,
-                    "rms": rms}
+                    "rms": residual_rms(pairs, matrix, offset)}
         return result
 
     __call__ = align
 
-    @staticmethod
-    def _fit(matching):  # alignment.py:278-282
-        transform_matrix = matching_correction(matching)
-        offset = numpy.array([transform_matrix[5], transform_matrix[2]], dtype=numpy.float32)
-        matrix = numpy.empty((2, 2), dtype=numpy.float32)
-        matrix[0, 0], matrix[0, 1] = transform_matrix[4], transform_matrix[3]
-        matrix[1, 0], matrix[1, 1] = transform_matrix[1], transform_matrix[0]
-        return matrix, offset
-
     def log_profile(self):
-        """Print the timing of the underlying plans (reference alignment.py:363-376)."""
+        """Print the timing of every device operation of the underlying plans and of the warp
+        (reference alignment.py:363-376)."""
         self.sift.log_profile()
         self.match.log_profile()
+        t = 0.0
+        for name, et in self.events:
+            print("%50s:\t%.3fms" % (name, et))
+            t += et
+        print("%50s:\t%.3fms" % ("Total transform", t))

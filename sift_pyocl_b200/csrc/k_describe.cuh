@@ -311,7 +311,8 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
 // prefix of the per-octave record counts -> first record slot of every octave, and the total
 __global__ void k_octave_offsets(const int *__restrict__ oct_valid, int n_oct, int *__restrict__ oct_offset,
                                  int *__restrict__ n_out, int *__restrict__ n_out_oct /* stride 4 */,
-                                 const int *__restrict__ size_hist, int *__restrict__ size_start) {
+                                 const int *__restrict__ size_hist, int *__restrict__ size_start,
+                                 int *__restrict__ n_order) {
     int acc = 0;
     for (int o = 0; o < n_oct; o++) {
         oct_offset[o] = acc;
@@ -324,6 +325,7 @@ __global__ void k_octave_offsets(const int *__restrict__ oct_valid, int n_oct, i
         size_start[b] = acc;
         acc += size_hist[b];
     }
+    *n_order = acc;  // keypoints k_orient accepted and stored (== entries k_size_order writes)
 }
 
 // order[] = keypoint indices sorted by descending descriptor-window size class (counting sort, unstable)
@@ -334,8 +336,11 @@ __global__ void __launch_bounds__(256) k_size_order(const float4 *__restrict__ k
     const int n = min(min(*n_base_p, cap) + *n_extra_p, cap);
     const int stride = gridDim.x * blockDim.x;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int b = desc_size_class(kp[i].z, 1 << (kp_tag[i] >> 8));
-        order[size_start[b] + atomicAdd(&size_fill[b], 1)] = i;
+        const float4 k = kp[i];
+        if (!(k.y >= 0.0f)) continue;  // rows k_orient skipped (never counted in size_hist)
+        const int b = desc_size_class(k.z, 1 << (kp_tag[i] >> 8));
+        const int pos = size_start[b] + atomicAdd(&size_fill[b], 1);
+        if (pos < cap) order[pos] = i;
     }
 }
 
@@ -344,8 +349,7 @@ __global__ void __launch_bounds__(256) k_size_order(const float4 *__restrict__ k
 // octave in octave order like the reference's concatenation (plan.py:555-565).
 __global__ void __launch_bounds__(DESC_WARPS * 32, 7) k_describe(OctTable T, const float4 *__restrict__ kp,
                                                                const int *__restrict__ kp_tag,
-                                                               const int *__restrict__ n_base_p,
-                                                               const int *__restrict__ n_extra_p, int cap,
+                                                               const int *__restrict__ n_order_p, int cap,
                                                                KpRecord *__restrict__ out, int out_cap,
                                                                const int *__restrict__ oct_offset,
                                                                int *__restrict__ oct_fill, int *__restrict__ queue,
@@ -355,7 +359,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 7) k_describe(OctTable T, con
     __shared__ DescStage s_stage[DESC_WARPS * 4];
     const int lane = threadIdx.x & 31, l8 = lane & 7, obase = lane & 24;
     float *hist = s_hist[threadIdx.x >> 5];
-    const int n = min(min(*n_base_p, cap) + *n_extra_p, cap);
+    const int n = min(*n_order_p, cap);
     // dynamic work queue: every warp fetches 4 keypoints at a time, so warps with small windows simply fetch
     // more often and the last wave is not quantised to the grid size
     for (;;) {

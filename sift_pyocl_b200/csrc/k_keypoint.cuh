@@ -320,10 +320,13 @@ __global__ void __launch_bounds__(256) k_orient(OctTable T, float4 *__restrict__
         const bool p1 = lane < 4 && peak_angle(32 + lane, a2_1);
         const unsigned b0 = __ballot_sync(0xffffffffu, p0), b1 = __ballot_sync(0xffffffffu, p1);
         const int n_extra_here = __popc(b0) + __popc(b1);
+        int n_stored = 0;  // extra rows that fit into the list: only those are counted below (the reference's
+                           // counter runs past the buffer, plan.py:771 only warns; here overflow truncates cleanly)
         if (n_extra_here) {
             int slot0 = 0;
             if (lane == 0) slot0 = n_base + atomicAdd(n_extra, n_extra_here);
             slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+            n_stored = max(0, min(n_extra_here, cap - slot0));
             if (p0) {
                 const int old = slot0 + __popc(b0 & lanemask_lt());
                 if (old < cap) { kp[old] = make_float4(o.x, o.y, o.z, a2_0); kp_tag[old] = tag; }
@@ -334,7 +337,7 @@ __global__ void __launch_bounds__(256) k_orient(OctTable T, float4 *__restrict__
             }
         }
         if (lane == 0) {
-            const int added = 1 + n_extra_here;
+            const int added = 1 + n_stored;
             if (stage) atomicAdd(&stage[oct * 9 + (sc - 1) * 3 + 2], added);
             // rows whose angle is NaN (flat histogram) are dropped on output (plan.py:546-550)
             if (oct_valid) atomicAdd(&oct_valid[oct], added - ((angle != angle) ? 1 : 0));

@@ -18,7 +18,7 @@
 #include <string>
 #include <vector>
 
-#include "../../include/siftb.h"
+#include "host_common.h"
 #include "common.cuh"
 #include "k_blur.cuh"
 #include "k_blur_tma.cuh"
@@ -26,34 +26,18 @@
 #include "k_frontend.cuh"
 #include "k_keypoint.cuh"
 #include "k_describe.cuh"
-#include "k_match.cuh"
+#include "k_warp.cuh"
 
 #define SIFTB_VERSION 100
 #define MAX_OCT 32
 #define AUX_INTS (8 + 3 * SIFTB_KOCT + 3 * DESC_CLASSES)
 #define NSLOT 3  // images in flight per plan
 
-static thread_local std::string g_err;
-static int fail(int code, const std::string &msg) {
-    g_err = msg;
-    return code;
-}
-#define CK(call)                                                                                        \
-    do {                                                                                                \
-        cudaError_t e_ = (call);                                                                        \
-        if (e_ != cudaSuccess)                                                                          \
-            return fail(e_ == cudaErrorMemoryAllocation ? SIFTB_ENOMEM : SIFTB_ECUDA,                  \
-                        std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" +       \
-                            std::to_string(__LINE__) + ")");                                            \
-    } while (0)
-#define CKL() CK(cudaGetLastError())
-
 // SIFT constants, param.py:52-79
 static const int kScales = 3, kBorderDist = 5;
 static const float kPeakThresh = (float)(255.0 * 0.04 / 3.0), kEdgeThresh = 0.06f, kEdgeThresh1 = 0.08f,
                    kOriSigma = 1.5f;
 
-static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 // image.cl:152 `fabs(val) > 0.8 * peak_thresh` is a double comparison; for an fp32 val it equals
 // fabsf(val) >= (smallest fp32 strictly above the double product)
 static float contrast_gate(float peak_thresh) {
@@ -141,12 +125,16 @@ struct siftb_plan {
     KpRecord *outs[NSLOT] = {};
     // device counters: [0]=n_out, [1..]: per octave {n_cand, n_kp, n_extra, n_out_oct}; then stage[n_oct][3][3]; then mm[2]
     // per slot AUX_INTS ints: [0] describe work-queue head, [1] refined keypoints (all octaves), [2] extra
-    // orientations, [8..8+KOCT) records per octave, [8+KOCT..) first record slot per octave, [8+2KOCT..) fill
+    // orientations, [3] keypoints in the descriptor processing order, [8..8+KOCT) records per octave, [8+KOCT..) first record slot per octave, [8+2KOCT..) fill
     int *d_queue = nullptr;
     int *d_cnts[NSLOT] = {};
     int *h_cnts[NSLOT] = {};  // pinned mirrors
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_h2d[NSLOT] = {}, ev_done[NSLOT] = {}, ev_d2h[NSLOT] = {};
+    cudaEvent_t ev_ext = nullptr;  // siftb_plan_wait_stream
+    const void *src_ptr[NSLOT] = {};  // device pointer of the image submitted to each slot, and its pixel type
+    int src_dtype[NSLOT] = {};
+    GrowBuf d_warp;                   // output of siftb_plan_warp_last
     int head = 0, n_flight = 0;  // slots [head, head + n_flight) are submitted and not yet collected
     int last = 0;                // slot of the most recently collected image
     int cnt_ints = 0;
@@ -189,7 +177,7 @@ static size_t dtype_bytes(int dtype) {
     return 0;
 }
 
-extern "C" const char *siftb_last_error(void) { return g_err.c_str(); }
+extern "C" const char *siftb_last_error(void) { return g_siftb_err.c_str(); }
 extern "C" int siftb_version(void) { return SIFTB_VERSION; }
 extern "C" int siftb_device_count(int *n) {
     if (!n) return fail(SIFTB_EINVAL, "n is null");
@@ -208,11 +196,12 @@ extern "C" int siftb_host_free(void *ptr) {
 
 extern "C" int siftb_plan_destroy(siftb_plan *p) {
     if (!p) return 0;
-    cudaSetDevice(p->device);
+    DeviceGuard dg_(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
     for (int s = 0; s < NSLOT; s++) { cudaFree(p->d_raws[s]); cudaFree(p->outs[s]); cudaFree(p->d_cnts[s]); }
     cudaFree(p->d_img);
+    p->d_warp.release();
     for (auto q : p->G) cudaFree(q);
     for (auto q : p->D) cudaFree(q);
     for (int o = 0; o < SIFTB_KOCT; o++)
@@ -224,6 +213,7 @@ extern "C" int siftb_plan_destroy(siftb_plan *p) {
         if (p->ev_done[s]) cudaEventDestroy(p->ev_done[s]);
         if (p->ev_d2h[s]) cudaEventDestroy(p->ev_d2h[s]);
     }
+    if (p->ev_ext) cudaEventDestroy(p->ev_ext);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
     for (auto &ev : p->events_s) for (auto &e : ev) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -232,7 +222,7 @@ extern "C" int siftb_plan_destroy(siftb_plan *p) {
 }
 
 static int plan_create_impl(siftb_plan *p) {
-    CK(cudaSetDevice(p->device));
+    DeviceGuard dg_(p->device);
     CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
     for (int s = 0; s < NSLOT; s++) {
@@ -240,6 +230,7 @@ static int plan_create_impl(siftb_plan *p) {
         CK(cudaEventCreateWithFlags(&p->ev_done[s], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&p->ev_d2h[s], cudaEventDisableTiming));
     }
+    CK(cudaEventCreateWithFlags(&p->ev_ext, cudaEventDisableTiming));
     // plan.py:213-224 _calc_scales
     {
         int h = p->h, w = p->w, n = 0;
@@ -346,9 +337,9 @@ extern "C" int siftb_plan_create(int height, int width, int dtype, int device, i
     p->force_generic = env_force_generic();
     int rc = plan_create_impl(p);
     if (rc) {
-        std::string keep = g_err;
+        std::string keep = g_siftb_err;
         siftb_plan_destroy(p);
-        g_err = keep;
+        g_siftb_err = keep;
         return rc;
     }
     if (octave_max > 0 && octave_max < p->n_oct) p->n_oct = octave_max;  // par.OctaveMax
@@ -469,7 +460,7 @@ struct ProfScope {
 static int submit_impl(siftb_plan *p, const void *image, int flags) {
     const int on_device = flags & SIFTB_ON_DEVICE;
     const int dtype = (flags & SIFTB_IS_F32) ? SIFTB_F32 : p->dtype;
-    CK(cudaSetDevice(p->device));
+    DeviceGuard dg_(p->device);
     cudaStream_t st = p->stream;
     const long N = (long)p->h * p->w;
     const void *src = image;
@@ -485,12 +476,14 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
         CK(cudaStreamWaitEvent(st, p->ev_h2d[slot], 0));
         src = p->d_raws[slot];
     }
+    p->src_ptr[slot] = src;
+    p->src_dtype[slot] = dtype;
     // the records of this slot's previous image must have left the device before they are overwritten
     CK(cudaStreamWaitEvent(st, p->ev_d2h[slot], 0));
     CK(cudaMemsetAsync(p->d_cnts[slot], 0, p->cnt_ints * sizeof(int), st));
     int *aux = p->d_queue + slot * AUX_INTS;
     CK(cudaMemsetAsync(aux, 0, AUX_INTS * sizeof(int), st));
-    int *q_head = aux, *n_kp = aux + 1, *n_extra = aux + 2;
+    int *q_head = aux, *n_kp = aux + 1, *n_extra = aux + 2, *n_order = aux + 3;
     int *oct_valid = aux + 8, *oct_offset = aux + 8 + SIFTB_KOCT, *oct_fill = aux + 8 + 2 * SIFTB_KOCT;
     int *size_hist = aux + 8 + 3 * SIFTB_KOCT, *size_start = size_hist + DESC_CLASSES, *size_fill = size_start + DESC_CLASSES;
     unsigned *mm = p->c_mm(slot);
@@ -576,9 +569,9 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
     {
         ProfScope ps(p, "descriptors");
         k_octave_offsets<<<1, 1, 0, st>>>(oct_valid, p->n_oct, oct_offset, p->c_nout(slot), p->c_oct(slot, 0) + 3,
-                                          size_hist, size_start);
+                                          size_hist, size_start, n_order);
         k_size_order<<<148, 256, 0, st>>>(p->kp, p->kp_tag, n_kp, n_extra, p->kp_cap, size_start, size_fill, p->kp_order);
-        k_describe<<<148 * 7, DESC_WARPS * 32, 0, st>>>(p->table, p->kp, p->kp_tag, n_kp, n_extra, p->kp_cap,
+        k_describe<<<148 * 7, DESC_WARPS * 32, 0, st>>>(p->table, p->kp, p->kp_tag, n_order, p->kp_cap,
                                                         p->outs[slot], p->out_cap, oct_offset, oct_fill, q_head,
                                                         p->kp_order);
         CKL();
@@ -593,7 +586,7 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
 
 static int collect_impl(siftb_plan *p, siftb_kp *out, int cap, int *n_out, int *n_per_octave, float *minmax) {
     if (p->n_flight == 0) return fail(SIFTB_EINVAL, "collect without submit");
-    CK(cudaSetDevice(p->device));
+    DeviceGuard dg_(p->device);
     const int slot = p->head;
     CK(cudaEventSynchronize(p->ev_done[slot]));
     p->head = (p->head + 1) % NSLOT;
@@ -654,16 +647,77 @@ extern "C" int siftb_plan_keypoints(siftb_plan *p, const void *image, int flags,
     if (rc) return rc;
     return collect_impl(p, out, cap, n_out, n_per_octave, minmax);
 }
+// host copy of the records of the most recently collected run (after collect(out = NULL))
+extern "C" int siftb_plan_fetch_records(siftb_plan *p, siftb_kp *out, int cap, int *n_out) {
+    if (!p || !out) return fail(SIFTB_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(p->mtx);
+    DeviceGuard dg_(p->device);
+    const int slot = p->last;
+    int n = p->h_cnts[slot][0];
+    if (n > p->out_cap) n = p->out_cap;
+    if (n > cap) n = cap;
+    if (n_out) *n_out = n;
+    if (n > 0) {
+        CK(cudaMemcpyAsync(out, p->outs[slot], (size_t)n * sizeof(siftb_kp), cudaMemcpyDeviceToHost, p->copy_stream));
+        CK(cudaEventRecord(p->ev_d2h[slot], p->copy_stream));
+        CK(cudaStreamSynchronize(p->copy_stream));
+    }
+    return 0;
+}
+extern "C" int siftb_plan_wait_stream(siftb_plan *p, void *stream) {
+    if (!p) return fail(SIFTB_EINVAL, "null plan");
+    std::lock_guard<std::mutex> lk(p->mtx);
+    DeviceGuard dg_(p->device);
+    CK(cudaEventRecord(p->ev_ext, (cudaStream_t)stream));
+    CK(cudaStreamWaitEvent(p->stream, p->ev_ext, 0));
+    return 0;
+}
+extern "C" int siftb_plan_device(const siftb_plan *p) { return p ? p->device : SIFTB_EINVAL; }
 extern "C" int siftb_plan_result_dev(const siftb_plan *p, const siftb_kp **recs, const int **count) {
     if (!p) return fail(SIFTB_EINVAL, "null plan");
     if (recs) *recs = reinterpret_cast<const siftb_kp *>(p->outs[p->last]);
     if (count) *count = p->d_cnts[p->last];
     return 0;
 }
+// alignment.py:324-349: warp of the image of the most recently collected run.  That image is still on the device
+// (the plan's input staging buffer, or the caller's device array), so LinearAlign uploads a frame once for both
+// keypoints() and the warp, like the reference does with buffers["input"] (alignment.py:242-246).
+extern "C" int siftb_plan_warp_last(siftb_plan *p, const float matrix[4], const float offset[2], float fill, int mode,
+                                    void *out, int out_height, int out_width, int out_on_device) {
+    if (!p || !matrix || !offset || !out || out_height <= 0 || out_width <= 0) return fail(SIFTB_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(p->mtx);
+    DeviceGuard dg_(p->device);
+    const int slot = p->last;
+    const void *src = p->src_ptr[slot];
+    const int dtype = p->src_dtype[slot];
+    if (!src) return fail(SIFTB_EINVAL, "no image has been processed by this plan yet");
+    if (dtype != SIFTB_F32 && dtype != SIFTB_RGB8)
+        return fail(SIFTB_EINVAL, "the warp needs a float32 or RGB8 image (alignment.py:237-240)");
+    const size_t bytes = (size_t)out_height * out_width * (dtype == SIFTB_RGB8 ? 3 : 4);
+    void *dst = out;
+    if (!out_on_device) {
+        CK(p->d_warp.reserve(bytes));
+        dst = p->d_warp.p;
+    }
+    const WarpMap m = make_warp_map(matrix, offset, p->h, p->w, out_height, out_width, fill, mode);
+    p->cur = slot;
+    {
+        ProfScope ps(p, "transform");
+        if (dtype == SIFTB_RGB8) CK(launch_warp_rgb8(p->stream, (const uint8_t *)src, (uint8_t *)dst, m));
+        else CK(launch_warp_f32(p->stream, (const float *)src, (float *)dst, m));
+        p->launches += 1;
+    }
+    if (!out_on_device) {
+        ProfScope ps(p, "copy D->H transformed image");
+        CK(cudaMemcpyAsync(out, dst, bytes, cudaMemcpyDeviceToHost, p->stream));
+    }
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
 extern "C" int siftb_plan_events(siftb_plan *p, const char *const **names, const float **ms, int *n) {
     if (!p) return fail(SIFTB_EINVAL, "null plan");
     std::lock_guard<std::mutex> lk(p->mtx);
-    CK(cudaSetDevice(p->device));
+    DeviceGuard dg_(p->device);
     // the events of the most recently collected image: all recorded before its ev_done, which collect() waited for
     // (no stream synchronisation here: the next images may already be running)
     auto &events = p->events_s[p->last];
@@ -689,37 +743,6 @@ extern "C" int siftb_plan_stage_counts(siftb_plan *p, int *counts) {
 
 // ---------------------------------------------------------------------------------------------
 // stage-level hooks: host in, host out, temporaries on the current device, default stream
-struct DevBuf {
-    void *p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
-    template <typename T> T *as() { return (T *)p; }
-};
-#define DALLOC(buf, bytes) CK((buf).alloc(bytes))
-
-// Scratch buffers of the stateless matcher entry point: taken from the device's stream-ordered memory pool, which
-// is told to keep freed memory (the reference's MatchPlan keeps its device buffers between calls, match.py:220-239),
-// so that repeated match() calls do not pay cudaMalloc / cudaFree.
-struct PoolBuf {
-    void *p = nullptr;
-    ~PoolBuf() { if (p) cudaFreeAsync(p, 0); }
-    cudaError_t alloc(size_t bytes) {
-        static bool configured[64] = {};
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (!configured[dev & 63]) {
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-                uint64_t keep = ~0ull;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-            }
-            configured[dev & 63] = true;
-        }
-        return cudaMallocAsync(&p, bytes ? bytes : 1, 0);
-    }
-    template <typename T> T *as() { return (T *)p; }
-};
-
 extern "C" int siftb_gauss_taps(double sigma, float *taps, int cap, int *n) {
     if (!taps || !n || !(sigma > 0)) return fail(SIFTB_EINVAL, "bad argument");
     int size = kernel_size(sigma);
@@ -947,63 +970,3 @@ extern "C" int siftb_descriptor(const float *kp4, int n, const float *grad, cons
     return 0;
 }
 
-extern "C" int siftb_match_l1(const siftb_kp *kp1, int n1, const siftb_kp *kp2, int n2, float ratio_th, int on_device,
-                              int device, int *pairs, int cap, int *n) {
-    if (!n || n1 < 0 || n2 < 0 || cap < 0 || (n1 && !kp1) || (n2 && !kp2)) return fail(SIFTB_EINVAL, "bad argument");
-    *n = 0;
-    if (n1 == 0) return 0;
-    CK(cudaSetDevice(device));
-    PoolBuf R1, R2, D1, D2, P, C;
-    const uint8_t *r1 = (const uint8_t *)kp1, *r2 = (const uint8_t *)kp2;
-    if (!on_device) {
-        DALLOC(R1, (size_t)n1 * 144); DALLOC(R2, (size_t)n2 * 144);
-        CK(cudaMemcpy(R1.p, kp1, (size_t)n1 * 144, cudaMemcpyHostToDevice));
-        if (n2) CK(cudaMemcpy(R2.p, kp2, (size_t)n2 * 144, cudaMemcpyHostToDevice));
-        r1 = R1.as<uint8_t>(); r2 = R2.as<uint8_t>();
-    }
-    DALLOC(D1, (size_t)n1 * 128); DALLOC(D2, (size_t)n2 * 128); DALLOC(P, (size_t)cap * 8); DALLOC(C, 4);
-    CK(cudaMemset(C.p, 0, 4));
-    k_extract_desc<<<(int)(((long)n1 * 32 + 255) / 256), 256>>>(r1, n1, D1.as<uint32_t>());
-    if (n2) k_extract_desc<<<(int)(((long)n2 * 32 + 255) / 256), 256>>>(r2, n2, D2.as<uint32_t>());
-    CKL();
-    k_match_l1<<<(n1 + MATCH_THREADS - 1) / MATCH_THREADS, MATCH_THREADS>>>(D1.as<uint32_t>(), n1, D2.as<uint32_t>(), n2, ratio_th, P.as<int2>(), cap,
-                                          C.as<int>());
-    CKL();
-    CK(cudaMemcpy(n, C.p, 4, cudaMemcpyDeviceToHost));
-    int m = *n < cap ? *n : cap;
-    if (m > 0 && pairs) CK(cudaMemcpy(pairs, P.p, (size_t)m * 8, cudaMemcpyDeviceToHost));
-    return 0;
-}
-
-extern "C" int siftb_transform(const float *image, int height, int width, float *out, int out_height, int out_width,
-                               const float matrix[4], const float offset[2], float fill, int mode, int device) {
-    if (!image || !out || !matrix || !offset || height <= 0 || width <= 0 || out_height <= 0 || out_width <= 0)
-        return fail(SIFTB_EINVAL, "bad argument");
-    CK(cudaSetDevice(device));
-    DevBuf I, O;
-    DALLOC(I, (size_t)height * width * 4); DALLOC(O, (size_t)out_height * out_width * 4);
-    CK(cudaMemcpy(I.p, image, (size_t)height * width * 4, cudaMemcpyHostToDevice));
-    dim3 grid((out_width + 255) / 256, out_height);
-    k_transform<<<grid, 256>>>(I.as<float>(), O.as<float>(), matrix[0], matrix[1], matrix[2], matrix[3], offset[0],
-                               offset[1], width, height, out_width, out_height, fill, mode);
-    CKL();
-    CK(cudaMemcpy(out, O.p, (size_t)out_height * out_width * 4, cudaMemcpyDeviceToHost));
-    return 0;
-}
-
-extern "C" int siftb_transform_rgb(const uint8_t *image, int height, int width, uint8_t *out, int out_height,
-                                   int out_width, const float matrix[4], const float offset[2], float fill, int mode,
-                                   int device) {
-    if (!image || !out || !matrix || !offset || height <= 0 || width <= 0 || out_height <= 0 || out_width <= 0)
-        return fail(SIFTB_EINVAL, "bad argument");
-    CK(cudaSetDevice(device));
-    DevBuf I, O;
-    DALLOC(I, (size_t)height * width * 3); DALLOC(O, (size_t)out_height * out_width * 3);
-    CK(cudaMemcpy(I.p, image, (size_t)height * width * 3, cudaMemcpyHostToDevice));
-    dim3 grid((3 * out_width + 255) / 256, out_height);
-    k_transform_rgb<<<grid, 256>>>(I.as<uint8_t>(), O.as<uint8_t>(), matrix[0], matrix[1], matrix[2], matrix[3],
-                                   offset[0], offset[1], width, height, out_width, out_height, fill, mode);
-    CKL();
-    CK(cudaMemcpy(out, O.p, (size_t)out_height * out_width * 3, cudaMemcpyDeviceToHost));
-    return 0;
-}

@@ -1,15 +1,23 @@
 """Multi-GPU sharding of an image batch (no equivalent in the single-device reference).
 
 One process per GPU (torchrun).  Image i of a batch goes to rank ``i % world``; each rank runs its own
-SiftPlan; the ragged keypoint arrays are all-gathered over NCCL (``torch.distributed``): first the
-int32 counts, then the records padded to the largest count.  The data path itself has no collective.
-With the ``gloo`` backend (CPU tests) the same code moves the records through host tensors.
+SiftPlan; the ragged keypoint arrays are all-gathered over NCCL (``torch.distributed``).  The data path
+itself has no collective.  With the ``gloo`` backend (CPU tests) the same code moves the records through
+host tensors.
+
+Two forms of the exchange:
+  * ``allgather_records`` -- blocking, exact sizes: counts first, then the records padded to the largest count;
+  * ``RecordExchange`` -- the pipelined form used per step by ``bench.py`` and ``keypoints_batch``: a fixed-capacity
+    slab per rank whose first row carries the count, gathered by ONE collective on a side stream, so the host
+    never waits for the exchange of the counts and nothing is allocated per step.
 """
 import numpy
 import torch
 import torch.distributed as dist
 
 from . import _lib
+
+REC = 144  # bytes per dtype_kp record
 
 
 def shard_indices(n_images, rank, world):
@@ -26,54 +34,134 @@ class _CudaView(object):
 
 
 def device_records_tensor(plan, n):
-    """uint8 torch tensor [n, 144] aliasing the plan's device-resident records of the last run."""
+    """uint8 torch tensor [n, 144] aliasing the plan's device-resident records of the last run.
+
+    The memory belongs to the plan and is recycled by a later submit(): consume it on a torch stream and then
+    call ``plan.wait_stream(that_stream)`` (RecordExchange does), or clone it and synchronise."""
     ptr, _ = plan.device_records()
     if n == 0:
-        return torch.empty((0, 144), dtype=torch.uint8, device="cuda:%d" % plan.device)
-    t = torch.as_tensor(_CudaView(ptr, n * 144), device="cuda:%d" % plan.device)
-    return t.view(n, 144)
-
-
-class _PendingGather(object):
-    """All-gather of ragged records split in two so that the host never waits for the exchange of the counts:
-    begin (constructor) copies the local records and starts the all-gather of the counts asynchronously;
-    ``finish()`` -- typically called one pipeline step later -- reads the counts and runs the all-gather of the
-    records padded to the largest count."""
-
-    def __init__(self, local, group=None):
-        self.group = group
-        self.world = dist.get_world_size(group)
-        self.local = local.clone()  # the plan's record buffer is recycled by a later submit()
-        dev = local.device
-        self.cnt = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
-        self.counts = torch.zeros(self.world, dtype=torch.int64, device=dev)
-        self.work = dist.all_gather_into_tensor(self.counts, self.cnt, group=group, async_op=True)
-
-    def finish(self):
-        self.work.wait()
-        counts_h = self.counts.cpu()
-        nmax = max(int(counts_h.max()), 1)
-        dev = self.local.device
-        padded = torch.zeros((nmax, 144), dtype=torch.uint8, device=dev)
-        padded[:self.local.shape[0]] = self.local
-        gathered = torch.empty((self.world * nmax, 144), dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(gathered, padded, group=self.group)
-        gathered = gathered.view(self.world, nmax, 144)
-        return [gathered[r, :int(counts_h[r])] for r in range(self.world)], counts_h
-
-
-def allgather_records_begin(local, group=None):
-    """Start the all-gather of ragged record tensors; returns a handle whose ``finish()`` completes it."""
-    return _PendingGather(local, group)
+        return torch.empty((0, REC), dtype=torch.uint8, device="cuda:%d" % plan.device)
+    t = torch.as_tensor(_CudaView(ptr, n * REC), device="cuda:%d" % plan.device)
+    return t.view(n, REC)
 
 
 def allgather_records(local, group=None):
-    """All-gather ragged record tensors.
+    """All-gather ragged record tensors (blocking).
 
     :param local: uint8 tensor [n_local, 144] (CUDA for nccl, CPU for gloo)
     :return: (list of per-rank uint8 tensors [n_r, 144], int64 tensor of counts)
     """
-    return _PendingGather(local, group).finish()
+    world = dist.get_world_size(group)
+    dev = local.device
+    cnt = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, cnt, group=group)
+    counts_h = counts.cpu()
+    nmax = max(int(counts_h.max()), 1)
+    padded = torch.zeros((nmax, REC), dtype=torch.uint8, device=dev)
+    padded[:local.shape[0]] = local
+    gathered = torch.empty((world * nmax, REC), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(gathered, padded, group=group)
+    gathered = gathered.view(world, nmax, REC)
+    return [gathered[r, :int(counts_h[r])] for r in range(world)], counts_h
+
+
+class _Pending(object):
+    """One exchange in flight; owns references to the slabs it was started with (the exchange may enlarge its
+    buffers while an older step is still pending)."""
+
+    def __init__(self, ex, send, recv, capacity, work, event, n_local, spill):
+        self.ex, self.send, self.recv, self.capacity = ex, send, recv, capacity
+        self.work, self.event, self.n_local, self.spill = work, event, n_local, spill
+
+    def finish(self):
+        """(list of per-rank uint8 tensors [n_r, 144], int64 counts).  The tensors alias the exchange's receive
+        buffer: valid until the second begin() from now (two buffers alternate)."""
+        ex = self.ex
+        if self.work is not None:
+            self.work.wait()
+        if self.event is not None:
+            self.event.synchronize()
+        recv = self.recv
+        counts = recv[:, 0, :8].contiguous().view(torch.int64).reshape(-1).cpu()
+        if int(counts.max()) > self.capacity:
+            # a rank produced more records than a slab holds (every rank sees the same counts, so all take this
+            # branch together): exact-size blocking exchange of the full local arrays, and larger slabs from now on
+            local = self.spill if self.spill is not None else self.send[1:1 + self.n_local]
+            out = allgather_records(local, ex.group)
+            if ex.capacity < int(counts.max()):
+                ex._allocate(int(int(counts.max()) * 1.25) + 1024)
+            return out
+        return [recv[r, 1:1 + int(counts[r])] for r in range(ex.world)], counts
+
+
+class RecordExchange(object):
+    """Per-step all-gather of ragged keypoint records without a host round trip for the counts.
+
+    Every rank contributes a slab of ``capacity + 1`` rows of 144 bytes: row 0 carries the count (int64), rows
+    1.. the records.  ``begin()`` copies the local records into the send slab and starts ONE all-gather on a side
+    stream; ``finish()`` -- typically one pipeline step later -- reads the counts out of the gathered slabs.  All
+    buffers are allocated once (``capacity`` must be the same on every rank); a step whose count exceeds the
+    capacity falls back to the exact-size exchange and enlarges the slabs.
+    """
+
+    def __init__(self, capacity, device, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.device = torch.device(device)
+        self.cuda = self.device.type == "cuda"
+        self.stream = torch.cuda.Stream(self.device) if self.cuda else None
+        self.turn = 0
+        self._allocate(int(capacity))
+
+    def _allocate(self, capacity):
+        self.capacity = capacity
+        rows = capacity + 1
+        self.send = [torch.zeros((rows, REC), dtype=torch.uint8, device=self.device) for _ in range(2)]
+        self.recv = [torch.empty((self.world, rows, REC), dtype=torch.uint8, device=self.device) for _ in range(2)]
+        self.header = [torch.zeros(1, dtype=torch.int64, pin_memory=self.cuda) for _ in range(2)]
+
+    def begin(self, local, plan=None):
+        """Start the exchange of ``local`` (uint8 [n, 144]; may alias a plan's record buffer: pass ``plan`` so that
+        the plan does not recycle that buffer before the copy out of it has run)."""
+        b = self.turn
+        self.turn ^= 1
+        n = int(local.shape[0])
+        send, recv = self.send[b], self.recv[b]
+        self.header[b][0] = n  # page-locked: the copy below is asynchronous; rewritten two steps later at the earliest
+        header = self.header[b].view(torch.uint8)
+        spill = None
+        if not self.cuda:
+            send[0, :8] = header
+            send[1:1 + min(n, self.capacity)] = local[:self.capacity]
+            if n > self.capacity:
+                spill = local.clone()
+            work = dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=self.group, async_op=True)
+            return _Pending(self, send, recv, self.capacity, work, None, n, spill)
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            send[0, :8].copy_(header, non_blocking=True)
+            send[1:1 + min(n, self.capacity)].copy_(local[:self.capacity], non_blocking=True)
+            if n > self.capacity:
+                spill = local.clone()
+            if plan is not None:  # the plan's next writer of this record buffer waits for the copies above
+                plan.wait_stream(self.stream.cuda_stream)
+            dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=self.group)
+            event = torch.cuda.Event()
+            event.record(self.stream)
+        return _Pending(self, send, recv, self.capacity, None, event, n, spill)
+
+
+def allgather_records_begin(local, group=None, exchange=None, plan=None):
+    """Start the all-gather of ragged record tensors; returns a handle whose ``finish()`` completes it.
+    Without an ``exchange`` a one-shot RecordExchange sized for ``local`` is used (allocates)."""
+    if exchange is None:
+        world = dist.get_world_size(group)
+        cap = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+        dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=group)
+        exchange = RecordExchange(max(int(cap.item()), 1), local.device, group)
+        del world
+    return exchange.begin(local, plan)
 
 
 def records_to_numpy(t):
@@ -108,7 +196,7 @@ def keypoints_batch(plan, images, group=None, gather=True):
     use_cuda = dist.get_backend(group) == "nccl"
     dev = torch.device("cuda:%d" % plan.device) if use_cuda else torch.device("cpu")
     flat = numpy.concatenate(local) if local else numpy.zeros(0, _lib.dtype_kp)
-    t = torch.from_numpy(flat.view(numpy.uint8).reshape(-1, 144).copy()).to(dev)
+    t = torch.from_numpy(flat.view(numpy.uint8).reshape(-1, REC).copy()).to(dev)
     per_rank, _ = allgather_records(t, group)
     # per-image sizes of every rank
     rounds = (n_images + world - 1) // world

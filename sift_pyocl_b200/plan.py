@@ -117,6 +117,7 @@ class SiftPlan(object):
             lib.siftb_plan_set_profile(handle, 1)
         self.last_counts = numpy.zeros(self.octave_max, numpy.int32)
         self._out = None  # host record buffer, allocated on first use
+        self._last_n = 0
         self._pending = 0
         self._keep = []
         logger.info("SiftPlan %s %s on CUDA device %d: %d octaves, kpsize %d, %.1f MB", self.shape, self.dtype,
@@ -143,17 +144,26 @@ class SiftPlan(object):
         assert tuple(image.shape[:2]) == self.shape
         dt = _np_dtype(image.dtype)
         assert dt in [self.dtype, numpy.dtype(numpy.float32)]
-        is_f32 = dt == numpy.float32 and not (self.RGB and len(image.shape) == 3)
+        if len(image.shape) == 3:  # interleaved colour: only uint8 RGB on an RGB plan (preprocess.cl:211 rgb_to_float)
+            assert self.RGB and image.shape[2] == 3 and dt == numpy.uint8, "colour images must be (H, W, 3) uint8"
+        is_f32 = dt == numpy.float32
         if self.RGB and not is_f32:
-            assert len(image.shape) == 3 and image.shape[2] == 3
+            assert len(image.shape) == 3
         flags = 0
         if is_f32 and self._code != 0:
             flags |= 2  # SIFTB_IS_F32
+        self._last_colour = not is_f32 and self.RGB  # pixel format of the image the plan keeps on the device
         dptr = _lib.device_pointer(image)
         if dptr is not None:
             if hasattr(image, "is_contiguous") and not image.is_contiguous():
                 image = image.contiguous()
                 dptr = _lib.device_pointer(image)
+            dev, stream = _lib.device_info(image)
+            assert dev is None or dev == self.device, "image lives on CUDA device %s, the plan on %d" % (dev, self.device)
+            if stream is not None:
+                # the plan runs on its own non-blocking stream: order it after the stream that produces the image
+                # (the reference shares one in-order queue with its pyopencl.array inputs, plan.py:451-456)
+                _lib.check(_lib.load().siftb_plan_wait_stream(self._plan, ctypes.c_void_p(stream)))
             return ctypes.c_void_p(dptr), flags | 1, image
         if not image.flags["C_CONTIGUOUS"]:
             image = numpy.ascontiguousarray(image)
@@ -203,6 +213,7 @@ class SiftPlan(object):
         for octave, cnt in enumerate(self.last_counts):
             logger.info("in octave %i found %i kp" % (octave, cnt))  # plan.py:543
         n = min(n, self._capacity)
+        self._last_n = n
         if self.profile:
             self._fetch_events()
         # fresh host array for the caller; copied as raw bytes (numpy copies a structured array field by field,
@@ -243,7 +254,8 @@ class SiftPlan(object):
                     if rc != _lib.SIFTB_EOVERFLOW:
                         _lib.check(rc)
                     self.buffers["min"].value[0], self.buffers["max"].value[0] = mm[0], mm[1]
-                    return min(n.value, self._capacity)
+                    self._last_n = min(n.value, self._capacity)
+                    return self._last_n
                 return self._finish(rc, n.value, mm)
             finally:
                 self._pending -= 1
@@ -252,17 +264,17 @@ class SiftPlan(object):
     def keypoints_many(self, images):
         """Generator: keypoints of every image of ``images`` in order, with the copies of one image
         overlapping the kernels of the others (three images in flight)."""
-        it = iter(images)
-        n_sub = 0
-        for image in it:
-            self.submit(image)
-            n_sub += 1
-            if n_sub == 3:
+        try:
+            for image in images:
+                self.submit(image)
+                if self._pending == 3:
+                    yield self.collect()
+            while self._pending:
                 yield self.collect()
-                n_sub -= 1
-        while n_sub:
-            yield self.collect()
-            n_sub -= 1
+        finally:
+            # consumer stopped early / a submit raised: drain what is still in flight so that the plan stays usable
+            while self._pending:
+                self.collect(records=False)
 
     @staticmethod
     def pinned_empty(shape, dtype=numpy.float32):
@@ -275,6 +287,50 @@ class SiftPlan(object):
         recs, cnt = ctypes.c_void_p(), ctypes.c_void_p()
         _lib.check(_lib.load().siftb_plan_result_dev(self._plan, ctypes.byref(recs), ctypes.byref(cnt)))
         return recs.value, cnt.value
+
+    def wait_stream(self, stream):
+        """Order the plan's queue after the work enqueued so far on ``stream`` (a cudaStream_t handle, e.g.
+        ``torch.cuda.current_stream().cuda_stream``): needed when another stream produces a device-resident
+        input image, or still reads the plan's device-resident records (device_records())."""
+        _lib.check(_lib.load().siftb_plan_wait_stream(self._plan, ctypes.c_void_p(int(stream))))
+
+    def device_keypoints(self, n=None):
+        """The keypoints of the last run as a device-resident array (``match.DeviceRecords``) -- what the reference
+        gets by keeping results in a ``pyopencl.array`` (alignment.py:246-249); valid until the third submit()
+        from now.  MatchPlan.match() accepts it directly, so the records never visit the host."""
+        from .match import DeviceRecords
+        recs, _ = self.device_records()
+        return DeviceRecords(recs or 0, self._last_n if n is None else n, self.device, owner=self)
+
+    def fetch_keypoints(self):
+        """Host recarray of the keypoints of the last run (for callers that used ``collect(records=False)``)."""
+        with self._sem:
+            out = self._records()
+            n = ctypes.c_int()
+            _lib.check(_lib.load().siftb_plan_fetch_records(self._plan, _lib.ptr(out), self._capacity, ctypes.byref(n)))
+            res = numpy.empty(n.value, dtype=self.dtype_kp)
+            numpy.copyto(res.view(numpy.uint8), out[:n.value].view(numpy.uint8))
+        return res.view(numpy.recarray)
+
+    def warp_last(self, matrix, offset, fill, out_shape=None, mode=1, out=None):
+        """Affine warp (transform.cl:22 / :116) of the image of the last run, which is still on the device: the
+        reference uploads a frame once for both SIFT and the warp (alignment.py:242-246, 336-349).
+
+        :param matrix, offset: output pixel (y, x) samples the image at ``matrix . (y, x) + offset``
+        :param out: optional preallocated result (e.g. page-locked, see pinned_empty)
+        """
+        m = numpy.ascontiguousarray(numpy.asarray(matrix, numpy.float32).reshape(4))
+        o = numpy.ascontiguousarray(numpy.asarray(offset, numpy.float32).reshape(2))
+        oh, ow = self.shape if out_shape is None else (int(out_shape[0]), int(out_shape[1]))
+        shape, dt = ((oh, ow, 3), numpy.uint8) if getattr(self, "_last_colour", False) else ((oh, ow), numpy.float32)
+        if out is None:
+            out = numpy.empty(shape, dt)
+        assert out.shape == shape and out.dtype == dt and out.flags["C_CONTIGUOUS"]
+        with self._sem:
+            _lib.check(_lib.load().siftb_plan_warp_last(self._plan, m.ctypes.data_as(_lib.c_float_p),
+                                                        o.ctypes.data_as(_lib.c_float_p), ctypes.c_float(fill),
+                                                        int(mode), _lib.ptr(out), oh, ow, 0))
+        return out
 
     @property
     def launches(self):

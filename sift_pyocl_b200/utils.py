@@ -31,27 +31,27 @@ def sizeof(shape, dtype="uint8"):
     return cnt * itemsize
 
 
-def matching_correction(matching):
-    """Least-squares affine transform mapping keypoints[:, 0] onto keypoints[:, 1].
+def affine_lstsq(x, y, xp, yp):
+    """Least-squares (a, b, c, d, e, f) of ``x' = a x + b y + c ; y' = d x + e y + f``.
 
-    Reference utils.py:156-189 builds the design matrix for ``x' = a x + b y + c ; y' = d x + e y + f``
-    but the snapshot lost the solve and the return; they are completed with ``pinv(X) . y`` as in the
-    reference's own test (test/test_transform.py:118-133).  Returns the flat vector (a, b, c, d, e, f).
+    The 2N x 6 system the reference builds (utils.py:156-189) is block structured: the even rows only involve
+    (a, b, c), the odd rows only (d, e, f), both with the same N x 3 design matrix [x, y, 1].  Solving the two
+    3-parameter problems gives the same solution as ``pinv(X) . y`` (test/test_transform.py:118-133) without the
+    SVD of a 2N x 6 matrix.  Fewer than 3 independent points: minimum-norm solution, like pinv.
     """
-    # The 2N x 6 system of the reference is block structured: the even rows only involve (a, b, c), the odd rows
-    # only (d, e, f), both with the same N x 3 design matrix [x, y, 1].  Solving the two 3-parameter problems gives
-    # the same least-squares solution as pinv(X) . y (the system has full rank) without the SVD of a 2N x 6 matrix
-    # (4x faster for the 2e5 matches of an 8192 x 8192 pair).  Fewer than 3 independent points: minimum-norm
-    # solution, like pinv.
-    A = numpy.empty((matching.shape[0], 3), numpy.float64)
-    A[:, 0] = matching.x[:, 0]
-    A[:, 1] = matching.y[:, 0]
-    A[:, 2] = 1.0
-    rhs = numpy.empty((matching.shape[0], 2), numpy.float64)
-    rhs[:, 0] = matching.x[:, 1]
-    rhs[:, 1] = matching.y[:, 1]
+    A = numpy.empty((len(x), 3), numpy.float64)
+    A[:, 0], A[:, 1], A[:, 2] = x, y, 1.0
+    rhs = numpy.empty((len(x), 2), numpy.float64)
+    rhs[:, 0], rhs[:, 1] = xp, yp
     sol = numpy.linalg.lstsq(A, rhs, rcond=None)[0]  # columns: (a, b, c) and (d, e, f)
     return sol.T.ravel()
+
+
+def matching_correction(matching):
+    """Least-squares affine transform mapping keypoints[:, 0] onto keypoints[:, 1] of an (m, 2) recarray of
+    matched keypoints.  Reference utils.py:156-189 builds the design matrix but the snapshot lost the solve and
+    the return; completed as in the reference's own test (test/test_transform.py:131).  Returns (a, b, c, d, e, f)."""
+    return affine_lstsq(matching.x[:, 0], matching.y[:, 0], matching.x[:, 1], matching.y[:, 1])
 
 
 def multiscale_image(n, seed=1234, shape=None):

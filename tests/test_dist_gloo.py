@@ -99,6 +99,48 @@ def _pipelined_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _exchange_worker(rank, world, port, q):
+    """RecordExchange: fixed-capacity slabs, one collective per step, overflow falls back to the exact exchange."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sift_pyocl_b200 import dist as sdist
+    ex = sdist.RecordExchange(8, "cpu")
+    sizes = [3, 0, 8, 20, 5, 31, 2]          # steps 3 and 5 exceed the capacity in force
+    steps = [torch.full((sz + rank, 144), 7 * i + rank, dtype=torch.uint8) for i, sz in enumerate(sizes)]
+    pending, results, ok = None, [], True
+
+    def done(p):  # the returned tensors alias the receive slabs (valid until the second begin() from now): copy
+        per_rank, counts = p.finish()
+        results.append(([t.clone() for t in per_rank], counts))
+    for t in steps:
+        started = ex.begin(t)
+        t.fill_(255)
+        if pending is not None:
+            done(pending)
+        pending = started
+    done(pending)
+    for i, (per_rank, counts) in enumerate(results):
+        for r in range(world):
+            ok = ok and int(counts[r]) == sizes[i] + r and tuple(per_rank[r].shape) == (sizes[i] + r, 144)
+            ok = ok and bool((per_rank[r] == 7 * i + r).all())
+    ok = ok and ex.capacity > 8              # enlarged after the overflow
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_record_exchange_world2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert res == [(0, True), (1, True)]
+
+
 def test_pipelined_allgather_world2():
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")

@@ -83,7 +83,12 @@ __device__ __forceinline__ float cr_atan2f_fast(float yf, float xf, const AtanCo
     const float hif = fmaxf(axf, ayf), lof = fminf(axf, ayf);
     // tables live in global memory and are read through L1 (__ldg): the index differs per lane, which the
     // constant cache would serialise.  Branch-free: lof == 0 (including 0/0) is selected to a = 0 at the end.
-    const float t = __fdividef(lof, hif);
+    // rough quotient, only used to pick the breakpoint: div.approx.ftz is MUFU.RCP + FMUL (the non-ftz form that
+    // __fdividef compiles to without -ftz carries ~7 more instructions of subnormal scaling); subnormal operands,
+    // where flushing would change the quotient, take the IEEE division
+    float t;
+    if (hif >= 1e-30f) asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(t) : "f"(lof), "f"(hif));
+    else t = lof / hif;
     const int k = max(min((int)(t * (21.5615f + -5.5615f * t) + 0.5f), 16), 0);
     const double hi = (double)hif, lo = (double)lof;
     const double c = __ldg(&c_atan_c[k]);

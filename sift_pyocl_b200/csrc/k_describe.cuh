@@ -27,19 +27,22 @@
 
 #define DESC_MAXROWS 100  // window rows per keypoint handled by the interval table (iradius <= 49; default sigmas need 97)
 
-struct DescRows {          // per-octet table of the non-empty window rows: only the j-interval that can be valid
-    signed char i[DESC_MAXROWS];   // window row i (-iradius..iradius; |.| <= 49 for tabled windows)
-    signed char jlo[DESC_MAXROWS]; // first candidate j of the row
-    signed char jhi[DESC_MAXROWS]; // last candidate j of the row
+// Per-octet table of the non-empty window rows: only the j-interval that can be valid.  One packed word per row:
+// byte 0 = window row i (-iradius..iradius; |.| <= 49 for tabled windows), byte 1 = first candidate j, byte 2 = last
+// candidate j (signed bytes).
+struct DescRows {
+    int w[DESC_MAXROWS];
 };
+__device__ __forceinline__ int desc_pack_row(int i, int jlo, int jhi) {
+    return (i & 0xff) | ((jlo & 0xff) << 8) | ((jhi & 0xff) << 16);
+}
 
 // Staging area of one octet for one pass (8 samples): the evaluating lane s writes, for each of the 8 parity
 // classes p = (row&1)<<2 | (col&1)<<1 | (ori&1), the ONE contribution of sample s to a bin of that class as
-// (byte offset of the bin inside the octet's histogram, value).  A sample feeds at most 8 bins (2 rows x 2
-// columns x 2 orientations of the trilinear interpolation) and those always differ in all three parities, so
-// every class receives exactly one (possibly null) term per sample.  Null terms (neighbour cell outside the 4x4
-// grid, sample rejected by the reference's tests) are stored as value +0.0 on the class's home bin: every
-// histogram term is >= +0, so adding +0.0 is an exact no-op.
+// (shared-memory byte address of the bin, value).  A sample feeds 8 bins (2 rows x 2 columns x 2 orientations of
+// the trilinear interpolation) and those always differ in all three parities, so every class receives exactly one
+// term per sample.  Rejected samples stage value +-0.0 (every histogram term is >= +0, so adding a zero of either
+// sign is an exact no-op).
 // Rows are 10 float2 apart (80 B) and octets 704 B apart: the 8 lanes of an octet then store their 16-byte
 // chunks to 8 different bank quads, and the per-class 8-byte loads of two neighbouring octets do not collide.
 struct __align__(16) DescStage {
@@ -47,21 +50,55 @@ struct __align__(16) DescStage {
     float2 pad[8];
 };
 
+// Histogram storage of one warp: the 4 x 4 x 8 bins of the reference plus a GUARD RING -- cells r, c in -1..4,
+// stored as r0 = r + 1, c0 = c + 1 in 0..5 -- so that the trilinear neighbours of a sample never need a range test
+// (the reference's `if (rindex >= 0 && rindex < 4)` etc., keypoints_cpu.cl:91-101, become writes to cells nobody
+// reads).  Octet g owns the bank group 8g..8g+7; bin (r0, c0, o) lives in row (o>>1) + 4*(c0>>1) + 12*(r0>>1),
+// bank 8g + 4*(r0&1) + 2*(c0&1) + (o&1): the 8 lanes of an octet (one per parity class) and the 4 octets of the
+// warp always hit 32 different banks -- every histogram access of the commit loop is a single conflict-free
+// wavefront.
+#define DESC_HROWS 36
+__device__ __forceinline__ int desc_bin(int r0, int c0, int o) {  // float index inside the octet's bank group
+    return 32 * ((o >> 1) + 4 * (c0 >> 1) + 12 * (r0 >> 1)) + 4 * (r0 & 1) + 2 * (c0 & 1) + (o & 1);
+}
+
+// exp(x) for x in [-16, 0] without the range check of cr_expf_neg (callers clamp): the same arithmetic, hence the
+// same result (exhaustively verified, tools/exp_check.c).  The double constants are read from the constant bank as
+// direct DFMA operands (as literals ptxas re-materialises each with two moves per use) and the 32-entry table from
+// shared memory (32-bit address, no 64-bit pointer arithmetic per sample).
+__constant__ double c_exp_k[8] = {0x1.71547652b82fep+5, 0x1.8p52, -0x1.62e42feep-6, -0x1.a39ef358p-38,
+                                  1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0};
+__device__ __forceinline__ float cr_expf_neg_inrange(float xf, const double *__restrict__ s_tab) {
+    const double x = (double)xf;
+    const double z = fma(x, c_exp_k[0], c_exp_k[1]);  // k = rint(x * 32/ln2) in the low word
+    const int k = __double2loint(z);
+    const double kd = z - c_exp_k[1];
+    double r = fma(kd, c_exp_k[2], x);
+    r = fma(kd, c_exp_k[3], r);
+    double q = fma(r, c_exp_k[4], c_exp_k[5]);
+    q = fma(r, q, c_exp_k[6]);
+    q = fma(r, q, c_exp_k[7]);
+    q = fma(r, q, 0.5);
+    const double p = fma(r * r, q, r);
+    const double t = s_tab[k & 31];
+    const double s = __hiloint2double(__double2hiint(t) + ((k >> 5) << 20), __double2loint(t));
+    return (float)fma(s, p, s);
+}
+
 // One warp, 4 keypoints (octet g handles kp[g] when act is true for that octet).
-// whist: the warp's 16 x 32 floats of histogram storage.  Octet g owns the bank group 8g..8g+7; bin (r, c, o)
-// lives in row (o>>1) + 4*(c>>1) + 8*(r>>1), bank 8g + 4*(r&1) + 2*(c&1) + (o&1): the 8 lanes of an octet (one
-// per parity class) and the 4 octets of the warp always hit 32 different banks -- every histogram access of the
-// commit loop is a single conflict-free wavefront.
+// whist: the warp's DESC_HROWS x 32 floats of histogram storage.
+// ANY_ANGLE: the keypoint angle may lie anywhere (stage hook fed by a caller); in the pipeline k_orient guarantees
+// [-pi, pi] up to one rounding.  s_exp: the CTA's shared copy of c_exp_t32.
+template <bool ANY_ANGLE>
 __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescRows &rows, DescStage &stage,
-                                                bool act, const float4 k,
-                                                const float *__restrict__ grad, const float *__restrict__ orim,
-                                                int pitch, int grad_width, int grad_height, int octsize,
+                                                const double *__restrict__ s_exp, bool act, const float4 k,
+                                                const float2 *__restrict__ go, int pitch, int grad_width, int grad_height, int octsize,
                                                 uint8_t *out128) {
     const int lane = threadIdx.x & 31, l8 = lane & 7, obase = lane & 24;
     const unsigned omask = 0xffu << obase;  // lanes of my octet
     float *hist = whist + obase;            // bank group of my octet
 #pragma unroll
-    for (int r = 0; r < 16; r++) hist[32 * r + l8] = 0.0f;
+    for (int r = 0; r < DESC_HROWS; r++) hist[32 * r + l8] = 0.0f;
     // keypoints_cpu.cl:55-61
     const float row = k.y / (float)octsize, col = k.x / (float)octsize, angle = k.w;
     const int irow = (int)(row + 0.5f), icol = (int)(col + 0.5f);
@@ -75,9 +112,9 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
     const bool tabled = nrows <= DESC_MAXROWS;
     // ---- row table: the reference scans j = -R..R of every row and keeps the samples with rx, cx in (-1, 4)
     // whose pixel is inside the image (keypoints_cpu.cl:66-67); those form one j-interval per row.  A
-    // conservative superset of it is computed here (real-valued bounds widened by a full sample on each side) so
-    // that only candidate samples are evaluated; every evaluated sample still goes through the reference's exact
-    // fp32 test.  Rows with an empty interval are dropped.
+    // conservative superset of it is computed here (real-valued bounds widened by a rigorous bound on the fp32
+    // evaluation error) so that only candidate samples are evaluated; every evaluated sample still goes through
+    // the reference's exact fp32 test.  Rows with an empty interval are dropped.
     int my_passes = 0, nrc = 0;  // passes (8 samples each) of this octet, number of table rows
     // untabled (enormous window, custom init_sigma): every row of the square that lies inside the image, full width
     const int u_r0 = max(0, iradius - irow), u_r1 = min(nrows - 1, iradius + grad_height - 1 - irow);
@@ -110,19 +147,16 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
             jlo = max(jlo, max(-iradius, -icol));
             jhi = min(jhi, min(iradius, grad_width - 1 - icol));
             if (jhi < jlo) { jlo = 1; jhi = 0; }  // empty (the real-valued bounds may not fit the table's type)
-            rows.jlo[r] = (signed char)jlo;
-            rows.jhi[r] = (signed char)jhi;
+            rows.w[r] = desc_pack_row(i, jlo, jhi);
         }
         __syncwarp();
         if (l8 == 0) {  // drop the empty rows (in place: the write index never overtakes the read index)
             int n = 0, acc = 0;
             for (int r = 0; r < nrows; r++) {
-                const int jlo = rows.jlo[r], jhi = rows.jhi[r];
+                const int w = rows.w[r];
+                const int jlo = (int)(signed char)(w >> 8), jhi = (int)(signed char)(w >> 16);
                 if (jhi >= jlo) {
-                    rows.i[n] = (signed char)(r - iradius);
-                    rows.jlo[n] = (signed char)jlo;
-                    rows.jhi[n] = (signed char)jhi;
-                    n++;
+                    rows.w[n++] = w;
                     acc += jhi - jlo + 1;
                 }
             }
@@ -139,12 +173,12 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
     // warp-uniform trip count: the longest of the 4 octets
     const int passes_max = __reduce_max_sync(0xffffffffu, my_passes);
     // Per-lane cursor over the candidate samples in row-major order: lane l8 takes candidates l8, l8 + 8, ... of
-    // the octet (table row rcur, column jcur, last column of that row jend, pixel offset of (row, j = 0)).  The
-    // gradient / orientation values of the lane's sample of pass p+1 are requested before pass p is evaluated
-    // and committed, so the L2 / DRAM gather latency overlaps the commit loop.
-    int rcur = -1, jcur = l8, jend = -1, n_i = 0, n_j = 0;
-    long rowoff = 0;
-    bool n_in = false;
+    // the octet (table row rcur, column jcur, last column of that row jend).  Per row the cursor keeps the pixel
+    // offset of (row, j = 0) and the two row-constant products of the rotation, cosine*i and sine*i
+    // (keypoints_cpu.cl:63-65 evaluates them per sample; same operands, same fp32 products).  The gradient /
+    // orientation values of the lane's sample of pass p+1 are requested before pass p is evaluated and committed,
+    // so the L2 / DRAM gather latency overlaps the commit loop.
+    int rcur = -1, jcur = l8, jend = -1, n_i = 0, n_j = 0, rowoff = 0;
     float n_g = 0.0f, n_o = 0.0f;
     auto fetch = [&]() {
         while (jcur > jend && rcur < nrc) {  // into the next table row(s)
@@ -152,118 +186,124 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
             rcur++;
             if (rcur < nrc) {
                 if (tabled) {
-                    n_i = rows.i[rcur];
-                    jcur = rows.jlo[rcur] + over;
-                    jend = rows.jhi[rcur];
+                    const int w = rows.w[rcur];
+                    n_i = (int)(signed char)w;
+                    jcur = (int)(signed char)(w >> 8) + over;
+                    jend = (int)(signed char)(w >> 16);
                 } else {
                     n_i = u_r0 + rcur - iradius;
                     jcur = u_jlo + over;
                     jend = u_jhi;
                 }
-                rowoff = (long)(irow + n_i) * pitch + icol;
             }
         }
         n_j = jcur;
-        n_in = rcur < nrc;
-        if (n_in) {
-            n_g = grad[rowoff + n_j];
-            n_o = orim[rowoff + n_j];
+        n_g = 0.0f;  // past the end of the window: a sample of zero gradient, i.e. eight +-0 terms
+        n_o = 0.0f;
+        if (rcur < nrc) {
+            rowoff = (irow + n_i) * pitch + icol;
+            const float2 v = __ldg(go + (rowoff + n_j));
+            n_g = v.x;
+            n_o = v.y;
         }
         jcur += 8;
     };
+    // shared-memory byte address of bin (0, 0, 0) of my octet: the stage carries absolute addresses
+    const unsigned hist_sa = (unsigned)__cvta_generic_to_shared(hist);
     fetch();
     for (int p = 0; p < passes_max; p++) {
-        const int i = n_i, j = n_j;
-        const bool in_image = n_in;
+        const float fi = (float)n_i, fj = (float)n_j;
         const float g_val = n_g, o_val = n_o;
         fetch();
-        // terms of this lane's sample, indexed by the parity of the row / column / orientation bin they go to;
-        // the defaults describe a null sample
-        float rw_e = 0.0f, rw_o = 0.0f, cf_e = 0.0f, cf_o = 0.0f, ow_e = 0.0f, ow_o = 0.0f;
-        int ra_e = 0, ra_o = 16, ca_e = 0, ca_o = 8, oa_e = 0, oa_o = 4;  // byte offsets in the bank group, home cell
-        if (in_image) {
-            const float rx = div_by((cosine * (float)i - sine * (float)j) - drow, inv_spacing) + 1.5f;
-            const float cx = div_by((sine * (float)i + cosine * (float)j) - dcol, inv_spacing) + 1.5f;
-            if (rx > -1.0f && rx < 4.0f && cx > -1.0f && cx < 4.0f) {
-                const float er = rx - 1.5f, ec = cx - 1.5f;
-                const float mag = g_val * cr_expf_neg(-0.125f * (er * er + ec * ec));
-                float ori = o_val - angle;
-                while (ori > 2.0f * SIFTB_M_PI_F) ori -= 2.0f * SIFTB_M_PI_F;
-                while (ori < 0.0f) ori += 2.0f * SIFTB_M_PI_F;
-                const float oval = (4.0f * ori) * SIFTB_M_1_PI_F;
-                // keypoints_cpu.cl:77-79 `(int)((v >= 0.0f) ? v : v - 1.0f)`: for v in (-1, 4) that is floor(v)
-                // (v - 1 lies in (-2, -1) for negative v, so the truncation gives -1); oval >= 0 always
-                const int ri = __float2int_rd(rx);
-                const int ci = __float2int_rd(cx);
-                const int oi = (int)((oval >= 0.0f) ? oval : oval - 1.0f);
-                const float rfrac = rx - (float)ri, cfrac = cx - (float)ci, ofrac = oval - (float)oi;
-                if ((ri >= -1 && ri < 4 && oi >= 0 && oi <= 8 && rfrac >= 0.0f && rfrac <= 1.0f)) {
-                    // rows ri (weight mag*(1-rfrac)) and ri+1 (mag*rfrac): the even one and the odd one
-                    const float rw0 = mag * (1.0f - rfrac), rw1 = mag * rfrac;
-                    const int rodd = ri & 1, r_e = ri + rodd, r_o = ri + 1 - rodd;
-                    if ((unsigned)r_e < 4u) { rw_e = rodd ? rw1 : rw0; ra_e = 512 * r_e; }
-                    if ((unsigned)r_o < 4u) { rw_o = rodd ? rw0 : rw1; ra_o = 512 * r_o - 496; }
-                    const float cf0 = 1.0f - cfrac;
-                    const int codd = ci & 1, c_e = ci + codd, c_o = ci + 1 - codd;
-                    if ((unsigned)c_e < 4u) { cf_e = codd ? cfrac : cf0; ca_e = 256 * c_e; }
-                    if ((unsigned)c_o < 4u) { cf_o = codd ? cf0 : cfrac; ca_o = 256 * c_o - 248; }
-                    const float of0 = 1.0f - ofrac;
-                    if (oi < 8) {
-                        const int o1 = (oi + 1) & 7;  // oindex = oi + orr; if (oindex >= 8) oindex = 0
-                        const bool oodd = oi & 1;
-                        ow_e = oodd ? ofrac : of0;
-                        ow_o = oodd ? of0 : ofrac;
-                        oa_e = 64 * (oodd ? o1 : oi);
-                        oa_o = 64 * (oodd ? oi : o1) - 60;
-                    } else {
-                        // oi == 8 <=> ori == 2*pi exactly (then oval == 8.0f and ofrac == 0): both terms go to
-                        // bin 0, cweight*(1-ofrac) then cweight*ofrac = +0 -- the second add is a no-op
-                        ow_e = of0;
-                        oa_e = 0;
-                    }
-                }
-            }
+        // ---- evaluate (straight-line code: a rejected sample is carried along with magnitude zero) -------------
+        // keypoints_cpu.cl:63-67
+        const float rx = div_by((cosine * fi - sine * fj) - drow, inv_spacing) + 1.5f;
+        const float cx = div_by((sine * fi + cosine * fj) - dcol, inv_spacing) + 1.5f;
+        const bool ok = rx > -1.0f && rx < 4.0f && cx > -1.0f && cx < 4.0f;
+        // :69-70 mag = grad * exp(-0.125 * ((rx-1.5)^2 + (cx-1.5)^2)); the argument of an accepted sample lies in
+        // [-1.5625, 0]; the clamp only keeps rejected samples inside the fast exp's range
+        const float er = rx - 1.5f, ec = cx - 1.5f;
+        const float earg = fmaxf(-0.125f * (er * er + ec * ec), -16.0f);
+        const float mag = (ok ? g_val : 0.0f) * cr_expf_neg_inrange(earg, s_exp);
+        // :71-75 orientation relative to the keypoint, wrapped into [0, 2 pi] (`>` : exactly 2 pi stays).  The
+        // planes hold atan2 values in [-pi, pi] and the keypoint angle lies in [-pi, pi] up to one rounding, so
+        // the reference's while loops run at most once / twice
+        float ori = o_val - angle;
+        if (ori > 2.0f * SIFTB_M_PI_F) ori -= 2.0f * SIFTB_M_PI_F;
+        if (ori < 0.0f) ori += 2.0f * SIFTB_M_PI_F;
+        if (ori < 0.0f) ori += 2.0f * SIFTB_M_PI_F;
+        if (ANY_ANGLE && (ori > 2.0f * SIFTB_M_PI_F || ori < 0.0f)) {  // caller-supplied angle far outside [-pi, pi]
+            while (ori > 2.0f * SIFTB_M_PI_F) ori -= 2.0f * SIFTB_M_PI_F;
+            while (ori < 0.0f) ori += 2.0f * SIFTB_M_PI_F;
         }
+        const float oval = (4.0f * ori) * SIFTB_M_1_PI_F;
+        // :77-85 integer cells and fractions.  `(int)((v >= 0) ? v : v - 1)` is floor(v) for v in (-1, 4) (v - 1
+        // lies in (-2, -1) for negative v, so the truncation gives -1); oval >= 0.  The reference's guards
+        // (ri in [-1, 4), oi in [0, 8], rfrac in [0, 1]) always hold for an accepted sample; a rejected one is
+        // evaluated at rx = cx = 0 so that its (zero) terms land inside the histogram.
+        const float rxs = ok ? rx : 0.0f, cxs = ok ? cx : 0.0f;
+        const int ri = __float2int_rd(rxs), ci = __float2int_rd(cxs), oi = (int)oval;
+        const float rfrac = rxs - (float)ri, cfrac = cxs - (float)ci, ofrac = oval - (float)oi;
+        // :87-104 the 2 x 2 x 2 trilinear terms, sorted by the parity of the cell they go to.  Rows r0 = ri + 1
+        // and r0 + 1 (guard-ring coordinates): the even one is (r0 + 1) & ~1, the odd one r0 | 1; if r0 is odd
+        // the even row is the upper neighbour and gets weight rfrac.  Same for the columns.  Orientation bins oi
+        // and oi + 1 wrap modulo 8 (`if (oindex >= 8) oindex = 0`); oi == 8 means ori == 2 pi exactly, i.e.
+        // ofrac == 0: its second term is cweight * 0 and may go to any bin.
+        const float rw0 = mag * (1.0f - rfrac), rw1 = mag * rfrac;
+        const bool rodd = !(ri & 1), codd = !(ci & 1), oodd = oi & 1;  // r0 = ri + 1 is odd when ri is even
+        const float rw_e = rodd ? rw1 : rw0, rw_o = rodd ? rw0 : rw1;
+        const float cf0 = 1.0f - cfrac;
+        const float cf_e = codd ? cfrac : cf0, cf_o = codd ? cf0 : cfrac;
+        const float of0 = 1.0f - ofrac;
+        const float ow_e = oodd ? ofrac : of0, ow_o = oodd ? of0 : ofrac;
+        // byte offsets of the cells: row index * 128 + bank * 4 (desc_bin), split per dimension
+        const unsigned ra_e = hist_sa + 768u * (unsigned)((ri + 2) & ~1), ra_o = hist_sa + 16u + 768u * (unsigned)((ri + 1) & ~1);
+        const unsigned ca_e = 256u * (unsigned)((ci + 2) & ~1), ca_o = 8u + 256u * (unsigned)((ci + 1) & ~1);
+        const unsigned oa_e = 64u * (unsigned)((oi + 1) & 6), oa_o = 64u * (unsigned)((oi | 1) & 7) - 60u;
         {
             // (rweight * c-factor) * o-factor, in the reference's multiplication order (keypoints_cpu.cl:93-104)
             const float cw_ee = rw_e * cf_e, cw_eo = rw_e * cf_o, cw_oe = rw_o * cf_e, cw_oo = rw_o * cf_o;
             float4 *dst = reinterpret_cast<float4 *>(&stage.e[l8][0]);
-            dst[0] = make_float4(__int_as_float(ra_e + ca_e + oa_e), cw_ee * ow_e,
-                                 __int_as_float(ra_e + ca_e + oa_o), cw_ee * ow_o);
-            dst[1] = make_float4(__int_as_float(ra_e + ca_o + oa_e), cw_eo * ow_e,
-                                 __int_as_float(ra_e + ca_o + oa_o), cw_eo * ow_o);
-            dst[2] = make_float4(__int_as_float(ra_o + ca_e + oa_e), cw_oe * ow_e,
-                                 __int_as_float(ra_o + ca_e + oa_o), cw_oe * ow_o);
-            dst[3] = make_float4(__int_as_float(ra_o + ca_o + oa_e), cw_oo * ow_e,
-                                 __int_as_float(ra_o + ca_o + oa_o), cw_oo * ow_o);
+            dst[0] = make_float4(__uint_as_float(ra_e + ca_e + oa_e), cw_ee * ow_e,
+                                 __uint_as_float(ra_e + ca_e + oa_o), cw_ee * ow_o);
+            dst[1] = make_float4(__uint_as_float(ra_e + ca_o + oa_e), cw_eo * ow_e,
+                                 __uint_as_float(ra_e + ca_o + oa_o), cw_eo * ow_o);
+            dst[2] = make_float4(__uint_as_float(ra_o + ca_e + oa_e), cw_oe * ow_e,
+                                 __uint_as_float(ra_o + ca_e + oa_o), cw_oe * ow_o);
+            dst[3] = make_float4(__uint_as_float(ra_o + ca_o + oa_e), cw_oo * ow_e,
+                                 __uint_as_float(ra_o + ca_o + oa_o), cw_oo * ow_o);
         }
         __syncwarp();
         // commit the 8 samples of the pass in sample order: lane (pr, pc, po) adds the one term of its class
+        float2 term[8];
+#pragma unroll
+        for (int sidx = 0; sidx < 8; sidx++) term[sidx] = stage.e[sidx][l8];
 #pragma unroll
         for (int sidx = 0; sidx < 8; sidx++) {
-            const float2 t = stage.e[sidx][l8];
-            float *bin = reinterpret_cast<float *>(reinterpret_cast<char *>(hist) + __float_as_int(t.x));
-            *bin += t.y;
+            const unsigned sa = __float_as_uint(term[sidx].x);
+            float v;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(sa));
+            v += term[sidx].y;
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(sa), "f"(v) : "memory");
         }
         __syncwarp();
     }
     __syncwarp();
     // finish, keypoints_cpu.cl:127-160: each lane of the octet owns 16 consecutive descriptor entries
-    // i = 16*l8 + q, i.e. r = l8>>1, c = 2*(l8&1) + (q>>3), o = q&7
-    float *mine = hist + 32 * (4 * (l8 & 1) + 8 * (l8 >> 2)) + 4 * ((l8 >> 1) & 1);
-#define DESC_QOFF(q) (32 * (((q) & 7) >> 1) + 2 * ((q) >> 3) + ((q) & 1))
+    // i = 16*l8 + q, i.e. r = l8>>1, c = 2*(l8&1) + (q>>3), o = q&7  (guard-ring coordinates r + 1, c + 1)
+    const int fr0 = (l8 >> 1) + 1, fc0 = 2 * (l8 & 1) + 1;
     float v[16];
 #pragma unroll
-    for (int q = 0; q < 16; q++) v[q] = mine[DESC_QOFF(q)];
+    for (int q = 0; q < 16; q++) v[q] = hist[desc_bin(fr0, fc0 + (q >> 3), q & 7)];
     __syncwarp();
 #pragma unroll
-    for (int q = 0; q < 16; q++) mine[DESC_QOFF(q)] = v[q] * v[q];
+    for (int q = 0; q < 16; q++) hist[desc_bin(fr0, fc0 + (q >> 3), q & 7)] = v[q] * v[q];
     __syncwarp();
     // the sums of squares are sequential over i = 0..127 in the reference: one lane adds them in that order
     auto ordered_sum = [&]() {
         float acc = 0.0f;
         for (int rc = 0; rc < 16; rc++) {
-            const float *cell = hist + 32 * (4 * ((rc & 3) >> 1) + 8 * (rc >> 3)) + 4 * ((rc >> 2) & 1) + 2 * (rc & 1);
+            const float *cell = hist + desc_bin((rc >> 2) + 1, (rc & 3) + 1, 0);
 #pragma unroll
             for (int o = 0; o < 8; o++) acc += cell[32 * (o >> 1) + (o & 1)];
         }
@@ -278,7 +318,7 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
     for (int q = 0; q < 16; q++) {
         v[q] *= norm;
         if (v[q] > 0.2f) { v[q] = 0.2f; changed = true; }
-        mine[DESC_QOFF(q)] = v[q] * v[q];
+        hist[desc_bin(fr0, fc0 + (q >> 3), q & 7)] = v[q] * v[q];
     }
     changed = (__ballot_sync(0xffffffffu, changed) & omask) != 0;
     __syncwarp();
@@ -347,16 +387,19 @@ __global__ void __launch_bounds__(256) k_size_order(const float4 *__restrict__ k
 // Pipeline form: octets fetch keypoints of ALL octaves from a work queue; rows with NaN are dropped
 // (plan.py:546-550); the survivors of octave o go to out[oct_offset[o] + ...], i.e. the output is grouped by
 // octave in octave order like the reference's concatenation (plan.py:555-565).
-__global__ void __launch_bounds__(DESC_WARPS * 32, 7) k_describe(OctTable T, const float4 *__restrict__ kp,
+__global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe(OctTable T, const float4 *__restrict__ kp,
                                                                const int *__restrict__ kp_tag,
                                                                const int *__restrict__ n_order_p, int cap,
                                                                KpRecord *__restrict__ out, int out_cap,
                                                                const int *__restrict__ oct_offset,
                                                                int *__restrict__ oct_fill, int *__restrict__ queue,
                                                                const int *__restrict__ order) {
-    __shared__ float s_hist[DESC_WARPS][16 * 32];
+    __shared__ float s_hist[DESC_WARPS][DESC_HROWS * 32];
     __shared__ DescRows s_rows[DESC_WARPS * 4];
     __shared__ DescStage s_stage[DESC_WARPS * 4];
+    __shared__ double s_exp[32];
+    if (threadIdx.x < 32) s_exp[threadIdx.x] = c_exp_t32[threadIdx.x];
+    __syncthreads();
     const int lane = threadIdx.x & 31, l8 = lane & 7, obase = lane & 24;
     float *hist = s_hist[threadIdx.x >> 5];
     const int n = min(*n_order_p, cap);
@@ -385,19 +428,21 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 7) k_describe(OctTable T, con
         if (slot >= out_cap) act = false;
         KpRecord *o = out + (act ? slot : 0);
         if (act && l8 == 0) { o->x = k.x; o->y = k.y; o->scale = k.z; o->angle = k.w; }
-        describe_octets(hist, s_rows[threadIdx.x >> 3], s_stage[threadIdx.x >> 3], act, k, T.grad[oct][sc - 1],
-                        T.ori[oct][sc - 1], T.pitch[oct], T.w[oct], T.h[oct], T.octsize[oct], o->desc);
+        describe_octets<false>(hist, s_rows[threadIdx.x >> 3], s_stage[threadIdx.x >> 3], s_exp, act, k, T.go[oct][sc - 1],
+                        T.pitch[oct], T.w[oct], T.h[oct], T.octsize[oct], o->desc);
     }
 }
 
 // Stage-hook form: desc[i] for every input row (no filtering), single gradient plane
-__global__ void __launch_bounds__(DESC_WARPS * 32, 8) k_describe_rows(const float *__restrict__ grad,
-                                                                    const float *__restrict__ ori, int pitch, int w,
+__global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe_rows(const float2 *__restrict__ go, int pitch, int w,
                                                                     int h, const float4 *__restrict__ kp, int n,
                                                                     int octsize, uint8_t *__restrict__ desc) {
-    __shared__ float s_hist[DESC_WARPS][16 * 32];
+    __shared__ float s_hist[DESC_WARPS][DESC_HROWS * 32];
     __shared__ DescRows s_rows[DESC_WARPS * 4];
     __shared__ DescStage s_stage[DESC_WARPS * 4];
+    __shared__ double s_exp[32];
+    if (threadIdx.x < 32) s_exp[threadIdx.x] = c_exp_t32[threadIdx.x];
+    __syncthreads();
     float *hist = s_hist[threadIdx.x >> 5];
     const int noct = (gridDim.x * blockDim.x) >> 3;
     const int rounds = (n + noct - 1) / noct;
@@ -409,7 +454,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 8) k_describe_rows(const floa
             k = kp[gid0];
             act = k.y >= 0.0f;
         }
-        describe_octets(hist, s_rows[threadIdx.x >> 3], s_stage[threadIdx.x >> 3], act, k, grad, ori, pitch, w, h, octsize,
+        describe_octets<true>(hist, s_rows[threadIdx.x >> 3], s_stage[threadIdx.x >> 3], s_exp, act, k, go, pitch, w, h, octsize,
                         desc + 128L * (act ? gid0 : 0));
     }
 }

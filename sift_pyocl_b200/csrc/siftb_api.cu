@@ -116,7 +116,7 @@ struct siftb_plan {
     void *d_raws[NSLOT] = {};  // staging for host input (plan dtype)
     float *d_img = nullptr;    // dense fp32 plane for converted integer/RGB/f64 input
     float *G[6] = {}, *D[5] = {};
-    float *gradp[SIFTB_KOCT][3] = {}, *orip[SIFTB_KOCT][3] = {};  // gradient planes of every octave (k_keypoint.cuh)
+    float2 *gop[SIFTB_KOCT][3] = {};  // (gradient, orientation) planes of every octave (k_keypoint.cuh)
     OctTable table;
     float4 *cand = nullptr, *kp = nullptr;
     int *kp_tag = nullptr;  // octave << 8 | scale
@@ -205,7 +205,7 @@ extern "C" int siftb_plan_destroy(siftb_plan *p) {
     for (auto q : p->G) cudaFree(q);
     for (auto q : p->D) cudaFree(q);
     for (int o = 0; o < SIFTB_KOCT; o++)
-        for (int i = 0; i < 3; i++) { cudaFree(p->gradp[o][i]); cudaFree(p->orip[o][i]); }
+        for (int i = 0; i < 3; i++) cudaFree(p->gop[o][i]);
     cudaFree(p->cand); cudaFree(p->kp); cudaFree(p->kp_tag); cudaFree(p->kp_order); cudaFree(p->d_queue);
     for (int s = 0; s < NSLOT; s++) {
         if (p->h_cnts[s]) cudaFreeHost(p->h_cnts[s]);
@@ -281,10 +281,8 @@ static int plan_create_impl(siftb_plan *p) {
     for (int o = 0; o < p->n_oct; o++) {
         const size_t pl = (size_t)p->opitch[o] * p->oh[o] * sizeof(float);
         for (int i = 0; i < 3; i++) {
-            if ((rc = dalloc(p, &p->gradp[o][i], pl))) return rc;
-            if ((rc = dalloc(p, &p->orip[o][i], pl))) return rc;
-            p->table.grad[o][i] = p->gradp[o][i];
-            p->table.ori[o][i] = p->orip[o][i];
+            if ((rc = dalloc(p, &p->gop[o][i], 2 * pl))) return rc;
+            p->table.go[o][i] = p->gop[o][i];
         }
         p->table.pitch[o] = p->opitch[o];
         p->table.w[o] = p->ow[o];
@@ -550,7 +548,7 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
         {
             ProfScope ps(p, "compute_gradient_orientation", o);
             GradArgs ga;
-            for (int i = 0; i < 3; i++) { ga.g[i] = p->G[i + 1]; ga.grad[i] = p->gradp[o][i]; ga.ori[i] = p->orip[o][i]; }
+            for (int i = 0; i < 3; i++) { ga.g[i] = p->G[i + 1]; ga.go[i] = p->gop[o][i]; }
             ga.pitch = pitch; ga.w = w; ga.h = h;
             dim3 grid((w + 511) / 512, (h + GRAD4_ROWS - 1) / GRAD4_ROWS, 3);  // planes: pitch % 32 == 0, aligned
             k_gradient4<<<grid, 128, 0, st>>>(ga);
@@ -571,7 +569,7 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
         k_octave_offsets<<<1, 1, 0, st>>>(oct_valid, p->n_oct, oct_offset, p->c_nout(slot), p->c_oct(slot, 0) + 3,
                                           size_hist, size_start, n_order);
         k_size_order<<<148, 256, 0, st>>>(p->kp, p->kp_tag, n_kp, n_extra, p->kp_cap, size_start, size_fill, p->kp_order);
-        k_describe<<<148 * 7, DESC_WARPS * 32, 0, st>>>(p->table, p->kp, p->kp_tag, n_order, p->kp_cap,
+        k_describe<<<148 * 6, DESC_WARPS * 32, 0, st>>>(p->table, p->kp, p->kp_tag, n_order, p->kp_cap,
                                                         p->outs[slot], p->out_cap, oct_offset, oct_fill, q_head,
                                                         p->kp_order);
         CKL();
@@ -857,11 +855,11 @@ extern "C" int siftb_pyramid_octave(const float *g0, int height, int width, doub
 extern "C" int siftb_gradient(const float *image, int height, int width, float *grad, float *ori) {
     if (!image || !grad || !ori || height < 2 || width < 2) return fail(SIFTB_EINVAL, "bad argument");
     const long n = (long)height * width;
-    DevBuf d, g, o;
-    DALLOC(d, n * 4); DALLOC(g, n * 4); DALLOC(o, n * 4);
+    DevBuf d, g, o, go;
+    DALLOC(d, n * 4); DALLOC(g, n * 4); DALLOC(o, n * 4); DALLOC(go, n * 8);
     CK(cudaMemcpy(d.p, image, n * 4, cudaMemcpyHostToDevice));
     GradArgs ga;
-    for (int i = 0; i < 3; i++) { ga.g[i] = d.as<float>(); ga.grad[i] = g.as<float>(); ga.ori[i] = o.as<float>(); }
+    for (int i = 0; i < 3; i++) { ga.g[i] = d.as<float>(); ga.go[i] = go.as<float2>(); }
     ga.pitch = width; ga.w = width; ga.h = height;
     if (width % 4 == 0) {  // the form the pipeline uses
         dim3 grid((width + 511) / 512, (height + GRAD4_ROWS - 1) / GRAD4_ROWS, 1);
@@ -870,6 +868,8 @@ extern "C" int siftb_gradient(const float *image, int height, int width, float *
         dim3 grid((width + 255) / 256, (height + GRAD_ROWS - 1) / GRAD_ROWS, 1);
         k_gradient<<<grid, 256>>>(ga);
     }
+    CKL();
+    k_deinterleave<<<148 * 4, 256>>>(go.as<float2>(), n, g.as<float>(), o.as<float>());
     CKL();
     CK(cudaMemcpy(grad, g.p, n * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(ori, o.p, n * 4, cudaMemcpyDeviceToHost));
@@ -927,10 +927,13 @@ extern "C" int siftb_orientation(const float *kp4_in, int n, const float *grad, 
                                  int octsize, float *kp4_out, int cap, int *n_out) {
     if (!kp4_in || !grad || !ori || !kp4_out || !n_out || n < 0 || cap < n) return fail(SIFTB_EINVAL, "bad argument");
     const long np = (long)height * width;
-    DevBuf Gd, Od, K, S, C;
-    DALLOC(Gd, np * 4); DALLOC(Od, np * 4); DALLOC(K, (size_t)cap * 16); DALLOC(S, (size_t)cap * 4); DALLOC(C, 8);
+    DevBuf Gd, Od, GO, K, S, C;
+    DALLOC(Gd, np * 4); DALLOC(Od, np * 4); DALLOC(GO, np * 8); DALLOC(K, (size_t)cap * 16); DALLOC(S, (size_t)cap * 4);
+    DALLOC(C, 8);
     CK(cudaMemcpy(Gd.p, grad, np * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(Od.p, ori, np * 4, cudaMemcpyHostToDevice));
+    k_interleave<<<148 * 4, 256>>>(Gd.as<float>(), Od.as<float>(), np, GO.as<float2>());
+    CKL();
     CK(cudaMemcpy(K.p, kp4_in, (size_t)n * 16, cudaMemcpyHostToDevice));
     std::vector<int> ones(cap > 0 ? cap : 1, 1);
     CK(cudaMemcpy(S.p, ones.data(), (size_t)cap * 4, cudaMemcpyHostToDevice));
@@ -938,7 +941,7 @@ extern "C" int siftb_orientation(const float *kp4_in, int n, const float *grad, 
     CK(cudaMemcpy(C.p, cnt, 8, cudaMemcpyHostToDevice));
     OctTable tb;  // a one-octave table; every row carries tag (0 << 8) | 1
     memset(&tb, 0, sizeof(tb));
-    for (int i = 0; i < 3; i++) { tb.grad[0][i] = Gd.as<float>(); tb.ori[0][i] = Od.as<float>(); }
+    for (int i = 0; i < 3; i++) tb.go[0][i] = GO.as<float2>();
     tb.pitch[0] = width; tb.w[0] = width; tb.h[0] = height; tb.octsize[0] = octsize;
     k_orient<<<148 * 4, 256>>>(tb, K.as<float4>(), S.as<int>(), C.as<int>(), C.as<int>() + 1, cap, kOriSigma, nullptr,
                                nullptr, nullptr);
@@ -955,14 +958,16 @@ extern "C" int siftb_descriptor(const float *kp4, int n, const float *grad, cons
                                 int octsize, uint8_t *desc) {
     if (!kp4 || !grad || !ori || !desc || n < 0) return fail(SIFTB_EINVAL, "bad argument");
     const long np = (long)height * width;
-    DevBuf Gd, Od, K, Dd;
-    DALLOC(Gd, np * 4); DALLOC(Od, np * 4); DALLOC(K, (size_t)n * 16); DALLOC(Dd, (size_t)n * 128);
+    DevBuf Gd, Od, GO, K, Dd;
+    DALLOC(Gd, np * 4); DALLOC(Od, np * 4); DALLOC(GO, np * 8); DALLOC(K, (size_t)n * 16); DALLOC(Dd, (size_t)n * 128);
     CK(cudaMemcpy(Gd.p, grad, np * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(Od.p, ori, np * 4, cudaMemcpyHostToDevice));
+    k_interleave<<<148 * 4, 256>>>(Gd.as<float>(), Od.as<float>(), np, GO.as<float2>());
+    CKL();
     CK(cudaMemcpy(K.p, kp4, (size_t)n * 16, cudaMemcpyHostToDevice));
     CK(cudaMemset(Dd.p, 0, (size_t)n * 128));
     if (n > 0) {
-        k_describe_rows<<<(n + DESC_WARPS - 1) / DESC_WARPS, DESC_WARPS * 32>>>(Gd.as<float>(), Od.as<float>(), width, width, height, K.as<float4>(), n,
+        k_describe_rows<<<(n + DESC_WARPS - 1) / DESC_WARPS, DESC_WARPS * 32>>>(GO.as<float2>(), width, width, height, K.as<float4>(), n,
                                                octsize, Dd.as<uint8_t>());
         CKL();
         CK(cudaMemcpy(desc, Dd.p, (size_t)n * 128, cudaMemcpyDeviceToHost));

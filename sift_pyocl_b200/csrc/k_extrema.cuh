@@ -22,38 +22,50 @@ struct DogStack {
 //  * maxmin_rest: the other 24 neighbours, ordered so that most pixels leave after a few compares, then the edge
 //    test (image.cl:180-186: H00/H11 in double (literal 2.0), H01 float differences then /4.0).
 __device__ __forceinline__ bool maxmin_gate(const float c[5], int scale, float gate) {
-    const float val = c[scale];
-    if (!(fabsf(val) >= gate)) return false;
-    const float sgn = (val > 0.0f) ? 1.0f : -1.0f;  // maximum test for val > 0, minimum test otherwise
-    const float sval = sgn * val;                   // sign flips are exact
-    return !(sgn * c[scale - 1] > sval || sgn * c[scale + 1] > sval);
+    // branch-free (12 of these run per thread and row): for val > 0 the neighbours must not exceed it, otherwise
+    // they must not lie below it -- the reference's sign-flipped strict comparisons, NaN compares false either way
+    const float val = c[scale], a = c[scale - 1], b = c[scale + 1];
+    const bool strong = fabsf(val) >= gate;
+    const bool above = (a > val) | (b > val), below = (a < val) | (b < val);
+    return strong & !((val > 0.0f) ? above : below);
 }
 __device__ __forceinline__ bool maxmin_rest(const DogStack &D, long pos, int scale, float edthresh) {
+    // Two batches of independent loads instead of 24 loads behind 24 early-outs (each a dependent L2 round trip):
+    // the 8 in-plane neighbours first -- they decide most candidates and also feed the edge test -- then the 16
+    // remaining neighbours in the two adjacent scales.
     const float *dc = D.d[scale];
+    const long up = pos - D.pitch, dn_ = pos + D.pitch;
     const float val = dc[pos];
+    const float n_l = dc[pos - 1], n_r = dc[pos + 1];
+    const float u_l = dc[up - 1], u_c = dc[up], u_r = dc[up + 1];
+    const float d_l = dc[dn_ - 1], d_c = dc[dn_], d_r = dc[dn_ + 1];
     const float sgn = (val > 0.0f) ? 1.0f : -1.0f;
     const float sval = sgn * val;
-    if (sgn * dc[pos - 1] > sval || sgn * dc[pos + 1] > sval) return false;
+    if (sgn * n_l > sval || sgn * n_r > sval || sgn * u_l > sval || sgn * u_c > sval || sgn * u_r > sval ||
+        sgn * d_l > sval || sgn * d_c > sval || sgn * d_r > sval)
+        return false;
+    float o[16];
 #pragma unroll
-    for (int dr = -1; dr <= 1; dr += 2) {
-        const float *rowp = dc + pos + (long)dr * D.pitch;
-        if (sgn * rowp[-1] > sval || sgn * rowp[0] > sval || sgn * rowp[1] > sval) return false;
-    }
+    for (int dpl = 0; dpl < 2; dpl++) {
+        const float *pl = D.d[scale + 2 * dpl - 1] + pos;
+        o[8 * dpl + 0] = pl[-1];
+        o[8 * dpl + 1] = pl[1];
 #pragma unroll
-    for (int dpl = -1; dpl <= 1; dpl += 2) {
-        const float *pl = D.d[scale + dpl] + pos;
-        if (sgn * pl[-1] > sval || sgn * pl[1] > sval) return false;
-#pragma unroll
-        for (int dr = -1; dr <= 1; dr += 2) {
-            const float *rowp = pl + (long)dr * D.pitch;
-            if (sgn * rowp[-1] > sval || sgn * rowp[0] > sval || sgn * rowp[1] > sval) return false;
+        for (int dr = 0; dr < 2; dr++) {
+            const float *rowp = pl + (long)(2 * dr - 1) * D.pitch;
+            o[8 * dpl + 2 + 3 * dr] = rowp[-1];
+            o[8 * dpl + 3 + 3 * dr] = rowp[0];
+            o[8 * dpl + 4 + 3 * dr] = rowp[1];
         }
     }
-    const long up = pos - D.pitch, dn_ = pos + D.pitch;
-    float H00 = (float)(((double)dc[up] - 2.0 * (double)val) + (double)dc[dn_]);
-    float H11 = (float)(((double)dc[pos - 1] - 2.0 * (double)val) + (double)dc[pos + 1]);
-    float d1 = dc[dn_ + 1] - dc[dn_ - 1];
-    float d2 = dc[up + 1] - dc[up - 1];
+    bool beaten = false;
+#pragma unroll
+    for (int i = 0; i < 16; i++) beaten = beaten || (sgn * o[i] > sval);
+    if (beaten) return false;
+    float H00 = (float)(((double)u_c - 2.0 * (double)val) + (double)d_c);
+    float H11 = (float)(((double)n_l - 2.0 * (double)val) + (double)n_r);
+    float d1 = d_r - d_l;
+    float d2 = u_r - u_l;
     float H01 = (float)((double)(d1 - d2) / 4.0);
     float det = H00 * H11 - H01 * H01, trace = H00 + H11;  // -fmad=false: no contraction
     float tt = edthresh * trace;
@@ -63,12 +75,139 @@ __device__ __forceinline__ bool maxmin_rest(const DogStack &D, long pos, int sca
 }
 
 #define EXT_ROWS 16
+// Vector form (every plane of a SiftPlan: pitch % 4 == 0, 16-byte aligned base).
+// grid: (ceil(w/512), ceil((h-2*border)/EXT_ROWS)), block 128 threads; a thread owns FOUR adjacent columns and walks
+// EXT_ROWS rows: one 128-bit load per DoG plane and row gives the five values of its four pixels (the row after next
+// is already requested), maxmin_gate runs on all 12 (pixel, scale) pairs from registers and leaves a 12-bit survivor
+// mask per thread.  The survivors of a warp (2-3.5 % of the pairs) are queued in shared memory -- slots come from a
+// warp prefix sum of the masks' popcounts -- and finished 32 at a time, one per lane (maxmin_rest is long and would
+// otherwise run for one or two lanes of a warp at a time).
+// cand rows: (val, row, col, scale).  n_cand = total candidates, stage[(s-1)*3] = per-scale count.
+#define EXT_QSIZE 512  // ring entries per warp: <= 31 left over + 32 lanes x 12 new survivors per row
+__global__ void __launch_bounds__(128) k_extrema(DogStack D, int border, float gate, float edthresh,
+                                                  float4 *__restrict__ cand, int cap, int *__restrict__ n_cand,
+                                                  int *__restrict__ stage /* [3][3] or null */, int scale_lo,
+                                                  int nscales) {
+    __shared__ unsigned short s_q[4][EXT_QSIZE];  // (row offset << 9) | (scale index << 7) | (lane << 2) | column in group
+    __shared__ float4 s_hits[4][64];
+    const int lane = threadIdx.x & 31;
+    const int x4 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const int col0 = x4 - 4 * lane;                // first column of the warp
+    const int row0 = border + blockIdx.y * EXT_ROWS;
+    unsigned short *q = s_q[threadIdx.x >> 5];
+    const bool active = x4 < D.pitch;              // the 128-bit loads stay inside the (padded) row
+    unsigned colmask = 0;                          // columns of my group inside [border, w - border)
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (x4 + k >= border && x4 + k < D.w - border) colmask |= 1u << k;
+    if (!active) colmask = 0;
+    colmask |= (colmask << 4) | (colmask << 8);    // the same columns for the three scales
+    unsigned scalemask = 0;
+#pragma unroll
+    for (int si = 0; si < 3; si++)
+        if (1 + si >= scale_lo && 1 + si < scale_lo + nscales) scalemask |= 0xfu << (4 * si);
+    colmask &= scalemask;
+    int head = 0, qn = 0;  // warp-uniform ring state
+    // Extrema found by this warp are collected in shared memory and appended to the candidate list in batches: one
+    // atomicAdd round trip per ~32 candidates instead of one per group of survivors (the warp waits for its result).
+    float4 *hits = s_hits[threadIdx.x >> 5];
+    int n_hits = 0, cnt_s1 = 0, cnt_s2 = 0, cnt_s3 = 0;  // warp-uniform
+    auto flush = [&]() {
+        if (n_hits == 0) return;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(n_cand, n_hits);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int i = lane; i < n_hits; i += 32)
+            if (base + i < cap) cand[base + i] = hits[i];  // image.cl:202-208
+        n_hits = 0;
+        __syncwarp();
+    };
+    auto finish = [&](int nb) {  // the first nb (<= 32) queued survivors, one per lane
+        bool hit = false;
+        int gid1 = 0, gcol = 0, scale = 1;
+        long pos = 0;
+        if (lane < nb) {
+            const unsigned e = q[(head + lane) & (EXT_QSIZE - 1)];
+            gid1 = row0 + (int)(e >> 9);
+            gcol = col0 + (int)(e & 127u);
+            scale = 1 + (int)((e >> 7) & 3u);
+            pos = (long)gid1 * D.pitch + gcol;
+            hit = maxmin_rest(D, pos, scale, edthresh);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (m) {
+            if (hit) hits[n_hits + __popc(m & lanemask_lt())] = make_float4(D.d[scale][pos], (float)gid1, (float)gcol, (float)scale);
+            n_hits += __popc(m);
+            cnt_s1 += __popc(__ballot_sync(0xffffffffu, hit && scale == 1));
+            cnt_s2 += __popc(__ballot_sync(0xffffffffu, hit && scale == 2));
+            cnt_s3 += __popc(__ballot_sync(0xffffffffu, hit && scale == 3));
+            __syncwarp();
+            if (n_hits > 32) flush();  // room for the next 32
+        }
+        head = (head + nb) & (EXT_QSIZE - 1);
+        qn -= nb;
+    };
+    const int r_end = min(EXT_ROWS, D.h - border - row0);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto ld5 = [&](int r, float4 v[5]) {
+#pragma unroll
+        for (int i = 0; i < 5; i++)
+            v[i] = (active && r < r_end) ? __ldg(reinterpret_cast<const float4 *>(D.d[i] + (long)(row0 + r) * D.pitch + x4)) : zero4;
+    };
+    float4 c1[5], c2[5];
+    ld5(0, c1);
+    ld5(1, c2);
+    for (int r = 0; r < r_end; r++) {
+        float4 c[5];
+#pragma unroll
+        for (int i = 0; i < 5; i++) { c[i] = c1[i]; c1[i] = c2[i]; }
+        ld5(r + 2, c2);
+        unsigned mask = 0;
+#pragma unroll
+        for (int si = 0; si < 3; si++) {
+            const float px[4][5] = {{c[0].x, c[1].x, c[2].x, c[3].x, c[4].x}, {c[0].y, c[1].y, c[2].y, c[3].y, c[4].y},
+                                    {c[0].z, c[1].z, c[2].z, c[3].z, c[4].z}, {c[0].w, c[1].w, c[2].w, c[3].w, c[4].w}};
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (maxmin_gate(px[k], 1 + si, gate)) mask |= 1u << (4 * si + k);
+        }
+        mask &= colmask;
+        if (__any_sync(0xffffffffu, mask != 0)) {
+            // queue slots: exclusive prefix sum of the popcounts over the lanes
+            const int cnt = __popc(mask);
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            int slot = head + qn + incl - cnt;
+            while (mask) {
+                const int bit = __ffs(mask) - 1;
+                mask &= mask - 1;
+                q[slot++ & (EXT_QSIZE - 1)] = (unsigned short)((r << 9) | ((bit >> 2) << 7) | (lane << 2) | (bit & 3));
+            }
+            qn += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        __syncwarp();
+        while (qn >= 32) { finish(32); __syncwarp(); }
+    }
+    while (qn > 0) { finish(min(qn, 32)); __syncwarp(); }
+    flush();
+    if (stage && lane == 0) {
+        if (cnt_s1) atomicAdd(&stage[0], cnt_s1);
+        if (cnt_s2) atomicAdd(&stage[3], cnt_s2);
+        if (cnt_s3) atomicAdd(&stage[6], cnt_s3);
+    }
+}
+
+// Scalar form for planes whose pitch is not a multiple of 4 floats (stage hook on dense host planes).
 // grid: (ceil(w/128), ceil((h-2*border)/EXT_ROWS)), block 128 threads along x; every thread walks EXT_ROWS rows
 // of its column and runs maxmin_gate on nscales scales per pixel from the five DoG values loaded together.  The
 // survivors of a warp are queued in shared memory and finished 32 at a time, one per lane (maxmin_rest is long and
 // would otherwise run for one or two lanes of a warp at a time).
 // cand rows: (val, row, col, scale).  n_cand = total candidates, stage[(s-1)*3] = per-scale count.
-__global__ void __launch_bounds__(128) k_extrema(DogStack D, int border, float gate, float edthresh,
+__global__ void __launch_bounds__(128) k_extrema_scalar(DogStack D, int border, float gate, float edthresh,
                                                   float4 *__restrict__ cand, int cap, int *__restrict__ n_cand,
                                                   int *__restrict__ stage /* [3][3] or null */, int scale_lo,
                                                   int nscales) {

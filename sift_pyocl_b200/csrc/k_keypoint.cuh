@@ -90,15 +90,28 @@ __global__ void __launch_bounds__(128, 8) k_gradient4(GradArgs a) {
         y = max(0, min(y, a.h - 1));
         return *reinterpret_cast<const float4 *>(g + (long)y * a.pitch + xc);
     };
+    // the two edge lanes of a warp need one value from outside the warp's 128 columns: lane 0 the pixel left of its
+    // group, lane 31 the pixel right of it.  Like the rows, it is requested one iteration ahead (a load issued and
+    // consumed in the same iteration stalls the whole warp for an L2 round trip: 25 % of this kernel's samples).
+    const bool has_left = active && x4 > 0, has_right = x4 + 4 < a.w;
+    auto ldedge = [&](int y) {
+        y = max(0, min(y, a.h - 1));
+        float v = 0.0f;
+        if (lane == 0 && has_left) v = g[(long)y * a.pitch + xc - 1];
+        if (lane == 31 && has_right) v = g[(long)y * a.pitch + xc + 4];
+        return v;
+    };
     const AtanConsts K;
     float4 up = ldrow(y0 - 1), cur = ldrow(y0), dn = ldrow(y0 + 1);
+    float edge = ldedge(y0);
     const int y_end = min(y0 + GRAD4_ROWS, a.h);
     for (int y = y0; y < y_end; y++) {
         const float4 nxt = ldrow(y + 2);
+        const float edge_nxt = ldedge(y + 1);
         // horizontal neighbours of the 4-column group
         float left = __shfl_up_sync(0xffffffffu, cur.w, 1), right = __shfl_down_sync(0xffffffffu, cur.x, 1);
-        if (lane == 0) left = (active && x4 > 0) ? g[(long)y * a.pitch + xc - 1] : cur.x;
-        if (lane == 31) right = x4 + 4 < a.w ? g[(long)y * a.pitch + xc + 4] : cur.w;
+        if (lane == 0) left = has_left ? edge : cur.x;
+        if (lane == 31) right = has_right ? edge : cur.w;
         // image.cl:58-66: xgrad = I[x+1]-I[x-1]; at the two image borders the one-sided difference, doubled
         const int last = a.w - 1 - x4;  // element index of the last image column inside this group (or >= 4)
         const float l0 = x4 == 0 ? cur.x : left, s0 = (x4 == 0 || last == 0) ? 2.0f : 1.0f;
@@ -131,6 +144,7 @@ __global__ void __launch_bounds__(128, 8) k_gradient4(GradArgs a) {
         up = cur;
         cur = dn;
         dn = nxt;
+        edge = edge_nxt;
     }
 }
 

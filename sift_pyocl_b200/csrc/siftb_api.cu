@@ -435,6 +435,24 @@ static DogStack make_dogstack(float *const D[5], int pitch, int w, int h) {
     return s;
 }
 
+// 3x3x3 extrema of one octave: the 4-columns-per-thread kernel on aligned planes, else the scalar one
+static int launch_extrema(cudaStream_t st, const DogStack &ds, float gate, float edthresh, float4 *cand, int cap,
+                          int *n_cand, int *stage, int scale_lo, int nscales) {
+    if (!(ds.w > 2 * kBorderDist && ds.h > 2 * kBorderDist)) return 0;
+    bool aligned = ds.pitch % 4 == 0;
+    for (int i = 0; i < 5; i++) aligned = aligned && (((uintptr_t)ds.d[i] & 15) == 0);
+    const int rows = (ds.h - 2 * kBorderDist + EXT_ROWS - 1) / EXT_ROWS;
+    if (aligned) {
+        dim3 grid((ds.w + 511) / 512, rows);
+        k_extrema<<<grid, 128, 0, st>>>(ds, kBorderDist, gate, edthresh, cand, cap, n_cand, stage, scale_lo, nscales);
+    } else {
+        dim3 grid((ds.w + 127) / 128, rows);
+        k_extrema_scalar<<<grid, 128, 0, st>>>(ds, kBorderDist, gate, edthresh, cand, cap, n_cand, stage, scale_lo, nscales);
+    }
+    CKL();
+    return 0;
+}
+
 struct ProfScope {
     siftb_plan *p;
     int idx = -1;
@@ -531,11 +549,9 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
         DogStack ds = make_dogstack(p->D, pitch, w, h);
         if (w > 2 * kBorderDist && h > 2 * kBorderDist) {
             ProfScope ps(p, "local_maxmin", o);
-            dim3 grid((w + 127) / 128, (h - 2 * kBorderDist + EXT_ROWS - 1) / EXT_ROWS);
-            k_extrema<<<grid, 128, 0, st>>>(ds, kBorderDist, contrast_gate(kPeakThresh),
-                                            octsize <= 1 ? kEdgeThresh1 : kEdgeThresh, p->cand, p->kpsize, c + 0, stage, 1,
-                                            kScales);
-            CKL();
+            if ((rc = launch_extrema(st, ds, contrast_gate(kPeakThresh), octsize <= 1 ? kEdgeThresh1 : kEdgeThresh, p->cand,
+                                     p->kpsize, c + 0, stage, 1, kScales)))
+                return rc;
             p->launches += 1;
         }
         {
@@ -889,10 +905,9 @@ extern "C" int siftb_local_maxmin(const float *dogs5, int height, int width, int
         float *Dp[5];
         for (int i = 0; i < 5; i++) Dp[i] = D.as<float>() + i * np;
         DogStack ds = make_dogstack(Dp, width, width, height);
-        dim3 grid((width + 127) / 128, (height - 2 * kBorderDist + EXT_ROWS - 1) / EXT_ROWS);
-        k_extrema<<<grid, 128>>>(ds, kBorderDist, contrast_gate(kPeakThresh), octsize <= 1 ? kEdgeThresh1 : kEdgeThresh,
-                                 K.as<float4>(), cap, C.as<int>(), nullptr, scale, 1);
-        CKL();
+        int rc = launch_extrema(0, ds, contrast_gate(kPeakThresh), octsize <= 1 ? kEdgeThresh1 : kEdgeThresh,
+                                K.as<float4>(), cap, C.as<int>(), nullptr, scale, 1);
+        if (rc) return rc;
     }
     CK(cudaMemcpy(n, C.p, 4, cudaMemcpyDeviceToHost));
     int m = *n < cap ? *n : cap;

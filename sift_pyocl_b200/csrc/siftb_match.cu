@@ -3,6 +3,7 @@
 // a non-Python host uses to shard a batch of images.
 #include <dlfcn.h>
 #include <nccl.h>  // types only: libnccl.so.2 is resolved at run time (dlopen), the library has no link-time dependency
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -27,7 +28,7 @@ struct siftb_matcher {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::mutex mtx;
-    GrowBuf recs[2], desc[2], pairs, gather;
+    GrowBuf recs[2], desc[2], pairs, gather, partial;
     int n[2] = {0, 0};
     int pairs_cap = 0, n_match = 0;  // n_match: pairs stored by the last run (<= pairs_cap)
     int *d_cnt = nullptr, *h_cnt = nullptr;
@@ -71,6 +72,7 @@ extern "C" int siftb_matcher_destroy(siftb_matcher *m) {
         for (int i = 0; i < 2; i++) { m->recs[i].release(); m->desc[i].release(); }
         m->pairs.release();
         m->gather.release();
+        m->partial.release();
         if (m->stream) cudaStreamDestroy(m->stream);
     }
     delete m;
@@ -149,10 +151,38 @@ extern "C" int siftb_matcher_run(siftb_matcher *m, float ratio_th, int cap, int 
     }
     {
         EvScope ev(m, "matching");
-        k_match_l1<<<(m->n[0] + MATCH_THREADS - 1) / MATCH_THREADS, MATCH_THREADS, 0, m->stream>>>(
-            m->desc[0].as<uint32_t>(), m->n[0], m->desc[1].as<uint32_t>(), m->n[1], ratio_th, m->pairs.as<int2>(), cap,
-            m->d_cnt);
-        CKL();
+        const int n1 = m->n[0], n2 = m->n[1];
+        // two queries per thread once the first list is long enough to fill the GPU that way (k_match.cuh)
+        int qpt = n1 >= 148 * 4 * MATCH_THREADS * 2 ? 2 : 1;
+        if (const char *e = getenv("SIFTB_MATCH_QPT")) qpt = e[0] == '2' ? 2 : 1;  // A/B switch for measurements
+        const int qblocks = (n1 + MATCH_THREADS * qpt - 1) / (MATCH_THREADS * qpt);
+        // long second lists are cut into up to 8 segments of >= 16384 rows (k_match.cuh: load balance); the
+        // per-segment partial results are folded by k_match_merge
+        int nseg = n2 / 16384;
+        nseg = nseg < 1 ? 1 : (nseg > 8 ? 8 : nseg);
+        const uint32_t *a1 = m->desc[0].as<uint32_t>(), *a2 = m->desc[1].as<uint32_t>();
+        if (nseg == 1) {
+            if (qpt == 2)
+                k_match_l1<false, 2><<<qblocks, MATCH_THREADS, 0, m->stream>>>(a1, n1, a2, n2, n2, ratio_th, m->pairs.as<int2>(),
+                                                                             cap, m->d_cnt, nullptr);
+            else
+                k_match_l1<false, 1><<<qblocks, MATCH_THREADS, 0, m->stream>>>(a1, n1, a2, n2, n2, ratio_th, m->pairs.as<int2>(),
+                                                                             cap, m->d_cnt, nullptr);
+            CKL();
+        } else {
+            const int seg_rows = ((n2 + nseg - 1) / nseg + MATCH_TILE - 1) / MATCH_TILE * MATCH_TILE;
+            CK(m->partial.reserve((size_t)n1 * nseg * sizeof(MatchPartial)));
+            if (qpt == 2)
+                k_match_l1<true, 2><<<dim3(qblocks, nseg), MATCH_THREADS, 0, m->stream>>>(
+                    a1, n1, a2, n2, seg_rows, ratio_th, nullptr, cap, nullptr, m->partial.as<MatchPartial>());
+            else
+                k_match_l1<true, 1><<<dim3(qblocks, nseg), MATCH_THREADS, 0, m->stream>>>(
+                    a1, n1, a2, n2, seg_rows, ratio_th, nullptr, cap, nullptr, m->partial.as<MatchPartial>());
+            CKL();
+            k_match_merge<<<(n1 + 255) / 256, 256, 0, m->stream>>>(m->partial.as<MatchPartial>(), n1, nseg, ratio_th,
+                                                                 m->pairs.as<int2>(), cap, m->d_cnt);
+            CKL();
+        }
     }
     CK(cudaMemcpyAsync(m->h_cnt, m->d_cnt, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));

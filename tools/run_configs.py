@@ -68,8 +68,13 @@ if "4" in which:  # MatchPlan 100k x 100k (L1, ratio 0.73^2)
     k1, k2 = np.zeros(n, dtype_kp), np.zeros(n, dtype_kp)
     k1["desc"], k2["desc"] = d1, d2.astype(np.uint8)
     k1, k2 = k1.view(np.recarray), k2.view(np.recarray)
-    mp = sift.MatchPlan()
-    dt, raw = timed(lambda: mp.match(k1, k2, raw_results=True), 2)
+    mp = sift.MatchPlan(profile=True)
+    dt, raw = timed(lambda: mp.match(k1, k2, raw_results=True), 3)
+    kernel_ms = sorted(ms for name, ms in mp.events if name == "matching")
+    kernel_ms = kernel_ms[len(kernel_ms) // 2]
+    mp.hold(0, k1)
+    mp.hold(1, k2)
+    dt_res, _ = timed(lambda: mp.match(k1, k2, raw_results=True), 3)   # both lists resident on the device
     sub = np.sort(rng.choice(n, 4000, replace=False))
     want = siftref.match(k1[sub], k2)
     got = raw[np.isin(raw[:, 0], sub)]
@@ -77,8 +82,13 @@ if "4" in which:  # MatchPlan 100k x 100k (L1, ratio 0.73^2)
     ok = np.array_equal(np.searchsorted(sub, got[:, 0]), want[:, 0]) and np.array_equal(got[:, 1], want[:, 1])
     inv = np.empty(n, np.int64)
     inv[perm] = np.arange(n)
-    print(json.dumps({"config": 4, "n1": n, "n2": n, "ms": 1e3 * dt, "matches": int(len(raw)),
-                      "sad_ops_per_s": n * n * 128 / dt, "subset_4000_equals_oracle": bool(ok),
+    # VABSDIFF4.U8.ACC issues at 64 lanes/clk/SM (tools/sad_probe.cu): the floor of a brute-force L1 scan
+    sm_clock = torch.cuda.clock_rate() * 1e6 if hasattr(torch.cuda, "clock_rate") else 1.965e9
+    floor_ms = 1e3 * (n * n * 32) / (64 * 148 * 1.965e9)
+    print(json.dumps({"config": 4, "n1": n, "n2": n, "ms_host_lists": 1e3 * dt, "ms_resident_lists": 1e3 * dt_res,
+                      "kernel_ms": kernel_ms, "vabsdiff4_floor_ms_at_1965MHz": floor_ms,
+                      "kernel_frac_of_floor": floor_ms / kernel_ms, "matches": int(len(raw)),
+                      "byte_sad_per_s_kernel": n * n * 128 / (kernel_ms / 1e3), "subset_4000_equals_oracle": bool(ok),
                       "true_pairs_found": int((inv[raw[:, 0]] == raw[:, 1]).sum())}))
 if "5" in which:  # LinearAlign 8192^2 pair
     from scipy.ndimage import affine_transform
@@ -87,13 +97,25 @@ if "5" in which:  # LinearAlign 8192^2 pair
     off = np.array([7.0, 5.0])
     moved = affine_transform(ref, M, offset=off, order=1, mode="reflect").astype(np.float32)
     t0 = time.perf_counter()
-    la = sift.LinearAlign(ref)
+    la = sift.LinearAlign(ref, profile=True)
     t_init = time.perf_counter() - t0
+    la.align(moved)  # warm-up (buffers of the matcher and of the warp are allocated on first use)
+    la.sift.reset_timer(), la.match.reset_timer()
+    la.events = []
     t0 = time.perf_counter()
-    out = la.align(moved, return_all=True)
+    res = la.align(moved)                      # the reference's call: aligned image only
     t_align = time.perf_counter() - t0
+    dev = {}
+    for name, ms in la.sift.events + la.match.events:
+        key = name.split(" octave")[0]
+        dev[key] = dev.get(key, 0.0) + ms
+    t0 = time.perf_counter()
+    out = la.align(moved, return_all=True)     # + keypoints and matched records on the host
+    t_all = time.perf_counter() - t0
     core = (slice(256, -256), slice(256, -256))
     print(json.dumps({"config": 5, "ref_keypoints": int(la.ref_kp.size), "init_s": t_init, "align_s": t_align,
+                      "align_return_all_s": t_all, "device_ms": {k: round(v, 3) for k, v in sorted(dev.items())},
+                      "device_ms_total": sum(dev.values()),
                       "matches": int(out["matching"].shape[0]), "rms": float(out["rms"]),
                       "err_before": float(abs(moved - ref)[core].mean()),
                       "err_after": float(abs(out["result"] - ref)[core].mean()),

@@ -62,6 +62,8 @@ SIFTB_API int siftb_device_count(int *n);                       /* replaces clin
 
 /* ---- page-locked host memory for asynchronous copies -------------------------------------- */
 SIFTB_API int siftb_host_alloc(void **ptr, uint64_t bytes);
+/* write-combined variant for upload-only buffers (the CPU writes, the device reads; CPU reads are very slow) */
+SIFTB_API int siftb_host_alloc_wc(void **ptr, uint64_t bytes);
 SIFTB_API int siftb_host_free(void *ptr);
 
 /* ---- SiftPlan ------------------------------------------------------------------------------ */

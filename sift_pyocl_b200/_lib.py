@@ -36,6 +36,7 @@ SIGNATURES = {
     "siftb_version": (c_int, []),
     "siftb_device_count": (c_int, [c_int_p]),
     "siftb_host_alloc": (c_int, [ctypes.POINTER(c_void_p), c_u64]),
+    "siftb_host_alloc_wc": (c_int, [ctypes.POINTER(c_void_p), c_u64]),
     "siftb_host_free": (c_int, [c_void_p]),
     "siftb_plan_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_double, c_int, ctypes.POINTER(c_void_p)]),
     "siftb_plan_destroy": (c_int, [c_void_p]),
@@ -171,13 +172,15 @@ def device_info(obj):
     return None, None
 
 
-def pinned_empty(shape, dtype):
-    """numpy array backed by page-locked host memory (asynchronous H<->D copies)."""
+def pinned_empty(shape, dtype, write_combined=False):
+    """numpy array backed by page-locked host memory (asynchronous H<->D copies).  ``write_combined``: for
+    upload-only buffers (fill them once, never read them back on the CPU)."""
     lib = load()
     dtype = numpy.dtype(dtype)
     nbytes = int(numpy.prod(shape)) * dtype.itemsize
     p = c_void_p()
-    check(lib.siftb_host_alloc(ctypes.byref(p), max(nbytes, 1)))
+    alloc = lib.siftb_host_alloc_wc if write_combined else lib.siftb_host_alloc
+    check(alloc(ctypes.byref(p), max(nbytes, 1)))
     buf = (ctypes.c_char * max(nbytes, 1)).from_address(p.value)
     arr = numpy.frombuffer(buf, dtype=dtype, count=int(numpy.prod(shape))).reshape(shape)
     _PINNED[arr.ctypes.data] = p.value

@@ -129,7 +129,8 @@ struct siftb_plan {
     int *d_queue = nullptr;
     int *d_cnts[NSLOT] = {};
     int *h_cnts[NSLOT] = {};  // pinned mirrors
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // host -> device image copies
+    cudaStream_t d2h_stream = nullptr;   // device -> host record copies (PCIe is full duplex: never queued behind an upload)
     cudaEvent_t ev_h2d[NSLOT] = {}, ev_done[NSLOT] = {}, ev_d2h[NSLOT] = {};
     cudaEvent_t ev_ext = nullptr;  // siftb_plan_wait_stream
     const void *src_ptr[NSLOT] = {};  // device pointer of the image submitted to each slot, and its pixel type
@@ -189,6 +190,13 @@ extern "C" int siftb_host_alloc(void **ptr, uint64_t bytes) {
     CK(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable));
     return 0;
 }
+// write-combined page-locked memory: for buffers the CPU only WRITES (input images); the device reads them over
+// PCIe without snooping the CPU caches.  CPU reads from it are very slow.
+extern "C" int siftb_host_alloc_wc(void **ptr, uint64_t bytes) {
+    if (!ptr) return fail(SIFTB_EINVAL, "ptr is null");
+    CK(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable | cudaHostAllocWriteCombined));
+    return 0;
+}
 extern "C" int siftb_host_free(void *ptr) {
     CK(cudaFreeHost(ptr));
     return 0;
@@ -199,6 +207,7 @@ extern "C" int siftb_plan_destroy(siftb_plan *p) {
     DeviceGuard dg_(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
+    if (p->d2h_stream) cudaStreamSynchronize(p->d2h_stream);
     for (int s = 0; s < NSLOT; s++) { cudaFree(p->d_raws[s]); cudaFree(p->outs[s]); cudaFree(p->d_cnts[s]); }
     cudaFree(p->d_img);
     p->d_warp.release();
@@ -215,6 +224,7 @@ extern "C" int siftb_plan_destroy(siftb_plan *p) {
     }
     if (p->ev_ext) cudaEventDestroy(p->ev_ext);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
+    if (p->d2h_stream) cudaStreamDestroy(p->d2h_stream);
     for (auto &ev : p->events_s) for (auto &e : ev) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
@@ -225,6 +235,7 @@ static int plan_create_impl(siftb_plan *p) {
     DeviceGuard dg_(p->device);
     CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&p->d2h_stream, cudaStreamNonBlocking));
     for (int s = 0; s < NSLOT; s++) {
         CK(cudaEventCreateWithFlags(&p->ev_h2d[s], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&p->ev_done[s], cudaEventDisableTiming));
@@ -629,11 +640,13 @@ static int collect_impl(siftb_plan *p, siftb_kp *out, int cap, int *n_out, int *
         memcpy(&minmax[1], &b, 4);
     }
     if (out && ncopy > 0) {
-        // D->H on the copy stream: the compute stream may already be running the next image
+        // D->H on its own stream: the compute stream may already be running the next image and the upload stream
+        // may hold the images after that (waiting for THEM here serialised upload and download: at 8 GPUs per host,
+        // where an upload takes longer than the kernels, that doubled the end-to-end step)
         CK(cudaMemcpyAsync(out, p->outs[slot], (size_t)ncopy * sizeof(siftb_kp), cudaMemcpyDeviceToHost,
-                           p->copy_stream));
-        CK(cudaEventRecord(p->ev_d2h[slot], p->copy_stream));
-        CK(cudaStreamSynchronize(p->copy_stream));
+                           p->d2h_stream));
+        CK(cudaEventRecord(p->ev_d2h[slot], p->d2h_stream));
+        CK(cudaStreamSynchronize(p->d2h_stream));
     }
     if (n_out) *n_out = n;
     if (rc == SIFTB_EOVERFLOW) return fail(rc, "keypoint buffer overflow (reference: plan.py:771 warning)");
@@ -672,9 +685,9 @@ extern "C" int siftb_plan_fetch_records(siftb_plan *p, siftb_kp *out, int cap, i
     if (n > cap) n = cap;
     if (n_out) *n_out = n;
     if (n > 0) {
-        CK(cudaMemcpyAsync(out, p->outs[slot], (size_t)n * sizeof(siftb_kp), cudaMemcpyDeviceToHost, p->copy_stream));
-        CK(cudaEventRecord(p->ev_d2h[slot], p->copy_stream));
-        CK(cudaStreamSynchronize(p->copy_stream));
+        CK(cudaMemcpyAsync(out, p->outs[slot], (size_t)n * sizeof(siftb_kp), cudaMemcpyDeviceToHost, p->d2h_stream));
+        CK(cudaEventRecord(p->ev_d2h[slot], p->d2h_stream));
+        CK(cudaStreamSynchronize(p->d2h_stream));
     }
     return 0;
 }

@@ -277,9 +277,10 @@ class SiftPlan(object):
                 self.collect(records=False)
 
     @staticmethod
-    def pinned_empty(shape, dtype=numpy.float32):
-        """numpy array in page-locked host memory (asynchronous H<->D copies)."""
-        return _lib.pinned_empty(shape, dtype)
+    def pinned_empty(shape, dtype=numpy.float32, write_combined=False):
+        """numpy array in page-locked host memory (asynchronous H<->D copies); ``write_combined`` for buffers
+        that are only filled by the CPU and read by the device."""
+        return _lib.pinned_empty(shape, dtype, write_combined)
 
     def device_records(self):
         """(device pointer of the record array, device pointer of the int32 record count) of the last

@@ -81,6 +81,10 @@ SIFTB_API int siftb_plan_octave_shape(const siftb_plan *plan, int octave, int *w
 SIFTB_API uint64_t siftb_plan_device_bytes(const siftb_plan *plan);   /* plan.py:226 _calc_memory */
 SIFTB_API void *siftb_plan_stream(const siftb_plan *plan);            /* cudaStream_t of the plan's queue */
 SIFTB_API int siftb_plan_set_profile(siftb_plan *plan, int enable);   /* plan.py:185-186 PROFILING_ENABLE */
+/* Which of the reference's two kernel families the orientation / descriptor stages reproduce (plan.py:667-725 picks
+ * by device type; they give different numbers): 0 = orientation_cpu.cl + keypoints_cpu.cl
+ * (default: devicetype "CPU", the parity target), 1 = orientation_gpu.cl + keypoints_gpu2.cl (devicetype "GPU"). */
+SIFTB_API int siftb_plan_set_variant(siftb_plan *plan, int variant);
 SIFTB_API int siftb_plan_device(const siftb_plan *plan);               /* CUDA ordinal the plan lives on */
 /* Orders the plan's queue after everything enqueued so far on `stream` (a cudaStream_t of the plan's device; the
  * handles 0x1 / 0x2 are CUDA's legacy / per-thread default streams): call it before handing a device-resident
@@ -154,6 +158,11 @@ SIFTB_API int siftb_orientation(const float *kp4_in, int n, const float *grad, c
 /* keypoints_cpu.cl:36: rows (x,y,sigma*oct,angle) -> uint8[n][128] */
 SIFTB_API int siftb_descriptor(const float *kp4, int n, const float *grad, const float *ori, int height, int width,
                      int octsize, uint8_t *desc);
+/* the same two stages with the kernel family selectable: variant 1 = orientation_gpu.cl:69 / keypoints_gpu2.cl:68 */
+SIFTB_API int siftb_orientation_v(const float *kp4_in, int n, const float *grad, const float *ori, int height, int width,
+                        int octsize, float *kp4_out, int cap, int *n_out, int variant);
+SIFTB_API int siftb_descriptor_v(const float *kp4, int n, const float *grad, const float *ori, int height, int width,
+                       int octsize, uint8_t *desc, int variant);
 
 /* ---- MatchPlan (match.py:52-272, matching_{cpu,gpu}.cl:matching) ----------------------------- */
 /* The matcher owns persistent device buffers like the reference's buffers["Kp_1"], ["Kp_2"], ["match"], ["cnt"]

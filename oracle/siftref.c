@@ -527,9 +527,92 @@ static int orient_one(float *k, const float *grad, const float *ori, int octsize
     return n_extra;
 }
 
-API int siftref_orientation(float *keypoints, const float *grad, const float *ori, int *counter, int octsize,
-                            float OriSigma, int nb_keypoints, int keypoints_start, int keypoints_end, int grad_width,
-                            int grad_height) {
+/* orientation_gpu.cl:69-315  the GPU variant of orientation_assignment (SURVEY App. A.7 "GPU variant       */
+/* differences"): bin = (int)(18 (ori + pi) / pi) with +-36 wrap, only the first WORKGROUP_SIZE = 128 columns of   */
+/* a window row are visited, smoothing multiplies by (1.0f / 3.0f), tree argmax (ties: :187-236), angle wrapped    */
+/* into [0, 2] then (a - 1) pi, extra peaks not range-filtered.  The cross-warp race of the smoothing step         */
+/* (:157-172) is resolved the way lock-step execution resolves it: every bin sees the OLD values of    */
+/* its neighbours, bin 35 the NEW bin 0 (the same data flow as the CPU variant).                                   */
+static int orient_one_gpu(float *k, const float *grad, const float *ori, int octsize, float OriSigma, int grad_width,
+                          int grad_height, float *extra_angles) {
+    const int WG = 128;
+    const float ONE_3 = 1.0f / 3.0f, ONE_18 = 1.0f / 18.0f;
+    int i, j, r, n_extra = 0;
+    float hist[36], hist2[128];
+    int pos[128];
+    for (i = 0; i < 36; i++) hist[i] = 0.0f;
+    int row = (int)((double)k[1] + 0.5), col = (int)((double)k[2] + 0.5);
+    float sigma = OriSigma * k[3];
+    int radius = (int)((double)sigma * 3.0);
+    int rmin = MAX(0, row - radius), cmin = MAX(0, col - radius);
+    int rmax = MIN(row + radius, grad_height - 2), cmax = MIN(col + radius, grad_width - 2);
+    float two_s2 = (2.0f * sigma) * sigma;
+    float rad2 = ((float)(radius * radius)) + 0.5f;
+    for (r = rmin; r <= rmax; r++) {
+        for (int lid0 = 0; lid0 < WG; lid0++) {   /* lane 0 adds the row's samples in lane order (:141-145) */
+            int c = cmin + lid0;
+            if (c > cmax) break;
+            float gval = grad[(long)r * grad_width + c];
+            float dr = (r - k[1]), dc = (c - k[2]);
+            float t1 = dr * dr, t2 = dc * dc;
+            float distsq = t1 + t2;
+            if (gval > 0.0f && distsq < rad2) {
+                float angle = ori[(long)r * grad_width + c];
+                int bin = (int)((18.0f * (angle + M_PI_F)) * M_1_PI_F);
+                if (bin < 0) bin += 36;
+                if (bin > 35) bin -= 36;
+                hist[bin] += cr_expf(-distsq / two_s2) * gval;
+            }
+        }
+    }
+    for (j = 0; j < 6; j++) {   /* :157-172 */
+        float old[36];
+        for (i = 0; i < 36; i++) old[i] = hist[i];
+        hist[0] = ((old[35] + old[0]) + old[1]) * ONE_3;
+        for (i = 1; i < 35; i++) hist[i] = ((old[i - 1] + old[i]) + old[i + 1]) * ONE_3;
+        hist[35] = ((old[34] + old[35]) + hist[0]) * ONE_3;
+    }
+    /* :187-236 tree reduction for the maximum */
+    for (i = 0; i < 32; i++) {
+        if (i + 32 < 36) {
+            if (hist[i] > hist[i + 32]) { hist2[i] = hist[i]; pos[i] = i; }
+            else { hist2[i] = hist[i + 32]; pos[i] = i + 32; }
+        } else { hist2[i] = hist[i]; pos[i] = i; }
+    }
+    for (int step = 16; step >= 1; step >>= 1)
+        for (i = 0; i < step; i++)
+            if (hist2[i + step] > hist2[i]) { hist2[i] = hist2[i + step]; pos[i] = pos[i + step]; }
+    int argmax = pos[0];
+    float maxval = hist2[0];
+    int prev = (argmax == 0 ? 35 : argmax - 1), next = (argmax == 35 ? 0 : argmax + 1);
+    float hist_prev = hist[prev], hist_next = hist[next];
+    float interp = 0.5f * (hist_prev - hist_next) / ((hist_prev - 2.0f * maxval) + hist_next);
+    float angle = ((argmax + 0.5f) + interp) * ONE_18;
+    if (angle < 0.0f) angle += 2.0f;
+    else if (angle > 2.0f) angle -= 2.0f;
+    {
+        float k0 = k[2] * octsize, k1 = k[1] * octsize, k2 = k[3] * octsize;
+        k[0] = k0; k[1] = k1; k[2] = k2; k[3] = (angle - 1.0f) * M_PI_F;
+    }
+    for (i = 0; i < 36; i++) {   /* :286-311 */
+        if (i == argmax) continue;
+        int pv = (i == 0 ? 35 : i - 1), nx = (i == 35 ? 0 : i + 1);
+        float hp = hist[pv], hc = hist[i], hn = hist[nx];
+        if (hc > hp && hc > hn && hc >= 0.8f * maxval) {
+            float itp = 0.5f * (hp - hn) / ((hp - 2.0f * hc) + hn);
+            float a = ((i + 0.5f) + itp) * ONE_18;
+            if (a < 0.0f) a += 2.0f;
+            else if (a > 2.0f) a -= 2.0f;
+            extra_angles[n_extra++] = (a - 1.0f) * M_PI_F;
+        }
+    }
+    return n_extra;
+}
+
+/* variant: 0 = orientation_cpu.cl, 1 = orientation_gpu.cl */
+API int siftref_orientation_v(float *keypoints, const float *grad, const float *ori, int *counter, int octsize,
+                              float OriSigma, int nb_keypoints, int keypoints_start, int keypoints_end, int grad_width,
+                              int grad_height, int variant) {
     int n = keypoints_end - keypoints_start;
     if (n <= 0) return *counter;
     float *extras = (float *)malloc((size_t)n * 36 * sizeof(float));
@@ -538,8 +621,9 @@ API int siftref_orientation(float *keypoints, const float *grad, const float *or
     for (int gid0 = keypoints_start; gid0 < keypoints_end; gid0++) {
         float *k = keypoints + 4 * (long)gid0;
         if (!(k[1] >= 0.0f)) continue;
-        n_extras[gid0 - keypoints_start] = orient_one(k, grad, ori, octsize, OriSigma, grad_width, grad_height,
-                                                      extras + 36 * (long)(gid0 - keypoints_start));
+        n_extras[gid0 - keypoints_start] =
+            (variant ? orient_one_gpu : orient_one)(k, grad, ori, octsize, OriSigma, grad_width, grad_height,
+                                                    extras + 36 * (long)(gid0 - keypoints_start));
     }
     for (int i = 0; i < n; i++) {
         const float *k = keypoints + 4 * (long)(keypoints_start + i);
@@ -555,6 +639,12 @@ API int siftref_orientation(float *keypoints, const float *grad, const float *or
     free(extras);
     free(n_extras);
     return *counter;
+}
+API int siftref_orientation(float *keypoints, const float *grad, const float *ori, int *counter, int octsize,
+                            float OriSigma, int nb_keypoints, int keypoints_start, int keypoints_end, int grad_width,
+                            int grad_height) {
+    return siftref_orientation_v(keypoints, grad, ori, counter, octsize, OriSigma, nb_keypoints, keypoints_start,
+                                 keypoints_end, grad_width, grad_height, 0);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -635,22 +725,106 @@ static void describe_one(const float *k, uint8_t *out, const float *grad, const 
     }
 }
 
-API void siftref_descriptor(const float *keypoints, uint8_t *descriptors, const float *grad, const float *orim,
-                            int octsize, int keypoints_start, int keypoints_end, int grad_width, int grad_height) {
+/* keypoints_gpu2.cl:68-284  the GPU variant of descriptor (SURVEY App. A.8 "GPU-variant differences"): fixed   */
+/* [-64, 64)^2 window, every trilinear term is accumulated as (uint)(100000 * term) with integer atomics (so the   */
+/* order of the samples does not matter; uint32 arithmetic wraps), histogram = (float)sum * 0.00001f, sums of      */
+/* squares by the 128 -> 2 tree of :214-241, and the final value is cast to uchar BEFORE MIN(255, .) (wraps >= 256) */
+static void describe_one_gpu(const float *k, uint8_t *out, const float *grad, const float *orim, int octsize,
+                             int grad_width, int grad_height) {
+    int i, j;
+    uint32_t acc[128];
+    float histogram[128], hist2[128];
+    for (i = 0; i < 128; i++) acc[i] = 0;
+    float one_octsize = 1.0f / octsize;
+    float row = k[1] * one_octsize, col = k[0] * one_octsize, angle = k[3];
+    int irow = (int)(row + 0.5f), icol = (int)(col + 0.5f);
+    float sine = cr_sinf(angle), cosine = cr_cosf(angle);
+    float spacing = k[2] * one_octsize * 3.0f;
+    float drow = row - irow, dcol = col - icol;
+    for (i = -64; i < 64; i++) {
+        for (j = -64; j < 64; j++) {
+            float rx, cx;
+            { float a = cosine * i, b = sine * j; rx = ((a - b) - drow) / spacing + 1.5f; }
+            { float a = sine * i, b = cosine * j; cx = ((a + b) - dcol) / spacing + 1.5f; }
+            if (!(rx > -1.0f && rx < 4.0f && cx > -1.0f && cx < 4.0f && (irow + i) >= 0 && (irow + i) < grad_height &&
+                  (icol + j) >= 0 && (icol + j) < grad_width))
+                continue;
+            float er = rx - 1.5f, ec = cx - 1.5f;
+            float e1 = er * er, e2 = ec * ec;
+            float mag = grad[(icol + j) + (long)(irow + i) * grad_width] * cr_expf(-0.125f * (e1 + e2));
+            float ori = orim[(icol + j) + (long)(irow + i) * grad_width] - angle;
+            while (ori > 2.0f * M_PI_F) ori -= 2.0f * M_PI_F;
+            while (ori < 0.0f) ori += 2.0f * M_PI_F;
+            float oval = (4.0f * ori) * M_1_PI_F;
+            int ri = (int)((rx >= 0.0f) ? rx : rx - 1.0f), ci = (int)((cx >= 0.0f) ? cx : cx - 1.0f),
+                oi = (int)((oval >= 0.0f) ? oval : oval - 1.0f);
+            float rfrac = rx - ri, cfrac = cx - ci, ofrac = oval - oi;
+            if (!(ri >= -1 && ri < 4 && oi >= 0 && oi <= 8 && rfrac >= 0.0f && rfrac <= 1.0f)) continue;
+            for (int r = 0; r < 2; r++) {
+                int rindex = ri + r;
+                if (!(rindex >= 0 && rindex < 4)) continue;
+                float rweight = mag * ((r == 0) ? 1.0f - rfrac : rfrac);
+                for (int c = 0; c < 2; c++) {
+                    int cindex = ci + c;
+                    if (!(cindex >= 0 && cindex < 4)) continue;
+                    float cweight = rweight * ((c == 0) ? 1.0f - cfrac : cfrac);
+                    for (int orr = 0; orr < 2; orr++) {
+                        int oindex = oi + orr;
+                        if (oindex >= 8) oindex = 0;
+                        float t = cweight * ((orr == 0) ? 1.0f - ofrac : ofrac);
+                        float scaled = 100000.0f * t;                       /* :190 */
+                        acc[(rindex * 4 + cindex) * 8 + oindex] += (scaled != scaled) ? 0u : (uint32_t)scaled;
+                    }
+                }
+            }
+        }
+    }
+    for (i = 0; i < 128; i++) histogram[i] = (float)acc[i] * 0.00001f;    /* :205-209 */
+    for (int pass = 0; pass < 2; pass++) {
+        for (i = 0; i < 128; i++) hist2[i] = histogram[i] * histogram[i];
+        for (int half = 64; half >= 2; half >>= 1)
+            for (i = 0; i < half; i++) hist2[i] += hist2[i + half];
+        float norm = cr_rsqrtf(hist2[1] + hist2[0]);
+        for (i = 0; i < 128; i++) histogram[i] *= norm;
+        if (pass == 1) break;
+        int changed = 0;
+        for (i = 0; i < 128; i++)
+            if (histogram[i] > 0.2f) { histogram[i] = 0.2f; changed = 1; }
+        if (!changed) break;
+    }
+    for (i = 0; i < 128; i++) {
+        float v = 512.0f * histogram[i];
+        int intval = (v != v) ? 0 : (int)v;
+        int wrapped = intval & 0xff;                                        /* (unsigned char) cast, :281 */
+        out[i] = (uint8_t)MIN(255, wrapped);
+    }
+}
+
+/* variant: 0 = keypoints_cpu.cl, 1 = keypoints_gpu2.cl */
+API void siftref_descriptor_v(const float *keypoints, uint8_t *descriptors, const float *grad, const float *orim,
+                              int octsize, int keypoints_start, int keypoints_end, int grad_width, int grad_height,
+                              int variant) {
 #pragma omp parallel for schedule(dynamic, 8)
     for (int gid0 = keypoints_start; gid0 < keypoints_end; gid0++) {
         const float *k = keypoints + 4 * (long)gid0;
         if (!(k[1] >= 0.0f)) continue;
-        describe_one(k, descriptors + 128 * (long)gid0, grad, orim, octsize, grad_width, grad_height);
+        (variant ? describe_one_gpu : describe_one)(k, descriptors + 128 * (long)gid0, grad, orim, octsize, grad_width,
+                                                    grad_height);
     }
+}
+API void siftref_descriptor(const float *keypoints, uint8_t *descriptors, const float *grad, const float *orim,
+                            int octsize, int keypoints_start, int keypoints_end, int grad_width, int grad_height) {
+    siftref_descriptor_v(keypoints, descriptors, grad, orim, octsize, keypoints_start, keypoints_end, grad_width,
+                         grad_height, 0);
 }
 
 /* ------------------------------------------------------------------------------------------ */
 /* plan.py:432-567 keypoints() + :596-756 _one_octave : the whole path                          */
 /* stage_counts (optional, may be NULL): int[octaves][3 scales][3] = {extrema, after interp, after orientation} */
-API int siftref_keypoints(const float *image, int height, int width, double init_sigma, int octave_limit,
-                          int pix_per_kp, siftref_kp *out, int out_cap, int *n_per_octave, float *minmax,
-                          int *stage_counts) {
+/* variant: 0 = the *_cpu.cl kernels (devicetype "CPU"), 1 = orientation_gpu.cl + keypoints_gpu2.cl ("GPU")       */
+API int siftref_keypoints_v(const float *image, int height, int width, double init_sigma, int octave_limit,
+                            int pix_per_kp, siftref_kp *out, int out_cap, int *n_per_octave, float *minmax,
+                            int *stage_counts, int variant) {
     const int Scales = 3, BorderDist = 5;
     const float PeakThresh = (float)(255.0 * 0.04 / 3.0), EdgeThresh = 0.06f, EdgeThresh1 = 0.08f, OriSigma = 1.5f;
     long N = (long)height * width;
@@ -712,9 +886,9 @@ API int siftref_keypoints(const float *image, int height, int width, double init
             cnt = newcnt;
             siftref_gradient(G[s], tmp, ori, w, h);
             if (newcnt && newcnt > last_start) {
-                siftref_orientation(Kp, tmp, ori, &cnt, octsize, OriSigma, kpsize, last_start, newcnt, w, h);
+                siftref_orientation_v(Kp, tmp, ori, &cnt, octsize, OriSigma, kpsize, last_start, newcnt, w, h, variant);
                 if (cnt > kpsize) cnt = kpsize;
-                siftref_descriptor(Kp, desc, tmp, ori, octsize, last_start, cnt, w, h);
+                siftref_descriptor_v(Kp, desc, tmp, ori, octsize, last_start, cnt, w, h, variant);
             }
             if (stage_counts) {
                 int *sc = stage_counts + (octave * 3 + (s - 1)) * 3;
@@ -745,6 +919,12 @@ API int siftref_keypoints(const float *image, int height, int width, double init
     for (int i = 0; i < 6; i++) free(G[i]);
     free(tmp); free(ori); free(DoGs); free(Kp); free(desc);
     return total;
+}
+API int siftref_keypoints(const float *image, int height, int width, double init_sigma, int octave_limit,
+                          int pix_per_kp, siftref_kp *out, int out_cap, int *n_per_octave, float *minmax,
+                          int *stage_counts) {
+    return siftref_keypoints_v(image, height, width, init_sigma, octave_limit, pix_per_kp, out, out_cap, n_per_octave,
+                               minmax, stage_counts, 0);
 }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -201,25 +201,28 @@ def compact(kp, start, end):
     return kp, n
 
 
-def orientation(kp, grad, ori, start, end, octsize=1, orisigma=1.5, counter=None):
+VARIANTS = {"cpu": 0, "gpu": 1, 0: 0, 1: 1}  # which reference kernels: *_cpu.cl, or orientation_gpu.cl + keypoints_gpu2.cl
+
+
+def orientation(kp, grad, ori, start, end, octsize=1, orisigma=1.5, counter=None, variant="cpu"):
     kp = _f32(kp).copy()
     grad, ori = _f32(grad), _f32(ori)
     cnt = ctypes.c_int(end if counter is None else counter)
-    lib().siftref_orientation(_fp(kp), _fp(grad), _fp(ori), ctypes.byref(cnt), octsize, ctypes.c_float(orisigma),
-                              kp.shape[0], start, end, grad.shape[1], grad.shape[0])
+    lib().siftref_orientation_v(_fp(kp), _fp(grad), _fp(ori), ctypes.byref(cnt), octsize, ctypes.c_float(orisigma),
+                                kp.shape[0], start, end, grad.shape[1], grad.shape[0], VARIANTS[variant])
     return kp, cnt.value
 
 
-def descriptor(kp, grad, ori, start, end, octsize=1):
+def descriptor(kp, grad, ori, start, end, octsize=1, variant="cpu"):
     kp = _f32(kp)
     grad, ori = _f32(grad), _f32(ori)
     desc = np.zeros((kp.shape[0], 128), np.uint8)
-    lib().siftref_descriptor(_fp(kp), desc.ctypes.data_as(_c_u8_p), _fp(grad), _fp(ori), octsize, start, end,
-                             grad.shape[1], grad.shape[0])
+    lib().siftref_descriptor_v(_fp(kp), desc.ctypes.data_as(_c_u8_p), _fp(grad), _fp(ori), octsize, start, end,
+                               grad.shape[1], grad.shape[0], VARIANTS[variant])
     return desc
 
 
-def keypoints(img, init_sigma=1.6, octave_max=0, pix_per_kp=10, return_all=False):
+def keypoints(img, init_sigma=1.6, octave_max=0, pix_per_kp=10, return_all=False, variant="cpu"):
     """Whole path (plan.py:432-567) on a 2-D float32 image.  Returns recarray[dtype_kp] (and details)."""
     img = _f32(img)
     h, w = img.shape
@@ -229,9 +232,9 @@ def keypoints(img, init_sigma=1.6, octave_max=0, pix_per_kp=10, return_all=False
     n_per_oct = np.zeros(noct, np.int32)
     stage = np.zeros((noct, 3, 3), np.int32)
     mm = np.zeros(2, np.float32)
-    n = lib().siftref_keypoints(_fp(img), h, w, ctypes.c_double(init_sigma), int(octave_max), int(pix_per_kp),
-                                out.ctypes.data_as(ctypes.c_void_p), cap, n_per_oct.ctypes.data_as(_c_int_p), _fp(mm),
-                                stage.ctypes.data_as(_c_int_p))
+    n = lib().siftref_keypoints_v(_fp(img), h, w, ctypes.c_double(init_sigma), int(octave_max), int(pix_per_kp),
+                                  out.ctypes.data_as(ctypes.c_void_p), cap, n_per_oct.ctypes.data_as(_c_int_p), _fp(mm),
+                                  stage.ctypes.data_as(_c_int_p), VARIANTS[variant])
     res = out[:min(n, cap)].view(np.recarray)
     if return_all:
         return res, {"n_per_octave": n_per_oct, "stage_counts": stage, "minmax": mm}

@@ -47,6 +47,7 @@ SIGNATURES = {
     "siftb_plan_device_bytes": (c_u64, [c_void_p]),
     "siftb_plan_stream": (c_void_p, [c_void_p]),
     "siftb_plan_set_profile": (c_int, [c_void_p, c_int]),
+    "siftb_plan_set_variant": (c_int, [c_void_p, c_int]),
     "siftb_plan_launches": (c_u64, [c_void_p]),
     "siftb_plan_device": (c_int, [c_void_p]),
     "siftb_plan_wait_stream": (c_int, [c_void_p, c_void_p]),
@@ -70,6 +71,9 @@ SIGNATURES = {
     "siftb_orientation": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
                                   c_int_p]),
     "siftb_descriptor": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "siftb_orientation_v": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
+                                    c_int_p, c_int]),
+    "siftb_descriptor_v": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int]),
     "siftb_matcher_create": (c_int, [c_int, ctypes.POINTER(c_void_p)]),
     "siftb_matcher_destroy": (c_int, [c_void_p]),
     "siftb_matcher_set_profile": (c_int, [c_void_p, c_int]),

@@ -118,8 +118,8 @@ class LinearAlign(object):
         self.ROI = ROI
         self.ctx = context
         self.device = device
-        self.sift = SiftPlan(template=self.ref, context=context, profile=self.profile, device=device,
-                             max_workgroup_size=max_workgroup_size, init_sigma=init_sigma)
+        self.sift = SiftPlan(template=self.ref, devicetype=devicetype, context=context, profile=self.profile,
+                             device=device, max_workgroup_size=max_workgroup_size, init_sigma=init_sigma)
         self.match = MatchPlan(context=context, profile=self.profile, device=device,
                                max_workgroup_size=max_workgroup_size)
         self._set_reference(self.sift.keypoints(self.ref))

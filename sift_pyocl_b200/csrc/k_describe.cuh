@@ -25,7 +25,7 @@
 
 #define DESC_WARPS 4  // warps per CTA -> 16 keypoints per CTA
 
-#define DESC_MAXROWS 100  // window rows per keypoint handled by the interval table (iradius <= 49; default sigmas need 97)
+#define DESC_MAXROWS 104  // window rows per keypoint handled by the interval table (default sigmas: 97, GPU variant 101)
 
 // Per-octet table of the non-empty window rows: only the j-interval that can be valid.  One packed word per row:
 // byte 0 = window row i (-iradius..iradius; |.| <= 49 for tabled windows), byte 1 = first candidate j, byte 2 = last
@@ -89,7 +89,12 @@ __device__ __forceinline__ float cr_expf_neg_inrange(float xf, const double *__r
 // whist: the warp's DESC_HROWS x 32 floats of histogram storage.
 // ANY_ANGLE: the keypoint angle may lie anywhere (stage hook fed by a caller); in the pipeline k_orient guarantees
 // [-pi, pi] up to one rounding.  s_exp: the CTA's shared copy of c_exp_t32.
-template <bool ANY_ANGLE>
+// GPUVAR: the semantics of keypoints_gpu2.cl instead of keypoints_cpu.cl (devicetype "GPU" in the
+// reference): the window is [-64, 64)^2 whatever the keypoint's size, every trilinear term is accumulated as
+// (uint)(100000 * term) by integer adds (order-free, wraps modulo 2^32), histogram = (float)sum * 0.00001f, the sums
+// of squares come from the reference's 128 -> 2 halving tree, and the result is cast to uchar BEFORE MIN(255, .).
+// The sample evaluation, the candidate table, the parity-class staging and the commit loop are shared.
+template <bool ANY_ANGLE, bool GPUVAR>
 __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescRows &rows, DescStage &stage,
                                                 const double *__restrict__ s_exp, bool act, const float4 k,
                                                 const float2 *__restrict__ go, int pitch, int grad_width, int grad_height, int octsize,
@@ -108,7 +113,12 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
     int iradius = (int)(((1.414f * spacing) * 2.5f) + 0.5f);
     const float drow = row - (float)irow, dcol = col - (float)icol;
     if (!(act && iradius >= 0)) iradius = -1;
-    const int nrows = 2 * iradius + 1;  // 0 rows for an inactive octet
+    // window rows / columns that are scanned: [-iradius, iradius] (keypoints_cpu.cl:63-64); the GPU variant scans
+    // [-64, 64) -- only the rows and columns within iradius + 2 can hold a sample that passes the (rx, cx) test
+    // (the test admits |.| < 2.5 * sqrt(2) * spacing < iradius + 1), so the table covers those
+    const int wlo = GPUVAR ? -min(iradius + 2, 64) : -iradius;
+    const int whi = GPUVAR ? min(iradius + 2, 63) : iradius;
+    const int nrows = iradius < 0 ? 0 : whi - wlo + 1;  // 0 rows for an inactive octet
     const bool tabled = nrows <= DESC_MAXROWS;
     // ---- row table: the reference scans j = -R..R of every row and keeps the samples with rx, cx in (-1, 4)
     // whose pixel is inside the image (keypoints_cpu.cl:66-67); those form one j-interval per row.  A
@@ -117,8 +127,8 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
     // the reference's exact fp32 test.  Rows with an empty interval are dropped.
     int my_passes = 0, nrc = 0;  // passes (8 samples each) of this octet, number of table rows
     // untabled (enormous window, custom init_sigma): every row of the square that lies inside the image, full width
-    const int u_r0 = max(0, iradius - irow), u_r1 = min(nrows - 1, iradius + grad_height - 1 - irow);
-    const int u_jlo = max(-iradius, -icol), u_jhi = min(iradius, grad_width - 1 - icol);
+    const int u_r0 = max(0, -wlo - irow), u_r1 = min(nrows - 1, -wlo + grad_height - 1 - irow);
+    const int u_jlo = max(wlo, -icol), u_jhi = min(whi, grad_width - 1 - icol);
     if (tabled) {
         // rx in (-1, 4)  <=>  |cs*i - sn*j - drow| < L = 2.5*spacing in exact arithmetic; the fp32 evaluation of
         // the reference (five roundings on magnitudes <= R + L) moves the left side by less than E.  Candidates
@@ -128,8 +138,8 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
         const bool use_sn = fabs(sn) > 1e-9, use_cs = fabs(cs) > 1e-9;
         const double isn = 1.0 / sn, ics = 1.0 / cs;
         for (int r = l8; r < nrows; r += 8) {
-            const int i = r - iradius;
-            double lo = -(double)iradius, hi = (double)iradius;
+            const int i = r + wlo;
+            double lo = (double)wlo, hi = (double)whi;
             if (irow + i < 0 || irow + i >= grad_height) hi = lo - 1.0;  // row outside the image
             const double A = cs * (double)i - (double)drow;
             if (use_sn) {
@@ -144,12 +154,15 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
                 hi = fmin(hi, fmax(a, b) + 1e-6);
             }
             int jlo = (int)ceil(lo), jhi = (int)floor(hi);
-            jlo = max(jlo, max(-iradius, -icol));
-            jhi = min(jhi, min(iradius, grad_width - 1 - icol));
+            jlo = max(jlo, max(wlo, -icol));
+            jhi = min(jhi, min(whi, grad_width - 1 - icol));
             if (jhi < jlo) { jlo = 1; jhi = 0; }  // empty (the real-valued bounds may not fit the table's type)
             rows.w[r] = desc_pack_row(i, jlo, jhi);
         }
-        __syncwarp();
+    }
+    // (the warp-level barriers sit outside the per-octet branches: the four octets of a warp may take different ones)
+    __syncwarp();
+    if (tabled) {
         if (l8 == 0) {  // drop the empty rows (in place: the write index never overtakes the read index)
             int n = 0, acc = 0;
             for (int r = 0; r < nrows; r++) {
@@ -163,11 +176,11 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
             nrc = n;
             my_passes = (acc + 7) >> 3;  // the candidates of all rows are packed back to back, 8 per pass
         }
-        __syncwarp();
     } else if (u_r1 >= u_r0 && u_jhi >= u_jlo) {
         nrc = u_r1 - u_r0 + 1;
         my_passes = (nrc * (u_jhi - u_jlo + 1) + 7) >> 3;
     }
+    __syncwarp();
     nrc = __shfl_sync(0xffffffffu, nrc, obase);
     my_passes = __shfl_sync(0xffffffffu, my_passes, obase);
     // warp-uniform trip count: the longest of the 4 octets
@@ -191,7 +204,7 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
                     jcur = (int)(signed char)(w >> 8) + over;
                     jend = (int)(signed char)(w >> 16);
                 } else {
-                    n_i = u_r0 + rcur - iradius;
+                    n_i = u_r0 + rcur + wlo;
                     jcur = u_jlo + over;
                     jend = u_jhi;
                 }
@@ -263,15 +276,18 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
         {
             // (rweight * c-factor) * o-factor, in the reference's multiplication order (keypoints_cpu.cl:93-104)
             const float cw_ee = rw_e * cf_e, cw_eo = rw_e * cf_o, cw_oe = rw_o * cf_e, cw_oo = rw_o * cf_o;
+            // GPU variant: the term enters the histogram as (uint)(100000 * term) (keypoints_gpu2.cl:189-191); its
+            // bit pattern travels through the stage in place of the float
+            auto term = [](float t) { return GPUVAR ? __uint_as_float((unsigned)(100000.0f * t)) : t; };
             float4 *dst = reinterpret_cast<float4 *>(&stage.e[l8][0]);
-            dst[0] = make_float4(__uint_as_float(ra_e + ca_e + oa_e), cw_ee * ow_e,
-                                 __uint_as_float(ra_e + ca_e + oa_o), cw_ee * ow_o);
-            dst[1] = make_float4(__uint_as_float(ra_e + ca_o + oa_e), cw_eo * ow_e,
-                                 __uint_as_float(ra_e + ca_o + oa_o), cw_eo * ow_o);
-            dst[2] = make_float4(__uint_as_float(ra_o + ca_e + oa_e), cw_oe * ow_e,
-                                 __uint_as_float(ra_o + ca_e + oa_o), cw_oe * ow_o);
-            dst[3] = make_float4(__uint_as_float(ra_o + ca_o + oa_e), cw_oo * ow_e,
-                                 __uint_as_float(ra_o + ca_o + oa_o), cw_oo * ow_o);
+            dst[0] = make_float4(__uint_as_float(ra_e + ca_e + oa_e), term(cw_ee * ow_e),
+                                 __uint_as_float(ra_e + ca_e + oa_o), term(cw_ee * ow_o));
+            dst[1] = make_float4(__uint_as_float(ra_e + ca_o + oa_e), term(cw_eo * ow_e),
+                                 __uint_as_float(ra_e + ca_o + oa_o), term(cw_eo * ow_o));
+            dst[2] = make_float4(__uint_as_float(ra_o + ca_e + oa_e), term(cw_oe * ow_e),
+                                 __uint_as_float(ra_o + ca_e + oa_o), term(cw_oe * ow_o));
+            dst[3] = make_float4(__uint_as_float(ra_o + ca_o + oa_e), term(cw_oo * ow_e),
+                                 __uint_as_float(ra_o + ca_o + oa_o), term(cw_oo * ow_o));
         }
         __syncwarp();
         // commit the 8 samples of the pass in sample order: lane (pr, pc, po) adds the one term of its class
@@ -281,10 +297,17 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
 #pragma unroll
         for (int sidx = 0; sidx < 8; sidx++) {
             const unsigned sa = __float_as_uint(term[sidx].x);
-            float v;
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(sa));
-            v += term[sidx].y;
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(sa), "f"(v) : "memory");
+            if (GPUVAR) {
+                unsigned u;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u) : "r"(sa));
+                u += __float_as_uint(term[sidx].y);
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa), "r"(u) : "memory");
+            } else {
+                float v;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(sa));
+                v += term[sidx].y;
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(sa), "f"(v) : "memory");
+            }
         }
         __syncwarp();
     }
@@ -294,40 +317,81 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
     const int fr0 = (l8 >> 1) + 1, fc0 = 2 * (l8 & 1) + 1;
     float v[16];
 #pragma unroll
-    for (int q = 0; q < 16; q++) v[q] = hist[desc_bin(fr0, fc0 + (q >> 3), q & 7)];
-    __syncwarp();
-#pragma unroll
-    for (int q = 0; q < 16; q++) hist[desc_bin(fr0, fc0 + (q >> 3), q & 7)] = v[q] * v[q];
-    __syncwarp();
-    // the sums of squares are sequential over i = 0..127 in the reference: one lane adds them in that order
-    auto ordered_sum = [&]() {
-        float acc = 0.0f;
-        for (int rc = 0; rc < 16; rc++) {
-            const float *cell = hist + desc_bin((rc >> 2) + 1, (rc & 3) + 1, 0);
-#pragma unroll
-            for (int o = 0; o < 8; o++) acc += cell[32 * (o >> 1) + (o & 1)];
-        }
-        return acc;
-    };
-    float norm = 0.0f;
-    if (l8 == 0) norm = ordered_sum();
-    norm = cr_rsqrtf(__shfl_sync(0xffffffffu, norm, obase));
-    bool changed = false;
-    __syncwarp();
-#pragma unroll
     for (int q = 0; q < 16; q++) {
-        v[q] *= norm;
-        if (v[q] > 0.2f) { v[q] = 0.2f; changed = true; }
-        hist[desc_bin(fr0, fc0 + (q >> 3), q & 7)] = v[q] * v[q];
+        const float raw = hist[desc_bin(fr0, fc0 + (q >> 3), q & 7)];
+        v[q] = GPUVAR ? (float)__float_as_uint(raw) * 0.00001f : raw;  // keypoints_gpu2.cl:205-209
     }
-    changed = (__ballot_sync(0xffffffffu, changed) & omask) != 0;
     __syncwarp();
-    float norm2 = 0.0f;
-    if (l8 == 0 && changed) norm2 = ordered_sum();
-    norm2 = cr_rsqrtf(__shfl_sync(0xffffffffu, norm2, obase));
-    if (changed) {
+    bool changed = false;
+    if (GPUVAR) {
+        // keypoints_gpu2.cl:211-272: hist2[l] = h[l]^2, then hist2[l] += hist2[l + half] for half = 64 .. 2 and
+        // rsqrt(hist2[1] + hist2[0]).  The octet's bank group serves as the linear scratch array hist2[128].
+        auto scratch = [&](int i) -> float & { return hist[32 * (i >> 3) + (i & 7)]; };
+        auto tree_norm = [&]() {
 #pragma unroll
-        for (int q = 0; q < 16; q++) v[q] *= norm2;
+            for (int q = 0; q < 16; q++) scratch(16 * l8 + q) = v[q] * v[q];
+            __syncwarp();
+#pragma unroll
+            for (int per = 8; per >= 1; per >>= 1) {  // halves 64, 32, 16, 8: `per` sums per lane
+                const int half = 8 * per;
+#pragma unroll
+                for (int t = 0; t < per; t++) scratch(l8 * per + t) += scratch(l8 * per + t + half);
+                __syncwarp();
+            }
+            if (l8 < 4) scratch(l8) += scratch(l8 + 4);
+            __syncwarp();
+            if (l8 < 2) scratch(l8) += scratch(l8 + 2);
+            __syncwarp();
+            const float nrm = cr_rsqrtf(scratch(1) + scratch(0));
+            __syncwarp();
+            return nrm;
+        };
+        const float norm = tree_norm();
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            v[q] *= norm;
+            if (v[q] > 0.2f) { v[q] = 0.2f; changed = true; }
+        }
+        changed = (__ballot_sync(0xffffffffu, changed) & omask) != 0;
+        // all 32 lanes run the second tree (it contains warp-level barriers); only octets that clamped use it
+        const float norm2 = tree_norm();
+        if (changed) {
+#pragma unroll
+            for (int q = 0; q < 16; q++) v[q] *= norm2;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 16; q++) hist[desc_bin(fr0, fc0 + (q >> 3), q & 7)] = v[q] * v[q];
+        __syncwarp();
+        // the sums of squares are sequential over i = 0..127 in the reference: one lane adds them in that order
+        auto ordered_sum = [&]() {
+            float acc = 0.0f;
+            for (int rc = 0; rc < 16; rc++) {
+                const float *cell = hist + desc_bin((rc >> 2) + 1, (rc & 3) + 1, 0);
+#pragma unroll
+                for (int o = 0; o < 8; o++) acc += cell[32 * (o >> 1) + (o & 1)];
+            }
+            return acc;
+        };
+        float norm = 0.0f;
+        if (l8 == 0) norm = ordered_sum();
+        norm = cr_rsqrtf(__shfl_sync(0xffffffffu, norm, obase));
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            v[q] *= norm;
+            if (v[q] > 0.2f) { v[q] = 0.2f; changed = true; }
+            hist[desc_bin(fr0, fc0 + (q >> 3), q & 7)] = v[q] * v[q];
+        }
+        changed = (__ballot_sync(0xffffffffu, changed) & omask) != 0;
+        __syncwarp();
+        float norm2 = 0.0f;
+        if (l8 == 0 && changed) norm2 = ordered_sum();
+        norm2 = cr_rsqrtf(__shfl_sync(0xffffffffu, norm2, obase));
+        if (changed) {
+#pragma unroll
+            for (int q = 0; q < 16; q++) v[q] *= norm2;
+        }
     }
     if (act) {
         uint32_t w4[4];
@@ -338,7 +402,8 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
             for (int q = 0; q < 4; q++) {
                 const float x = 512.0f * v[q4 * 4 + q];
                 const int intval = (x != x) ? 0 : (int)x;
-                pk |= (uint32_t)min(255, intval) << (8 * q);  // intval >= 0 here (hist >= 0)
+                // keypoints_cpu.cl:157-159 clamps; keypoints_gpu2.cl:281 casts to uchar first (values >= 256 wrap)
+                pk |= (uint32_t)(GPUVAR ? (intval & 0xff) : min(255, intval)) << (8 * q);  // intval >= 0 (hist >= 0)
             }
             w4[q4] = pk;
         }
@@ -387,6 +452,7 @@ __global__ void __launch_bounds__(256) k_size_order(const float4 *__restrict__ k
 // Pipeline form: octets fetch keypoints of ALL octaves from a work queue; rows with NaN are dropped
 // (plan.py:546-550); the survivors of octave o go to out[oct_offset[o] + ...], i.e. the output is grouped by
 // octave in octave order like the reference's concatenation (plan.py:555-565).
+template <bool GPUVAR>
 __global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe(OctTable T, const float4 *__restrict__ kp,
                                                                const int *__restrict__ kp_tag,
                                                                const int *__restrict__ n_order_p, int cap,
@@ -428,12 +494,13 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe(OctTable T, con
         if (slot >= out_cap) act = false;
         KpRecord *o = out + (act ? slot : 0);
         if (act && l8 == 0) { o->x = k.x; o->y = k.y; o->scale = k.z; o->angle = k.w; }
-        describe_octets<false>(hist, s_rows[threadIdx.x >> 3], s_stage[threadIdx.x >> 3], s_exp, act, k, T.go[oct][sc - 1],
+        describe_octets<false, GPUVAR>(hist, s_rows[threadIdx.x >> 3], s_stage[threadIdx.x >> 3], s_exp, act, k, T.go[oct][sc - 1],
                         T.pitch[oct], T.w[oct], T.h[oct], T.octsize[oct], o->desc);
     }
 }
 
 // Stage-hook form: desc[i] for every input row (no filtering), single gradient plane
+template <bool GPUVAR>
 __global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe_rows(const float2 *__restrict__ go, int pitch, int w,
                                                                     int h, const float4 *__restrict__ kp, int n,
                                                                     int octsize, uint8_t *__restrict__ desc) {
@@ -454,7 +521,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe_rows(const floa
             k = kp[gid0];
             act = k.y >= 0.0f;
         }
-        describe_octets<true>(hist, s_rows[threadIdx.x >> 3], s_stage[threadIdx.x >> 3], s_exp, act, k, go, pitch, w, h, octsize,
+        describe_octets<true, GPUVAR>(hist, s_rows[threadIdx.x >> 3], s_stage[threadIdx.x >> 3], s_exp, act, k, go, pitch, w, h, octsize,
                         desc + 128L * (act ? gid0 : 0));
     }
 }

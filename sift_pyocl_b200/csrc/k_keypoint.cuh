@@ -173,6 +173,13 @@ __device__ __forceinline__ int desc_size_class(float sigma_oct, int octsize) {
 // One warp per keypoint (grid-stride).  kp rows in: (peak, row, col, sigma); out: (x, y, sigma*oct, angle).
 // Extra-orientation keypoints are appended at n_base + atomicAdd(n_extra).
 // stage: [octave][3 scales][3] counters (may be null); oct_valid[o]: records octave o will emit (non-NaN rows).
+// GPUVAR: the semantics of orientation_gpu.cl instead of orientation_cpu.cl (devicetype "GPU" in the
+// reference): bin = (int)(18 (ori + pi) / pi) with a +-36 wrap, at most 128 columns per window row, smoothing
+// multiplies by (1.0f / 3.0f), the maximum comes from the reference's tree reduction (its tie rules), the angle is
+// (argmax + 0.5 + interp) / 18 wrapped into [0, 2] then (a - 1) pi, extra peaks are not range-filtered.  The samples
+// are accumulated in the same row-major order in both variants (lane 0 of the reference's work-group adds a row's
+// values in column order, orientation_gpu.cl:141-145).
+template <bool GPUVAR>
 __global__ void __launch_bounds__(256) k_orient(OctTable T, float4 *__restrict__ kp, int *__restrict__ kp_tag,
                                                  const int *__restrict__ n_base_p, int *__restrict__ n_extra, int cap,
                                                  float OriSigma, int *__restrict__ stage, int *__restrict__ oct_valid,
@@ -195,7 +202,9 @@ __global__ void __launch_bounds__(256) k_orient(OctTable T, float4 *__restrict__
         const float sigma = OriSigma * k.w;
         const int radius = (int)((double)sigma * 3.0);  // :71
         const int rmin = max(0, row - radius), cmin = max(0, col - radius);
-        const int rmax = min(row + radius, Gh - 2), cmax = min(col + radius, Gw - 2);
+        const int rmax = min(row + radius, Gh - 2);
+        int cmax = min(col + radius, Gw - 2);
+        if (GPUVAR) cmax = min(cmax, cmin + 127);  // c = cmin + lid0, lid0 < WORKGROUP_SIZE (orientation_gpu.cl:126-129)
         const float two_s2 = (2.0f * sigma) * sigma;
         const double inv_two_s2 = div_prepare(two_s2), inv_two_pi = div_prepare(2.0f * SIFTB_M_PI_F);
         const float rad2 = ((float)(radius * radius)) + 0.5f;
@@ -269,10 +278,18 @@ __global__ void __launch_bounds__(256) k_orient(OctTable T, float4 *__restrict__
                 dif = ((float)c - k.z);
                 distsq += dif * dif;
                 if (gval > 0.0f && distsq < rad2) {
-                    int b = (int)div_by(36.0f * ((angle + SIFTB_M_PI_F) + 0.001f), inv_two_pi);
-                    if (b >= 0 && b <= 36) {
-                        bin = min(b, 35);
+                    if (GPUVAR) {  // orientation_gpu.cl:135-139
+                        int b = (int)((18.0f * (angle + SIFTB_M_PI_F)) * SIFTB_M_1_PI_F);
+                        if (b < 0) b += 36;
+                        if (b > 35) b -= 36;
+                        bin = max(0, min(b, 35));  // (the clamp only guards shared memory against a NaN plane)
                         w = cr_expf_neg(div_by(-distsq, inv_two_s2)) * gval;
+                    } else {
+                        int b = (int)div_by(36.0f * ((angle + SIFTB_M_PI_F) + 0.001f), inv_two_pi);
+                        if (b >= 0 && b <= 36) {
+                            bin = min(b, 35);
+                            w = cr_expf_neg(div_by(-distsq, inv_two_s2)) * gval;
+                        }
                     }
                 }
             }
@@ -302,11 +319,14 @@ __global__ void __launch_bounds__(256) k_orient(OctTable T, float4 *__restrict__
             if (lane < 3) { a1 = hist[31 + lane], b1 = hist[32 + lane], c1 = hist[33 + lane]; }
             float o34 = hist[34], o35 = hist[35];
             __syncwarp();
-            const float n0 = third((a0 + b0) + c0);
+            // GPU variant: "* ONE_3" in fp32 (orientation_gpu.cl:160-170); same data flow (old neighbours, bin 35 sees
+            // the new bin 0: what lock-step execution makes of the reference's racy update)
+            const float ONE_3 = 1.0f / 3.0f;
+            const float n0 = GPUVAR ? ((a0 + b0) + c0) * ONE_3 : third((a0 + b0) + c0);
             hist[lane] = n0;
-            if (lane < 3) hist[32 + lane] = third((a1 + b1) + c1);
+            if (lane < 3) hist[32 + lane] = GPUVAR ? ((a1 + b1) + c1) * ONE_3 : third((a1 + b1) + c1);
             __syncwarp();
-            if (lane == 0) hist[35] = third((o34 + o35) + n0);
+            if (lane == 0) hist[35] = GPUVAR ? ((o34 + o35) + n0) * ONE_3 : third((o34 + o35) + n0);
             __syncwarp();
         }
         // orientation_cpu.cl:110-121 -- argmax = first bin holding the largest value > 0 (0 if there is none;
@@ -315,19 +335,41 @@ __global__ void __launch_bounds__(256) k_orient(OctTable T, float4 *__restrict__
         const float m0 = h0 > 0.0f ? h0 : 0.0f, m1 = h1 > 0.0f ? h1 : 0.0f;
         float maxval = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(m0, m1))));
         int argmax = 0;
-        if (maxval > 0.0f) {
+        if (GPUVAR) {
+            // orientation_gpu.cl:187-236: bins 32..35 are folded into lanes 0..3 (a tie keeps the HIGHER bin), then
+            // the halving steps 16, 8, 4, 2, 1 (a tie keeps the LOWER lane)
+            float v = h0;
+            int pbin = lane;
+            if (lane < 4 && !(h0 > h1)) { v = h1; pbin = lane + 32; }
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1) {
+                const float uv = __shfl_down_sync(0xffffffffu, v, step);
+                const int up = __shfl_down_sync(0xffffffffu, pbin, step);
+                if (lane < step && uv > v) { v = uv; pbin = up; }
+            }
+            maxval = __shfl_sync(0xffffffffu, v, 0);
+            argmax = __shfl_sync(0xffffffffu, pbin, 0);
+        } else if (maxval > 0.0f) {
             const unsigned e0 = __ballot_sync(0xffffffffu, h0 == maxval);
             const unsigned e1 = __ballot_sync(0xffffffffu, lane < 4 && h1 == maxval);
             argmax = e0 ? __ffs(e0) - 1 : 31 + __ffs(e1);
         }
+        const float ONE_18 = 1.0f / 18.0f;
+        auto gpu_angle = [&](int i, float itp) {  // orientation_gpu.cl:255-264, 303-306
+            float a = (((float)i + 0.5f) + itp) * ONE_18;
+            if (a < 0.0f) a += 2.0f;
+            else if (a > 2.0f) a -= 2.0f;
+            return (a - 1.0f) * SIFTB_M_PI_F;
+        };
         float angle;
         float4 o;
         {
             const int prev = (argmax == 0 ? 35 : argmax - 1), next = (argmax == 35 ? 0 : argmax + 1);
             float hist_prev = hist[prev], hist_next = hist[next];
-            if (maxval < 0.0f) { hist_prev = -hist_prev; maxval = -maxval; hist_next = -hist_next; }
+            if (!GPUVAR && maxval < 0.0f) { hist_prev = -hist_prev; maxval = -maxval; hist_next = -hist_next; }
             const float interp = 0.5f * (hist_prev - hist_next) / ((hist_prev - 2.0f * maxval) + hist_next);
-            angle = (2.0f * SIFTB_M_PI_F) * (((float)argmax + 0.5f) + interp) / 36.0f - SIFTB_M_PI_F;
+            angle = GPUVAR ? gpu_angle(argmax, interp)
+                           : (2.0f * SIFTB_M_PI_F) * (((float)argmax + 0.5f) + interp) / 36.0f - SIFTB_M_PI_F;
             o.x = k.z * (float)octsize;
             o.y = k.y * (float)octsize;
             o.z = k.w * (float)octsize;
@@ -339,8 +381,12 @@ __global__ void __launch_bounds__(256) k_orient(OctTable T, float4 *__restrict__
             const int pv = (i == 0 ? 35 : i - 1), nx = (i == 35 ? 0 : i + 1);
             float hp = hist[pv], hc = hist[i], hn = hist[nx];
             if (!(hc > hp && hc > hn && hc >= 0.8f * maxval && i != argmax)) return false;
-            if (hc < 0.0f) { hp = -hp; hc = -hc; hn = -hn; }
+            if (!GPUVAR && hc < 0.0f) { hp = -hp; hc = -hc; hn = -hn; }
             const float itp = 0.5f * (hp - hn) / ((hp - 2.0f * hc) + hn);
+            if (GPUVAR) {  // every such peak becomes a keypoint (no range filter, orientation_gpu.cl:286-311)
+                a2 = gpu_angle(i, itp);
+                return true;
+            }
             // orientation_cpu.cl:166: "/36.0" promotes the tail of the expression to double
             a2 = (float)((double)((2.0f * SIFTB_M_PI_F) * (((float)i + 0.5f) + itp)) / 36.0 - (double)SIFTB_M_PI_F);
             return a2 >= -SIFTB_M_PI_F && a2 <= SIFTB_M_PI_F;

@@ -146,6 +146,7 @@ struct siftb_plan {
     TbMaps tmap_raws[NSLOT], tmap_img;  // first blur: from the host-staging buffers / the converted fp32 plane
     bool tmap_raw_ok = false, tmap_img_ok = false;
     int force_generic = 0;
+    int variant = 0;  // 0: orientation_cpu.cl + keypoints_cpu.cl semantics, 1: orientation_gpu.cl + keypoints_gpu2.cl
     std::vector<Event> events_s[NSLOT];  // profiling events of the image in each slot
     int cur = 0;                         // slot being submitted (ProfScope)
     std::vector<const char *> ev_names;
@@ -368,6 +369,16 @@ extern "C" int siftb_plan_octave_shape(const siftb_plan *p, int o, int *w, int *
 extern "C" uint64_t siftb_plan_device_bytes(const siftb_plan *p) { return p ? p->dev_bytes : 0; }
 extern "C" void *siftb_plan_stream(const siftb_plan *p) { return p ? (void *)p->stream : nullptr; }
 extern "C" uint64_t siftb_plan_launches(const siftb_plan *p) { return p ? p->launches : 0; }
+// plan.py:667-725 picks orientation_gpu.cl / keypoints_gpu2.cl for devicetype "GPU" and the *_cpu.cl kernels for "CPU";
+// the two families give slightly different numbers.  0 = CPU-variant semantics (default,
+// the parity target), 1 = GPU-variant semantics.
+extern "C" int siftb_plan_set_variant(siftb_plan *p, int variant) {
+    if (!p || variant < 0 || variant > 1) return fail(SIFTB_EINVAL, "variant must be 0 (cpu) or 1 (gpu)");
+    std::lock_guard<std::mutex> lk(p->mtx);
+    if (p->n_flight) return fail(SIFTB_EINVAL, "images are in flight");
+    p->variant = variant;
+    return 0;
+}
 extern "C" int siftb_plan_set_profile(siftb_plan *p, int enable) {
     if (!p) return fail(SIFTB_EINVAL, "plan is null");
     p->profile = enable != 0;
@@ -586,8 +597,12 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
     // once per image: orientation assignment and descriptors over the keypoints of all octaves
     {
         ProfScope ps(p, "orientation_assignment");
-        k_orient<<<148 * 4, 256, 0, st>>>(p->table, p->kp, p->kp_tag, n_kp, n_extra, p->kp_cap, kOriSigma,
-                                          p->c_stage(slot, 0), oct_valid, size_hist);
+        if (p->variant)
+            k_orient<true><<<148 * 4, 256, 0, st>>>(p->table, p->kp, p->kp_tag, n_kp, n_extra, p->kp_cap, kOriSigma,
+                                                    p->c_stage(slot, 0), oct_valid, size_hist);
+        else
+            k_orient<false><<<148 * 4, 256, 0, st>>>(p->table, p->kp, p->kp_tag, n_kp, n_extra, p->kp_cap, kOriSigma,
+                                                     p->c_stage(slot, 0), oct_valid, size_hist);
         CKL();
         p->launches += 1;
     }
@@ -596,9 +611,14 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
         k_octave_offsets<<<1, 1, 0, st>>>(oct_valid, p->n_oct, oct_offset, p->c_nout(slot), p->c_oct(slot, 0) + 3,
                                           size_hist, size_start, n_order);
         k_size_order<<<148, 256, 0, st>>>(p->kp, p->kp_tag, n_kp, n_extra, p->kp_cap, size_start, size_fill, p->kp_order);
-        k_describe<<<148 * 6, DESC_WARPS * 32, 0, st>>>(p->table, p->kp, p->kp_tag, n_order, p->kp_cap,
-                                                        p->outs[slot], p->out_cap, oct_offset, oct_fill, q_head,
-                                                        p->kp_order);
+        if (p->variant)
+            k_describe<true><<<148 * 6, DESC_WARPS * 32, 0, st>>>(p->table, p->kp, p->kp_tag, n_order, p->kp_cap,
+                                                                  p->outs[slot], p->out_cap, oct_offset, oct_fill,
+                                                                  q_head, p->kp_order);
+        else
+            k_describe<false><<<148 * 6, DESC_WARPS * 32, 0, st>>>(p->table, p->kp, p->kp_tag, n_order, p->kp_cap,
+                                                                   p->outs[slot], p->out_cap, oct_offset, oct_fill,
+                                                                   q_head, p->kp_order);
         CKL();
         p->launches += 3;
     }
@@ -951,8 +971,8 @@ extern "C" int siftb_interp(const float *dogs5, int height, int width, const flo
     return 0;
 }
 
-extern "C" int siftb_orientation(const float *kp4_in, int n, const float *grad, const float *ori, int height, int width,
-                                 int octsize, float *kp4_out, int cap, int *n_out) {
+extern "C" int siftb_orientation_v(const float *kp4_in, int n, const float *grad, const float *ori, int height,
+                                   int width, int octsize, float *kp4_out, int cap, int *n_out, int variant) {
     if (!kp4_in || !grad || !ori || !kp4_out || !n_out || n < 0 || cap < n) return fail(SIFTB_EINVAL, "bad argument");
     const long np = (long)height * width;
     DevBuf Gd, Od, GO, K, S, C;
@@ -971,8 +991,12 @@ extern "C" int siftb_orientation(const float *kp4_in, int n, const float *grad, 
     memset(&tb, 0, sizeof(tb));
     for (int i = 0; i < 3; i++) tb.go[0][i] = GO.as<float2>();
     tb.pitch[0] = width; tb.w[0] = width; tb.h[0] = height; tb.octsize[0] = octsize;
-    k_orient<<<148 * 4, 256>>>(tb, K.as<float4>(), S.as<int>(), C.as<int>(), C.as<int>() + 1, cap, kOriSigma, nullptr,
-                               nullptr, nullptr);
+    if (variant)
+        k_orient<true><<<148 * 4, 256>>>(tb, K.as<float4>(), S.as<int>(), C.as<int>(), C.as<int>() + 1, cap, kOriSigma,
+                                         nullptr, nullptr, nullptr);
+    else
+        k_orient<false><<<148 * 4, 256>>>(tb, K.as<float4>(), S.as<int>(), C.as<int>(), C.as<int>() + 1, cap, kOriSigma,
+                                          nullptr, nullptr, nullptr);
     CKL();
     CK(cudaMemcpy(cnt, C.p, 8, cudaMemcpyDeviceToHost));
     int total = n + cnt[1];
@@ -982,8 +1006,13 @@ extern "C" int siftb_orientation(const float *kp4_in, int n, const float *grad, 
     return 0;
 }
 
-extern "C" int siftb_descriptor(const float *kp4, int n, const float *grad, const float *ori, int height, int width,
-                                int octsize, uint8_t *desc) {
+extern "C" int siftb_orientation(const float *kp4_in, int n, const float *grad, const float *ori, int height, int width,
+                                 int octsize, float *kp4_out, int cap, int *n_out) {
+    return siftb_orientation_v(kp4_in, n, grad, ori, height, width, octsize, kp4_out, cap, n_out, 0);
+}
+
+extern "C" int siftb_descriptor_v(const float *kp4, int n, const float *grad, const float *ori, int height, int width,
+                                  int octsize, uint8_t *desc, int variant) {
     if (!kp4 || !grad || !ori || !desc || n < 0) return fail(SIFTB_EINVAL, "bad argument");
     const long np = (long)height * width;
     DevBuf Gd, Od, GO, K, Dd;
@@ -995,11 +1024,21 @@ extern "C" int siftb_descriptor(const float *kp4, int n, const float *grad, cons
     CK(cudaMemcpy(K.p, kp4, (size_t)n * 16, cudaMemcpyHostToDevice));
     CK(cudaMemset(Dd.p, 0, (size_t)n * 128));
     if (n > 0) {
-        k_describe_rows<<<(n + DESC_WARPS - 1) / DESC_WARPS, DESC_WARPS * 32>>>(GO.as<float2>(), width, width, height, K.as<float4>(), n,
-                                               octsize, Dd.as<uint8_t>());
+        const int blocks = (n + 4 * DESC_WARPS - 1) / (4 * DESC_WARPS);  // 4 keypoints per warp
+        if (variant)
+            k_describe_rows<true><<<blocks, DESC_WARPS * 32>>>(GO.as<float2>(), width, width, height, K.as<float4>(), n,
+                                                              octsize, Dd.as<uint8_t>());
+        else
+            k_describe_rows<false><<<blocks, DESC_WARPS * 32>>>(GO.as<float2>(), width, width, height, K.as<float4>(), n,
+                                                               octsize, Dd.as<uint8_t>());
         CKL();
         CK(cudaMemcpy(desc, Dd.p, (size_t)n * 128, cudaMemcpyDeviceToHost));
     }
     return 0;
 }
 
+
+extern "C" int siftb_descriptor(const float *kp4, int n, const float *grad, const float *ori, int height, int width,
+                                int octsize, uint8_t *desc) {
+    return siftb_descriptor_v(kp4, n, grad, ori, height, width, octsize, desc, 0);
+}

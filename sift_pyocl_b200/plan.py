@@ -77,7 +77,12 @@ class SiftPlan(object):
         self.profile = bool(profile)
         self.events = []
         self._sem = threading.Semaphore()
-        self.devicetype = "GPU"
+        # The reference runs orientation_gpu.cl + keypoints_gpu2.cl on devicetype "GPU" and the *_cpu.cl kernels on
+        # "CPU" (plan.py:667-725); the two families give slightly different angles / descriptors.
+        # Everything runs on the B200 here; ``devicetype`` selects whose NUMBERS are reproduced: "CPU" (the
+        # reference's default, and the parity target of this package) or "GPU".
+        self.devicetype = str(devicetype).upper() if devicetype is not None else "CPU"
+        self.variant = "gpu" if self.devicetype == "GPU" else "cpu"
         self.max_workgroup_size = max_workgroup_size
         self.ctx = context
         self.queue = None
@@ -103,6 +108,8 @@ class SiftPlan(object):
                                          int(self.PIX_PER_KP), self._init_sigma, octave_limit, ctypes.byref(handle)),
                    RuntimeError)
         self._plan = handle
+        if self.variant == "gpu":
+            _lib.check(lib.siftb_plan_set_variant(handle, 1))
         self.kpsize = lib.siftb_plan_kpsize(handle)
         self._capacity = lib.siftb_plan_capacity(handle)
         self.octave_max = lib.siftb_plan_octaves(handle)

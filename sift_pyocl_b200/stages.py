@@ -82,20 +82,24 @@ def interp(dogs, kp, init_sigma=1.6):
     return out[:n.value]
 
 
-def orientation(kp, grad, ori, octsize=1, cap=None):
+VARIANTS = {"cpu": 0, "gpu": 1}  # orientation_cpu.cl / keypoints_cpu.cl, or orientation_gpu.cl / keypoints_gpu2.cl
+
+
+def orientation(kp, grad, ori, octsize=1, cap=None, variant="cpu"):
     kp, grad, ori = _f32(kp), _f32(grad), _f32(ori)
     n = kp.shape[0]
     cap = max(4 * n, 16) if cap is None else cap
     out = numpy.zeros((cap, 4), numpy.float32)
     m = ctypes.c_int()
-    _lib.check(_lib.load().siftb_orientation(_lib.ptr(kp), n, _lib.ptr(grad), _lib.ptr(ori), grad.shape[0],
-                                             grad.shape[1], octsize, _lib.ptr(out), cap, ctypes.byref(m)))
+    _lib.check(_lib.load().siftb_orientation_v(_lib.ptr(kp), n, _lib.ptr(grad), _lib.ptr(ori), grad.shape[0],
+                                               grad.shape[1], octsize, _lib.ptr(out), cap, ctypes.byref(m),
+                                               VARIANTS[variant]))
     return out[:min(m.value, cap)], m.value
 
 
-def descriptor(kp, grad, ori, octsize=1):
+def descriptor(kp, grad, ori, octsize=1, variant="cpu"):
     kp, grad, ori = _f32(kp), _f32(grad), _f32(ori)
     desc = numpy.zeros((kp.shape[0], 128), numpy.uint8)
-    _lib.check(_lib.load().siftb_descriptor(_lib.ptr(kp), kp.shape[0], _lib.ptr(grad), _lib.ptr(ori), grad.shape[0],
-                                            grad.shape[1], octsize, _lib.ptr(desc)))
+    _lib.check(_lib.load().siftb_descriptor_v(_lib.ptr(kp), kp.shape[0], _lib.ptr(grad), _lib.ptr(ori), grad.shape[0],
+                                              grad.shape[1], octsize, _lib.ptr(desc), VARIANTS[variant]))
     return desc

@@ -304,3 +304,61 @@ def test_profile_events_match_and_align(sift, capsys):
     la.log_profile()
     out = capsys.readouterr().out
     assert "transform" in out and "matching" in out and "descriptors" in out
+
+
+# ---- devicetype="GPU": the numbers of orientation_gpu.cl + keypoints_gpu2.cl ---------------
+def _stage_inputs(oracle, shape=(240, 320), seed=9, octsize=1):
+    g0 = oracle.blur(oracle.normalize(ms(0, seed, shape)), oracle.gaussian_taps(1.5199))
+    G, D = oracle.pyramid_octave(g0)
+    out = []
+    for s in (1, 2, 3):
+        ko, no = oracle.local_maxmin(D, s, octsize=octsize)
+        kc, nc = oracle.compact(oracle.interp_keypoint(D, ko, 0, no), 0, no)
+        grad, ori = oracle.gradient(G[s])
+        out.append((kc, nc, grad, ori))
+    return out
+
+
+@pytest.mark.parametrize("octsize", [1, 4])
+def test_gpu_variant_stages(oracle, octsize):
+    from sift_pyocl_b200 import stages
+    differs = 0
+    for kc, nc, grad, ori in _stage_inputs(oracle, octsize=octsize):
+        want, nw = oracle.orientation(kc, grad, ori, 0, nc, octsize=octsize, variant="gpu")
+        got, ng = stages.orientation(kc[:nc], grad, ori, octsize, variant="gpu")
+        assert ng == nw and nw >= nc
+        assert np.array_equal(got[:nc], want[:nc])
+        assert np.array_equal(sort_rows(got[nc:]), sort_rows(want[nc:nw]))
+        cpu, _ = oracle.orientation(kc, grad, ori, 0, nc, octsize=octsize)
+        differs += int((cpu[:nc, 3] != want[:nc, 3]).sum())          # the two families really differ ...
+        assert np.median(abs(cpu[:nc, 3] - want[:nc, 3])) < 2e-2      # ... mostly by the bin offset and the wrap
+        dw = oracle.descriptor(want, grad, ori, 0, nw, octsize=octsize, variant="gpu")[:nw]
+        dg = stages.descriptor(want[:nw], grad, ori, octsize, variant="gpu")
+        assert dw.any() and np.array_equal(dg, dw)
+        dc = oracle.descriptor(want, grad, ori, 0, nw, octsize=octsize)[:nw]
+        assert (dc != dw).any() and np.median(np.abs(dc.astype(int) - dw.astype(int))) <= 1   # 1e-5 quantisation
+    assert differs > 0
+
+
+def test_gpu_variant_whole_path(sift, oracle):
+    img = ms(512, 1234)
+    plan = sift.SiftPlan(template=img, devicetype="GPU")
+    assert plan.variant == "gpu"
+    kp = plan.keypoints(img)
+    want, info = oracle.keypoints(img, return_all=True, variant="gpu")
+    assert np.array_equal(plan.last_counts, info["n_per_octave"]) and same_records(kp, want)
+    cpu = sift.SiftPlan(template=img).keypoints(img)       # default devicetype: the *_cpu.cl numbers
+    assert same_records(cpu, oracle.keypoints(img)) and not same_records(cpu, kp)
+    # keypoints with enormous windows (custom init_sigma): the fixed [-64, 64) window of keypoints_gpu2.cl truncates them
+    big = sift.SiftPlan(template=img, devicetype="GPU", init_sigma=3.5)
+    assert same_records(big.keypoints(img), oracle.keypoints(img, init_sigma=3.5, variant="gpu"))
+
+
+@pytest.mark.parametrize("init_sigma", [2.5, 3.5])
+def test_large_init_sigma_windows_beyond_the_row_table(sift, oracle, init_sigma):
+    """Descriptor windows with more rows than the per-keypoint interval table holds (iradius >= 52) take the
+    full-scan path; warps mix tabled, full-scan and idle octets (a divergent warp barrier there hung round 1's
+    kernel for init_sigma >= 2.5)."""
+    img = ms(384, 91)
+    plan, kp, ref = compare_whole(sift, oracle, img, init_sigma=init_sigma)
+    assert kp.size > 50 and kp.scale.max() > 3 * init_sigma

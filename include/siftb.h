@@ -174,6 +174,9 @@ SIFTB_API int siftb_matcher_create(int device, siftb_matcher **out);          /*
 SIFTB_API int siftb_matcher_destroy(siftb_matcher *m);
 SIFTB_API int siftb_matcher_set_profile(siftb_matcher *m, int enable);
 SIFTB_API void *siftb_matcher_stream(const siftb_matcher *m);
+/* distance: 0 = L1 on the uint8 descriptors, the reference's metric (matching_gpu.cl:79-99; default);
+ * 1 = squared L2 (an extra: BASELINE config 4 words the workload as "L2"), ratio test on the squared distances */
+SIFTB_API int siftb_matcher_set_metric(siftb_matcher *m, int metric);
 /* which = 0 / 1: first / second list of match(); records: n dtype_kp records in host (on_device = 0) or device
  * memory of the matcher's device (on_device = 1, e.g. siftb_plan_result_dev) -- match.py:216-239 */
 SIFTB_API int siftb_matcher_set_list(siftb_matcher *m, int which, const siftb_kp *records, int n, int on_device);

@@ -929,8 +929,10 @@ API int siftref_keypoints(const float *image, int height, int width, double init
 
 /* ------------------------------------------------------------------------------------------ */
 /* matching_cpu.cl:57-109  matching (L1 on uint8, ratio test); output pairs in kp1 order        */
-API int siftref_match(const siftref_kp *keypoints1, const siftref_kp *keypoints2, int *matchings, int max_nb_match,
-                      float ratio_th, int size1, int size2) {
+/* metric: 0 = the reference's L1 distance; 1 = squared L2 distance (not in the reference: the "L2" wording of     */
+/* BASELINE config 4), same scan, same tie rules, same ratio threshold applied to the squared distances          */
+API int siftref_match_metric(const siftref_kp *keypoints1, const siftref_kp *keypoints2, int *matchings,
+                             int max_nb_match, float ratio_th, int size1, int size2, int metric) {
     int *best = (int *)malloc((size_t)MAX(size1, 1) * sizeof(int));
 #pragma omp parallel for schedule(static)
     for (int gid0 = 0; gid0 < size1; gid0++) {
@@ -940,9 +942,16 @@ API int siftref_match(const siftref_kp *keypoints1, const siftref_kp *keypoints2
         for (int i = 0; i < size2; i++) {
             const uint8_t *desc2 = keypoints2[i].desc;
             int dist = 0;
-            for (int j = 0; j < 128; j++) {
-                int a = desc1[j], b = desc2[j];
-                dist += (a > b) ? (a - b) : (-a + b);
+            if (metric) {
+                for (int j = 0; j < 128; j++) {
+                    int d = (int)desc1[j] - (int)desc2[j];
+                    dist += d * d;
+                }
+            } else {
+                for (int j = 0; j < 128; j++) {
+                    int a = desc1[j], b = desc2[j];
+                    dist += (a > b) ? (a - b) : (-a + b);
+                }
             }
             if (dist < dist1) { dist2 = dist1; dist1 = (float)dist; current_min = i; }
             else if (dist < dist2) { dist2 = (float)dist; }
@@ -957,6 +966,10 @@ API int siftref_match(const siftref_kp *keypoints1, const siftref_kp *keypoints2
     }
     free(best);
     return counter;
+}
+API int siftref_match(const siftref_kp *keypoints1, const siftref_kp *keypoints2, int *matchings, int max_nb_match,
+                      float ratio_th, int size1, int size2) {
+    return siftref_match_metric(keypoints1, keypoints2, matchings, max_nb_match, ratio_th, size1, size2, 0);
 }
 
 /* ------------------------------------------------------------------------------------------ */

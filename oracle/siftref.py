@@ -241,13 +241,14 @@ def keypoints(img, init_sigma=1.6, octave_max=0, pix_per_kp=10, return_all=False
     return res
 
 
-def match(kp1, kp2, ratio_th=np.float32(0.73 * 0.73), cap=None):
+def match(kp1, kp2, ratio_th=np.float32(0.73 * 0.73), cap=None, metric="l1"):
     kp1 = np.ascontiguousarray(kp1, dtype=dtype_kp)
     kp2 = np.ascontiguousarray(kp2, dtype=dtype_kp)
     cap = max(16384, min(kp1.size, kp2.size)) if cap is None else cap  # match.py:241-243
     out = np.zeros((cap, 2), np.int32)
-    n = lib().siftref_match(kp1.ctypes.data_as(ctypes.c_void_p), kp2.ctypes.data_as(ctypes.c_void_p),
-                            out.ctypes.data_as(_c_int_p), cap, ctypes.c_float(ratio_th), kp1.size, kp2.size)
+    n = lib().siftref_match_metric(kp1.ctypes.data_as(ctypes.c_void_p), kp2.ctypes.data_as(ctypes.c_void_p),
+                                   out.ctypes.data_as(_c_int_p), cap, ctypes.c_float(ratio_th), kp1.size, kp2.size,
+                                   {"l1": 0, "l2": 1}[metric])
     return out[:min(n, cap)]
 
 

@@ -78,6 +78,7 @@ SIGNATURES = {
     "siftb_matcher_destroy": (c_int, [c_void_p]),
     "siftb_matcher_set_profile": (c_int, [c_void_p, c_int]),
     "siftb_matcher_stream": (c_void_p, [c_void_p]),
+    "siftb_matcher_set_metric": (c_int, [c_void_p, c_int]),
     "siftb_matcher_set_list": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int]),
     "siftb_matcher_run": (c_int, [c_void_p, c_float, c_int, c_void_p, c_int_p]),
     "siftb_matcher_pairs": (c_int, [c_void_p, c_void_p]),

@@ -76,7 +76,11 @@ struct MatchPartial {
 // memory feeds eight SADs instead of four: the LDS.128 broadcasts (8 per row and warp) otherwise keep the
 // load/store data path as busy as the SADs keep the ALU pipe.  QPT = 2 needs ~64 more registers, so it is used for
 // long first lists only (enough warps either way).
-template <bool SEGMENTED, int QPT>
+// L2: squared Euclidean distance instead of the reference's L1 (an extra, BASELINE config 4 words the workload as
+// "brute-force L2"; the reference's metric and this package's default is L1): per 4 bytes one VABSDIFF4 (packed
+// |a-b|) and one IDP4A (sum of their squares), i.e. two integer-pipe instructions where L1 needs one.  Same scan,
+// same tie rules, the ratio test is applied to the squared distances with the same threshold (0.73^2).
+template <bool SEGMENTED, int QPT, bool L2>
 __global__ void __launch_bounds__(MATCH_THREADS) k_match_l1(const uint32_t *__restrict__ d1, int n1,
                                                              const uint32_t *__restrict__ d2_all, int n2_all,
                                                              int seg_rows, float ratio_th, int2 *__restrict__ pairs,
@@ -117,10 +121,18 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_match_l1(const uint32_t *__re
             const uint4 v = row[i];
 #pragma unroll
             for (int u = 0; u < QPT; u++) {
-                d[u] = sad4_acc(q[u][4 * i], v.x, d[u]);
-                d[u] = sad4_acc(q[u][4 * i + 1], v.y, d[u]);
-                d[u] = sad4_acc(q[u][4 * i + 2], v.z, d[u]);
-                d[u] = sad4_acc(q[u][4 * i + 3], v.w, d[u]);
+                if (L2) {
+                    unsigned t;
+                    t = __vabsdiffu4(q[u][4 * i], v.x);     d[u] = __dp4a(t, t, d[u]);
+                    t = __vabsdiffu4(q[u][4 * i + 1], v.y); d[u] = __dp4a(t, t, d[u]);
+                    t = __vabsdiffu4(q[u][4 * i + 2], v.z); d[u] = __dp4a(t, t, d[u]);
+                    t = __vabsdiffu4(q[u][4 * i + 3], v.w); d[u] = __dp4a(t, t, d[u]);
+                } else {
+                    d[u] = sad4_acc(q[u][4 * i], v.x, d[u]);
+                    d[u] = sad4_acc(q[u][4 * i + 1], v.y, d[u]);
+                    d[u] = sad4_acc(q[u][4 * i + 2], v.z, d[u]);
+                    d[u] = sad4_acc(q[u][4 * i + 3], v.w, d[u]);
+                }
             }
         }
     };

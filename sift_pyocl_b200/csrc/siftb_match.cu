@@ -31,6 +31,7 @@ struct siftb_matcher {
     GrowBuf recs[2], desc[2], pairs, gather, partial;
     int n[2] = {0, 0};
     int pairs_cap = 0, n_match = 0;  // n_match: pairs stored by the last run (<= pairs_cap)
+    int metric = 0;                  // 0: L1 (the reference's), 1: squared L2 (extra)
     int *d_cnt = nullptr, *h_cnt = nullptr;
     bool profile = false;
     std::vector<MatchEvent> events;
@@ -108,6 +109,12 @@ extern "C" int siftb_matcher_set_profile(siftb_matcher *m, int enable) {
     m->profile = enable != 0;
     return 0;
 }
+extern "C" int siftb_matcher_set_metric(siftb_matcher *m, int metric) {
+    if (!m || metric < 0 || metric > 1) return fail(SIFTB_EINVAL, "metric must be 0 (L1) or 1 (L2)");
+    std::lock_guard<std::mutex> lk(m->mtx);
+    m->metric = metric;
+    return 0;
+}
 extern "C" void *siftb_matcher_stream(const siftb_matcher *m) { return m ? (void *)m->stream : nullptr; }
 
 // match.py:220-239: (re)size the list buffer, copy the records in, and extract the dense descriptor rows
@@ -161,24 +168,23 @@ extern "C" int siftb_matcher_run(siftb_matcher *m, float ratio_th, int cap, int 
         int nseg = n2 / 16384;
         nseg = nseg < 1 ? 1 : (nseg > 8 ? 8 : nseg);
         const uint32_t *a1 = m->desc[0].as<uint32_t>(), *a2 = m->desc[1].as<uint32_t>();
+        const int seg_rows = nseg == 1 ? n2 : ((n2 + nseg - 1) / nseg + MATCH_TILE - 1) / MATCH_TILE * MATCH_TILE;
+        if (nseg > 1) CK(m->partial.reserve((size_t)n1 * nseg * sizeof(MatchPartial)));
+        int2 *out_pairs = m->pairs.as<int2>();
+        MatchPartial *part = m->partial.as<MatchPartial>();
+        const dim3 grid(qblocks, nseg);
+#define MATCH_LAUNCH(SEG, QPT, L2)                                                                              \
+    k_match_l1<SEG, QPT, L2><<<grid, MATCH_THREADS, 0, m->stream>>>(a1, n1, a2, n2, seg_rows, ratio_th, out_pairs, cap, \
+                                                                    m->d_cnt, part)
         if (nseg == 1) {
-            if (qpt == 2)
-                k_match_l1<false, 2><<<qblocks, MATCH_THREADS, 0, m->stream>>>(a1, n1, a2, n2, n2, ratio_th, m->pairs.as<int2>(),
-                                                                             cap, m->d_cnt, nullptr);
-            else
-                k_match_l1<false, 1><<<qblocks, MATCH_THREADS, 0, m->stream>>>(a1, n1, a2, n2, n2, ratio_th, m->pairs.as<int2>(),
-                                                                             cap, m->d_cnt, nullptr);
+            if (m->metric) { if (qpt == 2) MATCH_LAUNCH(false, 2, true); else MATCH_LAUNCH(false, 1, true); }
+            else           { if (qpt == 2) MATCH_LAUNCH(false, 2, false); else MATCH_LAUNCH(false, 1, false); }
             CKL();
         } else {
-            const int seg_rows = ((n2 + nseg - 1) / nseg + MATCH_TILE - 1) / MATCH_TILE * MATCH_TILE;
-            CK(m->partial.reserve((size_t)n1 * nseg * sizeof(MatchPartial)));
-            if (qpt == 2)
-                k_match_l1<true, 2><<<dim3(qblocks, nseg), MATCH_THREADS, 0, m->stream>>>(
-                    a1, n1, a2, n2, seg_rows, ratio_th, nullptr, cap, nullptr, m->partial.as<MatchPartial>());
-            else
-                k_match_l1<true, 1><<<dim3(qblocks, nseg), MATCH_THREADS, 0, m->stream>>>(
-                    a1, n1, a2, n2, seg_rows, ratio_th, nullptr, cap, nullptr, m->partial.as<MatchPartial>());
+            if (m->metric) { if (qpt == 2) MATCH_LAUNCH(true, 2, true); else MATCH_LAUNCH(true, 1, true); }
+            else           { if (qpt == 2) MATCH_LAUNCH(true, 2, false); else MATCH_LAUNCH(true, 1, false); }
             CKL();
+#undef MATCH_LAUNCH
             k_match_merge<<<(n1 + 255) / 256, 256, 0, m->stream>>>(m->partial.as<MatchPartial>(), n1, nseg, ratio_th,
                                                                  m->pairs.as<int2>(), cap, m->d_cnt);
             CKL();

@@ -93,8 +93,23 @@ class MatchPlan(object):
         self.queue = lib.siftb_matcher_stream(handle)
         if self.profile:
             lib.siftb_matcher_set_profile(handle, 1)
+        self._metric = "l1"
         if roi is not None:
             self.set_roi(roi)
+
+    @property
+    def metric(self):
+        """Distance between descriptors: "l1" (the reference's, matching_gpu.cl:79-99; default) or "l2" (squared
+        Euclidean distance with the ratio test on the squared values -- an extra, not the reference's arithmetic)."""
+        return self._metric
+
+    @metric.setter
+    def metric(self, name):
+        name = str(name).lower()
+        assert name in ("l1", "l2")
+        with self._sem:
+            _lib.check(_lib.load().siftb_matcher_set_metric(self._matcher, 1 if name == "l2" else 0))
+            self._metric = name
 
     def __del__(self):
         m, self._matcher = getattr(self, "_matcher", None), None

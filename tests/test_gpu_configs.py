@@ -362,3 +362,23 @@ def test_large_init_sigma_windows_beyond_the_row_table(sift, oracle, init_sigma)
     img = ms(384, 91)
     plan, kp, ref = compare_whole(sift, oracle, img, init_sigma=init_sigma)
     assert kp.size > 50 and kp.scale.max() > 3 * init_sigma
+
+
+def test_match_l2_metric_option(sift, oracle):
+    """The optional squared-L2 matcher (not the reference's metric) against its own oracle, short and long lists."""
+    k1, k2, _ = desc_sets(3000, 2500, seed=5)
+    mp = sift.MatchPlan()
+    l1 = mp.match(k1, k2, raw_results=True)
+    mp.metric = "l2"
+    got = mp.match(k1, k2, raw_results=True)
+    assert np.array_equal(sort_rows(got), sort_rows(oracle.match(k1, k2, metric="l2"))) and len(got) > 2000
+    k1, k2, _ = desc_sets(80000, 40000, seed=6)       # two queries per thread, segmented second list
+    got = mp.match(k1, k2, raw_results=True)
+    sample = np.arange(0, 80000, 37)
+    want = oracle.match(k1[sample], k2, metric="l2")
+    want[:, 0] = sample[want[:, 0]]
+    assert np.array_equal(sort_rows(got[np.isin(got[:, 0], sample)]), sort_rows(want)) and len(want) > 500
+    mp.metric = "l1"
+    assert np.array_equal(sort_rows(mp.match(k1[:3000], k2[:2500], raw_results=True)),
+                          sort_rows(oracle.match(k1[:3000], k2[:2500])))
+    assert len(l1) > 2000

@@ -91,6 +91,12 @@ def _worker(rank, world, port, q):
             ok = ok and same_records(host[start:start + counts[r]].view(np.recarray), solo[first[r]])
             start += counts[r]
         _lib.check(lib.siftb_comm_destroy(comm))
+        # (d) MatchPlan with the rows of list 1 sharded over the ranks, index pairs all-gathered over NCCL
+        mp = sift.MatchPlan(device=rank)
+        whole = mp.match(solo[0], solo[1], raw_results=True)
+        whole = whole[np.argsort(whole[:, 0], kind="stable")]
+        sharded = sdist.match_sharded(mp, solo[0], solo[1])
+        ok = ok and np.array_equal(sharded, whole) and len(whole) > 0
         q.put((rank, bool(ok), ""))
         dist.destroy_process_group()
     except Exception as exc:  # report instead of hanging the parent

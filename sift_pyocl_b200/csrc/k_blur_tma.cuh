@@ -153,13 +153,16 @@ k_blur_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUt
             phase ^= 1;
         }
         if (MODE == TB_NORM) {  // preprocess.cl:250 on the staged pixels
+            // (255 * (x - min)) / (max - min): the division by the image-wide constant is the exact double-reciprocal
+            // form of common.cuh (3 instructions instead of the ~12 of an IEEE fp32 division, same result)
             const float mn = ordered_to_float(a.norm_mm[0]);
             const float den = ordered_to_float(a.norm_mm[1]) - mn;
+            const double inv_den = div_prepare(den);
             float4 *t4 = reinterpret_cast<float4 *>(tile);
             for (int i = tid; i < nrows * BW / 4; i += TB_THREADS) {
                 float4 v = t4[i];
-                v.x = (255.0f * (v.x - mn)) / den; v.y = (255.0f * (v.y - mn)) / den;
-                v.z = (255.0f * (v.z - mn)) / den; v.w = (255.0f * (v.w - mn)) / den;
+                v.x = div_by(255.0f * (v.x - mn), inv_den); v.y = div_by(255.0f * (v.y - mn), inv_den);
+                v.z = div_by(255.0f * (v.z - mn), inv_den); v.w = div_by(255.0f * (v.w - mn), inv_den);
                 t4[i] = v;
             }
             __syncthreads();

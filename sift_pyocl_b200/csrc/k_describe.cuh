@@ -413,39 +413,55 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
     __syncwarp();
 }
 
-// prefix of the per-octave record counts -> first record slot of every octave, and the total
-__global__ void k_octave_offsets(const int *__restrict__ oct_valid, int n_oct, int *__restrict__ oct_offset,
-                                 int *__restrict__ n_out, int *__restrict__ n_out_oct /* stride 4 */,
-                                 const int *__restrict__ size_hist, int *__restrict__ size_start,
-                                 int *__restrict__ n_order) {
-    int acc = 0;
-    for (int o = 0; o < n_oct; o++) {
-        oct_offset[o] = acc;
-        acc += oct_valid[o];
-        n_out_oct[4 * o] = oct_valid[o];
-    }
-    *n_out = acc;
-    acc = 0;  // processing order: largest windows first
-    for (int b = DESC_CLASSES - 1; b >= 0; b--) {
-        size_start[b] = acc;
-        acc += size_hist[b];
-    }
-    *n_order = acc;  // keypoints k_orient accepted and stored (== entries k_size_order writes)
-}
-
-// order[] = keypoint indices sorted by descending descriptor-window size class (counting sort, unstable)
+// order[] = keypoint indices sorted by descending descriptor-window size class (counting sort, unstable), plus --
+// by block 0 -- the prefix of the per-octave record counts: first record slot of every octave, and the totals.
+// Every block derives the class offsets from the histogram k_orient filled (64 adds; cheaper than a launch of its
+// own); lanes of a warp that hold the same class share one atomicAdd.
 __global__ void __launch_bounds__(256) k_size_order(const float4 *__restrict__ kp, const int *__restrict__ kp_tag,
                                                      const int *__restrict__ n_base_p, const int *__restrict__ n_extra_p,
-                                                     int cap, const int *__restrict__ size_start,
-                                                     int *__restrict__ size_fill, int *__restrict__ order) {
+                                                     int cap, const int *__restrict__ size_hist,
+                                                     int *__restrict__ size_fill, int *__restrict__ order,
+                                                     int *__restrict__ n_order, const int *__restrict__ oct_valid,
+                                                     int n_oct, int *__restrict__ oct_offset, int *__restrict__ n_out,
+                                                     int *__restrict__ n_out_oct /* stride 4 */) {
+    __shared__ int s_start[DESC_CLASSES];
+    if (threadIdx.x == 0) {
+        int acc = 0;  // processing order: largest windows first
+        for (int b = DESC_CLASSES - 1; b >= 0; b--) {
+            s_start[b] = acc;
+            acc += size_hist[b];
+        }
+        if (blockIdx.x == 0) {
+            *n_order = acc;  // keypoints k_orient accepted and stored (== entries written below)
+            acc = 0;
+            for (int o = 0; o < n_oct; o++) {
+                oct_offset[o] = acc;
+                acc += oct_valid[o];
+                n_out_oct[4 * o] = oct_valid[o];
+            }
+            *n_out = acc;
+        }
+    }
+    __syncthreads();
     const int n = min(min(*n_base_p, cap) + *n_extra_p, cap);
     const int stride = gridDim.x * blockDim.x;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float4 k = kp[i];
-        if (!(k.y >= 0.0f)) continue;  // rows k_orient skipped (never counted in size_hist)
-        const int b = desc_size_class(k.z, 1 << (kp_tag[i] >> 8));
-        const int pos = size_start[b] + atomicAdd(&size_fill[b], 1);
-        if (pos < cap) order[pos] = i;
+    const int lane = threadIdx.x & 31;
+    for (int i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += stride) {  // warp-uniform trip count
+        const int i = i0 + lane;
+        int b = -1;
+        if (i < n) {
+            const float4 k = kp[i];
+            if (k.y >= 0.0f) b = desc_size_class(k.z, 1 << (kp_tag[i] >> 8));  // rows k_orient skipped are not ordered
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, b);
+        const int leader = __ffs(peers) - 1;
+        int pos = 0;
+        if (lane == leader && b >= 0) pos = atomicAdd(&size_fill[b], __popc(peers));
+        pos = __shfl_sync(0xffffffffu, pos, leader);
+        if (b >= 0) {
+            pos += s_start[b] + __popc(peers & lanemask_lt());
+            if (pos < cap) order[pos] = i;
+        }
     }
 }
 

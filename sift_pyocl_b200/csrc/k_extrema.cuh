@@ -84,16 +84,17 @@ __device__ __forceinline__ bool maxmin_rest(const DogStack &D, long pos, int sca
 // otherwise run for one or two lanes of a warp at a time).
 // cand rows: (val, row, col, scale).  n_cand = total candidates, stage[(s-1)*3] = per-scale count.
 #define EXT_QSIZE 512  // ring entries per warp: <= 31 left over + 32 lanes x 12 new survivors per row
-__global__ void __launch_bounds__(128) k_extrema(DogStack D, int border, float gate, float edthresh,
-                                                  float4 *__restrict__ cand, int cap, int *__restrict__ n_cand,
-                                                  int *__restrict__ stage /* [3][3] or null */, int scale_lo,
-                                                  int nscales) {
+// (bx, by): the block's position in the grid described above
+__device__ __forceinline__ void extrema_block(const DogStack &D, int border, float gate, float edthresh,
+                                              float4 *__restrict__ cand, int cap, int *__restrict__ n_cand,
+                                              int *__restrict__ stage /* [3][3] or null */, int scale_lo, int nscales,
+                                              int bx, int by) {
     __shared__ unsigned short s_q[4][EXT_QSIZE];  // (row offset << 9) | (scale index << 7) | (lane << 2) | column in group
     __shared__ float4 s_hits[4][64];
     const int lane = threadIdx.x & 31;
-    const int x4 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+    const int x4 = 4 * (bx * blockDim.x + threadIdx.x);
     const int col0 = x4 - 4 * lane;                // first column of the warp
-    const int row0 = border + blockIdx.y * EXT_ROWS;
+    const int row0 = border + by * EXT_ROWS;
     unsigned short *q = s_q[threadIdx.x >> 5];
     const bool active = x4 < D.pitch;              // the 128-bit loads stay inside the (padded) row
     unsigned colmask = 0;                          // columns of my group inside [border, w - border)
@@ -199,6 +200,38 @@ __global__ void __launch_bounds__(128) k_extrema(DogStack D, int border, float g
         if (cnt_s2) atomicAdd(&stage[3], cnt_s2);
         if (cnt_s3) atomicAdd(&stage[6], cnt_s3);
     }
+}
+
+__global__ void __launch_bounds__(128) k_extrema(DogStack D, int border, float gate, float edthresh,
+                                                  float4 *__restrict__ cand, int cap, int *__restrict__ n_cand,
+                                                  int *__restrict__ stage, int scale_lo, int nscales) {
+    extrema_block(D, border, gate, edthresh, cand, cap, n_cand, stage, scale_lo, nscales, blockIdx.x, blockIdx.y);
+}
+
+// All octaves of an image in ONE launch (the DoG planes of every octave are kept): the small octaves -- a few dozen
+// blocks each, pure launch latency on their own -- ride in the tail of octave 0's grid.  The table lives in device
+// memory (written once per plan and slot); 1-D grid, block b belongs to the octave whose [start, start + blocks)
+// range holds it.
+#define SIFTB_KOCT 16
+struct PyrTable {
+    DogStack ds[SIFTB_KOCT];
+    float4 *cand[SIFTB_KOCT];
+    int *n_cand[SIFTB_KOCT];      // per octave: candidates found (k_extrema) ...
+    int *n_kp_oct[SIFTB_KOCT];    // ... and kept by k_refine
+    int *stage[SIFTB_KOCT];       // [3 scales][3] counters
+    int cap[SIFTB_KOCT];
+    float edthresh[SIFTB_KOCT];
+    int ext_bx[SIFTB_KOCT], ext_start[SIFTB_KOCT + 1];   // k_extrema_all: blocks per row of octave o, first block of octave o
+    int n_oct;
+};
+__global__ void __launch_bounds__(128, 6) k_extrema_all(const PyrTable *__restrict__ T, int border, float gate) {
+    int o = 0;
+    const int n_oct = T->n_oct;
+    while (o + 1 < n_oct && (int)blockIdx.x >= T->ext_start[o + 1]) o++;
+    const int local = blockIdx.x - T->ext_start[o], bxn = T->ext_bx[o];
+    const DogStack D = T->ds[o];
+    extrema_block(D, border, gate, T->edthresh[o], T->cand[o], T->cap[o], T->n_cand[o], T->stage[o], 1, 3, local % bxn,
+                  local / bxn);
 }
 
 // Scalar form for planes whose pitch is not a multiple of 4 floats (stage hook on dense host planes).
@@ -340,6 +373,49 @@ __device__ __forceinline__ bool interp_one(const DogStack &D, float4 k, float pe
         return true;
     }
     return false;
+}
+
+// All octaves in one launch: thread t takes candidate t of the concatenation of the per-octave candidate lists
+// (grid-stride over the device-resident counts); survivors are appended to the image-wide keypoint list.
+__global__ void __launch_bounds__(128) k_refine_all(const PyrTable *__restrict__ T, float peak_thresh, float InitSigma,
+                                                     float4 *__restrict__ kp, int *__restrict__ kp_tag, int kp_cap,
+                                                     int *__restrict__ n_kp) {
+    __shared__ int s_first[SIFTB_KOCT + 1];  // first[o] = candidates of the octaves before o
+    const int n_oct = T->n_oct;
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int o = 0; o < n_oct; o++) {
+            s_first[o] = acc;
+            acc += min(*T->n_cand[o], T->cap[o]);
+        }
+        for (int o = n_oct; o <= SIFTB_KOCT; o++) s_first[o] = acc;
+    }
+    __syncthreads();
+    const int n = s_first[SIFTB_KOCT];
+    const int stride = gridDim.x * blockDim.x;
+    const int rounds = (n + stride - 1) / stride;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int it = 0; it < rounds; it++, i += stride) {
+        bool keep = false;
+        float4 res = make_float4(-1.f, -1.f, -1.f, -1.f);
+        int scale = 0, oct = 0;
+        if (i < n) {
+            while (oct + 1 < n_oct && i >= s_first[oct + 1]) oct++;
+            const float4 k = T->cand[oct][i - s_first[oct]];
+            scale = (int)k.w;
+            if ((int)k.y != -1) keep = interp_one(T->ds[oct], k, peak_thresh, InitSigma, &res);
+        }
+        int slot = warp_append(keep, n_kp);
+        if (keep && slot < kp_cap) { kp[slot] = res; kp_tag[slot] = (oct << 8) | scale; }
+        // counters per (octave, scale): the lanes of a warp that kept a candidate of the same (octave, scale) share
+        // one atomicAdd (tens of thousands of single increments on a handful of addresses serialise in L2)
+        const int key = keep ? ((oct << 2) | scale) : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (keep && (int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+            atomicAdd(&T->stage[oct][(scale - 1) * 3 + 1], __popc(peers));
+            atomicAdd(T->n_kp_oct[oct], __popc(peers));
+        }
+    }
 }
 
 // grid-stride over the device-resident candidate count; survivors appended to kp / kp_scale

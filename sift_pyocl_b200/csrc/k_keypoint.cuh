@@ -79,11 +79,17 @@ __device__ __forceinline__ void grad_one(float xgrad, float ygrad, float &gr, fl
     gr = sqrtf(xgrad * xgrad + ygrad * ygrad);
     orv = cr_atan2f_fast(-ygrad, xgrad, K);
 }
-__global__ void __launch_bounds__(128, 8) k_gradient4(GradArgs a) {
-    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, z = blockIdx.z, lane = threadIdx.x & 31;
-    const int y0 = blockIdx.y * GRAD4_ROWS;
-    const float *g = a.g[z];
-    float2 *gop = a.go[z];
+// one plane: g -> gop, block (bx, by) of the grid (ceil(w/512), ceil(h/GRAD4_ROWS))
+struct GradPlane {
+    const float *g;
+    float2 *go;
+    int pitch, w, h;
+};
+__device__ __forceinline__ void gradient4_block(const GradPlane a, int bx, int by) {
+    const int x4 = (bx * blockDim.x + threadIdx.x) * 4, lane = threadIdx.x & 31;
+    const int y0 = by * GRAD4_ROWS;
+    const float *g = a.g;
+    float2 *gop = a.go;
     const bool active = x4 < a.w;
     const int xc = active ? x4 : 0;  // idle threads of a partly filled warp still take part in the shuffles
     auto ldrow = [&](int y) {
@@ -148,11 +154,35 @@ __global__ void __launch_bounds__(128, 8) k_gradient4(GradArgs a) {
     }
 }
 
+__global__ void __launch_bounds__(128, 8) k_gradient4(GradArgs a) {
+    GradPlane pl;
+    pl.g = a.g[blockIdx.z]; pl.go = a.go[blockIdx.z]; pl.pitch = a.pitch; pl.w = a.w; pl.h = a.h;
+    gradient4_block(pl, blockIdx.x, blockIdx.y);
+}
+
+// The three planes of EVERY octave in one launch (the Gaussian planes of all octaves are kept): 1-D grid, the table
+// (device memory, written once per plan) gives the first block of each (octave, plane).
+#define GRAD_MAXPLANES 48
+struct GradTable {
+    GradPlane plane[GRAD_MAXPLANES];
+    int bx[GRAD_MAXPLANES], start[GRAD_MAXPLANES + 1];
+    int n_planes;
+};
+__global__ void __launch_bounds__(128, 8) k_gradient4_all(const GradTable *__restrict__ T) {
+    int pidx = 0;
+    const int n = T->n_planes;
+    while (pidx + 1 < n && (int)blockIdx.x >= T->start[pidx + 1]) pidx++;
+    const int local = blockIdx.x - T->start[pidx], bxn = T->bx[pidx];
+    gradient4_block(T->plane[pidx], local % bxn, local / bxn);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Gradient / orientation planes of EVERY octave of an image: orientation assignment and descriptors run once
 // per image over the keypoints of all octaves (a keypoint carries tag = octave << 8 | scale), so that the
 // small octaves do not each pay the latency of a nearly empty launch.
+#ifndef SIFTB_KOCT
 #define SIFTB_KOCT 16
+#endif
 struct OctTable {
     const float2 *go[SIFTB_KOCT][3];  // (gradient magnitude, orientation) planes, see GradArgs
     int pitch[SIFTB_KOCT], w[SIFTB_KOCT], h[SIFTB_KOCT];
@@ -186,6 +216,13 @@ __global__ void __launch_bounds__(256) k_orient(OctTable T, float4 *__restrict__
                                                  int *__restrict__ size_hist) {
     __shared__ float s_hist[8][36];
     __shared__ int s_clo[8][ORI_MAXROWS], s_chi[8][ORI_MAXROWS];
+    // per-CTA partial counters, added to the global ones once at the end (one keypoint = three increments on a handful
+    // of hot addresses otherwise: ~2e5 same-address atomics per image)
+    __shared__ int s_stage[SIFTB_KOCT * 9], s_valid[SIFTB_KOCT], s_size[DESC_CLASSES];
+    for (int i = threadIdx.x; i < SIFTB_KOCT * 9; i += blockDim.x) s_stage[i] = 0;
+    for (int i = threadIdx.x; i < SIFTB_KOCT; i += blockDim.x) s_valid[i] = 0;
+    for (int i = threadIdx.x; i < DESC_CLASSES; i += blockDim.x) s_size[i] = 0;
+    __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     int *clo = s_clo[wib], *chi = s_chi[wib];
     const int n_base = min(*n_base_p, cap);
@@ -414,14 +451,24 @@ __global__ void __launch_bounds__(256) k_orient(OctTable T, float4 *__restrict__
         }
         if (lane == 0) {
             const int added = 1 + n_stored;
-            if (stage) atomicAdd(&stage[oct * 9 + (sc - 1) * 3 + 2], added);
+            atomicAdd(&s_stage[oct * 9 + (sc - 1) * 3 + 2], added);
             // rows whose angle is NaN (flat histogram) are dropped on output (plan.py:546-550)
-            if (oct_valid) atomicAdd(&oct_valid[oct], added - ((angle != angle) ? 1 : 0));
+            atomicAdd(&s_valid[oct], added - ((angle != angle) ? 1 : 0));
             // descriptor-window size class of this keypoint and of its extra orientations (same sigma)
-            if (size_hist) atomicAdd(&size_hist[desc_size_class(o.z, octsize)], added);
+            atomicAdd(&s_size[desc_size_class(o.z, octsize)], added);
         }
         __syncwarp();
     }
+    __syncthreads();
+    if (stage)
+        for (int i = threadIdx.x; i < SIFTB_KOCT * 9; i += blockDim.x)
+            if (s_stage[i]) atomicAdd(&stage[i], s_stage[i]);
+    if (oct_valid)
+        for (int i = threadIdx.x; i < SIFTB_KOCT; i += blockDim.x)
+            if (s_valid[i]) atomicAdd(&oct_valid[i], s_valid[i]);
+    if (size_hist)
+        for (int i = threadIdx.x; i < DESC_CLASSES; i += blockDim.x)
+            if (s_size[i]) atomicAdd(&size_hist[i], s_size[i]);
 }
 
 struct KpRecord {  // == siftb_kp

@@ -99,7 +99,7 @@ struct Event {
 };
 
 struct siftb_plan {
-    int device = 0, h = 0, w = 0, dtype = 0, pix_per_kp = 10, n_oct = 0, kpsize = 0;
+    int device = 0, h = 0, w = 0, dtype = 0, pix_per_kp = 10, n_oct = 0, kpsize = 0, octave_limit = 0;
     int out_cap = 0;  // records of ALL octaves: the reference's limit (kpsize) is per octave (plan.py:243,748-752)
     double init_sigma = 1.6;  // python double in the reference (plan.py:123-126); fp32 only as a kernel argument
     int ow[MAX_OCT], oh[MAX_OCT], opitch[MAX_OCT];
@@ -115,10 +115,17 @@ struct siftb_plan {
     // and keypoint lists are shared (kernels of successive images are serialised on the compute stream).
     void *d_raws[NSLOT] = {};  // staging for host input (plan dtype)
     float *d_img = nullptr;    // dense fp32 plane for converted integer/RGB/f64 input
-    float *G[6] = {}, *D[5] = {};
+    // Gaussian and DoG planes of EVERY octave (octave o: h_o rows at pitch align32(w_o)): the extrema, refinement
+    // and gradient kernels run once per image over all octaves after the whole pyramid has been built
+    float *G[MAX_OCT][6] = {}, *D[MAX_OCT][5] = {};
+    float4 *cands[MAX_OCT] = {};      // per-octave candidate lists, capacity cand_cap[o]
+    int cand_cap[MAX_OCT] = {};
+    PyrTable *d_pyr[NSLOT] = {};      // device tables of k_extrema_all / k_refine_all (per slot: counter addresses)
+    GradTable *d_grad = nullptr;      // device table of k_gradient4_all
+    int ext_blocks = 0, grad_blocks = 0;
     float2 *gop[SIFTB_KOCT][3] = {};  // (gradient, orientation) planes of every octave (k_keypoint.cuh)
     OctTable table;
-    float4 *cand = nullptr, *kp = nullptr;
+    float4 *kp = nullptr;
     int *kp_tag = nullptr;  // octave << 8 | scale
     int *kp_order = nullptr;  // keypoint indices by descending descriptor-window size
     int kp_cap = 0;         // keypoints of one image over all octaves
@@ -212,11 +219,16 @@ extern "C" int siftb_plan_destroy(siftb_plan *p) {
     for (int s = 0; s < NSLOT; s++) { cudaFree(p->d_raws[s]); cudaFree(p->outs[s]); cudaFree(p->d_cnts[s]); }
     cudaFree(p->d_img);
     p->d_warp.release();
-    for (auto q : p->G) cudaFree(q);
-    for (auto q : p->D) cudaFree(q);
+    for (int o = 0; o < MAX_OCT; o++) {
+        for (auto q : p->G[o]) cudaFree(q);
+        for (auto q : p->D[o]) cudaFree(q);
+        cudaFree(p->cands[o]);
+    }
+    for (int s = 0; s < NSLOT; s++) cudaFree(p->d_pyr[s]);
+    cudaFree(p->d_grad);
     for (int o = 0; o < SIFTB_KOCT; o++)
         for (int i = 0; i < 3; i++) cudaFree(p->gop[o][i]);
-    cudaFree(p->cand); cudaFree(p->kp); cudaFree(p->kp_tag); cudaFree(p->kp_order); cudaFree(p->d_queue);
+    cudaFree(p->kp); cudaFree(p->kp_tag); cudaFree(p->kp_order); cudaFree(p->d_queue);
     for (int s = 0; s < NSLOT; s++) {
         if (p->h_cnts[s]) cudaFreeHost(p->h_cnts[s]);
         if (p->ev_h2d[s]) cudaEventDestroy(p->ev_h2d[s]);
@@ -254,6 +266,7 @@ static int plan_create_impl(siftb_plan *p) {
         }
         n--;
         p->n_oct = n;
+        if (p->octave_limit > 0 && p->octave_limit < p->n_oct) p->n_oct = p->octave_limit;  // par.OctaveMax
     }
     if (p->n_oct < 1) return fail(SIFTB_EINVAL, "image too small: min(shape) must exceed 12 (plan.py:216)");
     for (int o = 0; o < p->n_oct; o++) p->opitch[o] = align_up(p->ow[o], 32);
@@ -286,8 +299,12 @@ static int plan_create_impl(siftb_plan *p) {
     int rc;
     for (int s = 0; s < NSLOT; s++) if ((rc = dalloc(p, &p->d_raws[s], p->raw_bytes))) return rc;
     if (p->dtype != SIFTB_F32 && (rc = dalloc(p, &p->d_img, N * sizeof(float)))) return rc;
-    for (int i = 0; i < 6; i++) if ((rc = dalloc(p, &p->G[i], plane))) return rc;
-    for (int i = 0; i < 5; i++) if ((rc = dalloc(p, &p->D[i], plane))) return rc;
+    (void)plane;
+    for (int o = 0; o < p->n_oct; o++) {
+        const size_t pl = (size_t)p->opitch[o] * p->oh[o] * sizeof(float);
+        for (int i = 0; i < 6; i++) if ((rc = dalloc(p, &p->G[o][i], pl))) return rc;
+        for (int i = 0; i < 5; i++) if ((rc = dalloc(p, &p->D[o][i], pl))) return rc;
+    }
     if (p->n_oct > SIFTB_KOCT) return fail(SIFTB_EINVAL, "image too large: more than 16 octaves");
     memset(&p->table, 0, sizeof(p->table));
     for (int o = 0; o < p->n_oct; o++) {
@@ -301,7 +318,14 @@ static int plan_create_impl(siftb_plan *p) {
         p->table.h[o] = p->oh[o];
         p->table.octsize[o] = 1 << o;
     }
-    if ((rc = dalloc(p, &p->cand, (size_t)p->kpsize * sizeof(float4)))) return rc;
+    for (int o = 0; o < p->n_oct; o++) {
+        // plan.py:243: kpsize slots per octave; an octave cannot produce more than 3 candidates per pixel, so the
+        // small octaves get by with less memory without changing what can overflow
+        const long most = 3L * p->ow[o] * p->oh[o];
+        p->cand_cap[o] = (int)(most < p->kpsize ? most : p->kpsize);
+        if (p->cand_cap[o] < 1) p->cand_cap[o] = 1;
+        if ((rc = dalloc(p, &p->cands[o], (size_t)p->cand_cap[o] * sizeof(float4)))) return rc;
+    }
     p->kp_cap = 2 * p->kpsize;
     if ((rc = dalloc(p, &p->kp, (size_t)p->kp_cap * sizeof(float4)))) return rc;
     if ((rc = dalloc(p, &p->kp_tag, (size_t)p->kp_cap * sizeof(int)))) return rc;
@@ -313,7 +337,7 @@ static int plan_create_impl(siftb_plan *p) {
         for (int o = 0; o < p->n_oct; o++)
             for (int s = 0; s < 5; s++)
                 if (tb_supported(p->ntaps[s], s == kScales - 1 && o + 1 < p->n_oct ? TB_DOG_HALF : TB_DOG))
-                    p->tmaps_ok[o][s] = tb_encode_pair(&p->tmaps[o][s], p->G[s], p->ow[o], p->oh[o], p->opitch[o], p->ntaps[s] >> 1) == 0;
+                    p->tmaps_ok[o][s] = tb_encode_pair(&p->tmaps[o][s], p->G[o][s], p->ow[o], p->oh[o], p->opitch[o], p->ntaps[s] >> 1) == 0;
         if (tb_supported(p->ntaps[5], TB_NORM) && p->w % 4 == 0) {
             p->tmap_raw_ok = true;
             for (int s = 0; s < NSLOT; s++)
@@ -330,6 +354,49 @@ static int plan_create_impl(siftb_plan *p) {
     }
     CK(cudaFuncSetAttribute(k_blur_generic, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)blur_generic_smem(SIFTB_MAX_TAPS - 1)));
+    // device tables of the whole-pyramid launches (k_extrema_all, k_refine_all, k_gradient4_all)
+    for (int s = 0; s < NSLOT; s++) {
+        PyrTable t;
+        memset(&t, 0, sizeof(t));
+        t.n_oct = p->n_oct;
+        int start = 0;
+        for (int o = 0; o < p->n_oct; o++) {
+            for (int i = 0; i < 5; i++) t.ds[o].d[i] = p->D[o][i];
+            t.ds[o].pitch = p->opitch[o]; t.ds[o].w = p->ow[o]; t.ds[o].h = p->oh[o];
+            t.cand[o] = p->cands[o];
+            t.cap[o] = p->cand_cap[o];
+            t.n_cand[o] = p->c_oct(s, o) + 0;
+            t.n_kp_oct[o] = p->c_oct(s, o) + 1;
+            t.stage[o] = p->c_stage(s, o);
+            t.edthresh[o] = (1 << o) <= 1 ? kEdgeThresh1 : kEdgeThresh;  // plan.py:633-634, image.cl:195
+            const bool has = p->ow[o] > 2 * kBorderDist && p->oh[o] > 2 * kBorderDist;
+            t.ext_bx[o] = (p->ow[o] + 511) / 512;
+            t.ext_start[o] = start;
+            if (has) start += t.ext_bx[o] * ((p->oh[o] - 2 * kBorderDist + EXT_ROWS - 1) / EXT_ROWS);
+        }
+        for (int o = p->n_oct; o <= SIFTB_KOCT; o++) t.ext_start[o] = start;
+        p->ext_blocks = start;
+        if ((rc = dalloc(p, &p->d_pyr[s], sizeof(PyrTable)))) return rc;
+        CK(cudaMemcpy(p->d_pyr[s], &t, sizeof(t), cudaMemcpyHostToDevice));
+    }
+    {
+        GradTable g;
+        memset(&g, 0, sizeof(g));
+        int start = 0, n = 0;
+        for (int o = 0; o < p->n_oct; o++)
+            for (int i = 0; i < 3; i++, n++) {
+                g.plane[n].g = p->G[o][i + 1]; g.plane[n].go = p->gop[o][i];
+                g.plane[n].pitch = p->opitch[o]; g.plane[n].w = p->ow[o]; g.plane[n].h = p->oh[o];
+                g.bx[n] = (p->ow[o] + 511) / 512;
+                g.start[n] = start;
+                start += g.bx[n] * ((p->oh[o] + GRAD4_ROWS - 1) / GRAD4_ROWS);
+            }
+        g.n_planes = n;
+        for (int i = n; i <= GRAD_MAXPLANES; i++) g.start[i] = start;
+        p->grad_blocks = start;
+        if ((rc = dalloc(p, &p->d_grad, sizeof(GradTable)))) return rc;
+        CK(cudaMemcpy(p->d_grad, &g, sizeof(g), cudaMemcpyHostToDevice));
+    }
     return 0;
 }
 
@@ -344,6 +411,7 @@ extern "C" int siftb_plan_create(int height, int width, int dtype, int device, i
     siftb_plan *p = new siftb_plan();
     p->device = device; p->h = height; p->w = width; p->dtype = dtype;
     p->pix_per_kp = pix_per_kp; p->init_sigma = init_sigma;
+    p->octave_limit = octave_max;
     p->force_generic = env_force_generic();
     int rc = plan_create_impl(p);
     if (rc) {
@@ -352,7 +420,6 @@ extern "C" int siftb_plan_create(int height, int width, int dtype, int device, i
         g_siftb_err = keep;
         return rc;
     }
-    if (octave_max > 0 && octave_max < p->n_oct) p->n_oct = octave_max;  // par.OctaveMax
     *out = p;
     return 0;
 }
@@ -544,55 +611,45 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
         const TbMaps *pm = nullptr;
         if (img == (const float *)p->d_raws[slot] && p->tmap_raw_ok) pm = &p->tmap_raws[slot];
         else if (img == p->d_img && p->tmap_img_ok) pm = &p->tmap_img;
-        if ((rc = launch_blur(st, img, p->w, p->w, p->h, p->G[0], p->opitch[0], nullptr, nullptr, 0, p->taps[5],
+        if ((rc = launch_blur(st, img, p->w, p->w, p->h, p->G[0][0], p->opitch[0], nullptr, nullptr, 0, p->taps[5],
                               p->ntaps[5], mm, pm, p->force_generic)))
             return rc;
         p->launches += 1;
     }
-    // per octave: pyramid, extrema, refinement (into the image-wide keypoint list), gradient planes
+    // the whole pyramid first: five blur + DoG launches per octave, chained (the s = 2 launch also writes the next
+    // octave's base); then extrema, refinement and gradient planes of ALL octaves with one launch each
     for (int o = 0; o < p->n_oct; o++) {
         const int w = p->ow[o], h = p->oh[o], pitch = p->opitch[o];
-        const int octsize = 1 << o;
-        int *c = p->c_oct(slot, o);
-        int *stage = p->c_stage(slot, o);
-        {
-            ProfScope ps(p, "blur + DoG", o);
-            for (int s = 0; s < kScales + 2; s++) {
-                float *half = nullptr;
-                int hp = 0;
-                if (s == kScales - 1 && o + 1 < p->n_oct) { half = p->G[0]; hp = p->opitch[o + 1]; }
-                if ((rc = launch_blur(st, p->G[s], pitch, w, h, p->G[s + 1], pitch, p->D[s], half, hp, p->taps[s],
-                                      p->ntaps[s], nullptr, p->tmaps_ok[o][s] ? &p->tmaps[o][s] : nullptr,
-                                      p->force_generic)))
-                    return rc;
-                p->launches += 1;
-            }
-        }
-        DogStack ds = make_dogstack(p->D, pitch, w, h);
-        if (w > 2 * kBorderDist && h > 2 * kBorderDist) {
-            ProfScope ps(p, "local_maxmin", o);
-            if ((rc = launch_extrema(st, ds, contrast_gate(kPeakThresh), octsize <= 1 ? kEdgeThresh1 : kEdgeThresh, p->cand,
-                                     p->kpsize, c + 0, stage, 1, kScales)))
+        ProfScope ps(p, "blur + DoG", o);
+        for (int s = 0; s < kScales + 2; s++) {
+            float *half = nullptr;
+            int hp = 0;
+            if (s == kScales - 1 && o + 1 < p->n_oct) { half = p->G[o + 1][0]; hp = p->opitch[o + 1]; }
+            if ((rc = launch_blur(st, p->G[o][s], pitch, w, h, p->G[o][s + 1], pitch, p->D[o][s], half, hp, p->taps[s],
+                                  p->ntaps[s], nullptr, p->tmaps_ok[o][s] ? &p->tmaps[o][s] : nullptr,
+                                  p->force_generic)))
                 return rc;
             p->launches += 1;
         }
-        {
-            ProfScope ps(p, "interp_keypoint + compact", o);
-            k_refine<<<148 * 4, 128, 0, st>>>(ds, p->cand, c + 0, p->kpsize, kPeakThresh, (float)p->init_sigma, p->kp,
-                                              p->kp_tag, p->kp_cap, n_kp, stage, o, c + 1);
-            CKL();
-            p->launches += 1;
-        }
-        {
-            ProfScope ps(p, "compute_gradient_orientation", o);
-            GradArgs ga;
-            for (int i = 0; i < 3; i++) { ga.g[i] = p->G[i + 1]; ga.go[i] = p->gop[o][i]; }
-            ga.pitch = pitch; ga.w = w; ga.h = h;
-            dim3 grid((w + 511) / 512, (h + GRAD4_ROWS - 1) / GRAD4_ROWS, 3);  // planes: pitch % 32 == 0, aligned
-            k_gradient4<<<grid, 128, 0, st>>>(ga);
-            CKL();
-            p->launches += 1;
-        }
+    }
+    if (p->ext_blocks > 0) {
+        ProfScope ps(p, "local_maxmin");
+        k_extrema_all<<<p->ext_blocks, 128, 0, st>>>(p->d_pyr[slot], kBorderDist, contrast_gate(kPeakThresh));
+        CKL();
+        p->launches += 1;
+    }
+    {
+        ProfScope ps(p, "interp_keypoint + compact");
+        k_refine_all<<<148 * 8, 128, 0, st>>>(p->d_pyr[slot], kPeakThresh, (float)p->init_sigma, p->kp, p->kp_tag,
+                                              p->kp_cap, n_kp);
+        CKL();
+        p->launches += 1;
+    }
+    {
+        ProfScope ps(p, "compute_gradient_orientation");
+        k_gradient4_all<<<p->grad_blocks, 128, 0, st>>>(p->d_grad);
+        CKL();
+        p->launches += 1;
     }
     // once per image: orientation assignment and descriptors over the keypoints of all octaves
     {
@@ -608,9 +665,9 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
     }
     {
         ProfScope ps(p, "descriptors");
-        k_octave_offsets<<<1, 1, 0, st>>>(oct_valid, p->n_oct, oct_offset, p->c_nout(slot), p->c_oct(slot, 0) + 3,
-                                          size_hist, size_start, n_order);
-        k_size_order<<<148, 256, 0, st>>>(p->kp, p->kp_tag, n_kp, n_extra, p->kp_cap, size_start, size_fill, p->kp_order);
+        k_size_order<<<148, 256, 0, st>>>(p->kp, p->kp_tag, n_kp, n_extra, p->kp_cap, size_hist, size_fill, p->kp_order,
+                                          n_order, oct_valid, p->n_oct, oct_offset, p->c_nout(slot),
+                                          p->c_oct(slot, 0) + 3);
         if (p->variant)
             k_describe<true><<<148 * 6, DESC_WARPS * 32, 0, st>>>(p->table, p->kp, p->kp_tag, n_order, p->kp_cap,
                                                                   p->outs[slot], p->out_cap, oct_offset, oct_fill,
@@ -620,7 +677,7 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
                                                                    p->outs[slot], p->out_cap, oct_offset, oct_fill,
                                                                    q_head, p->kp_order);
         CKL();
-        p->launches += 3;
+        p->launches += 2;
     }
     CK(cudaMemcpyAsync(p->d_cnts[slot] + 1 + 13 * p->n_oct + 2, n_kp, 2 * sizeof(int), cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(p->h_cnts[slot], p->d_cnts[slot], p->cnt_ints * sizeof(int), cudaMemcpyDeviceToHost, st));

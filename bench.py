@@ -8,15 +8,23 @@ A "step" is one pass of the hot path (plan.keypoints) over one synthetic image p
 BASELINE.json configs[1]: SiftPlan 4096x4096 float32, 3 octaves x 3 scales (par.OctaveMax = 3), images
 = seeded "multiscale noise" (sift_pyocl_b200.utils.multiscale_image, seed 1234 + index).
   value : whole-job keypoints/s with the images already resident in HBM (device pointer input), records
-          left on the device, CUDA events on the plan's stream, max over ranks;
+          left on the device, CUDA events on the plan's stream around EXACTLY K software-pipelined steps,
+          max over ranks.  The K-step region is measured --repeats times (default 5); the line reports the
+          median region and lists all of them (`timed_regions`).
   e2e   : the same metric through the public API with HOST buffers: pinned host image -> H2D copy ->
-          kernels -> D2H copy of the records -> numpy recarray, every step;
-  roofline : the Gaussian blur(+DoG) kernel family, algorithmic bytes (12*W*H per blur+DoG launch,
-          8*W*H for the first blur) / CUDA-event time of those launches inside the timed
-          region, against MEASURED_PEAKS.json hbm_gbs;
-  cpu_baseline : the oracle (CPU port of the reference kernels, OpenMP) on the same image.
-For N > 1 (torchrun) every rank runs the same per-GPU work on different images (weak scaling) and
-each step ends with the NCCL all-gather of the keypoint records (counts + padded payload).
+          kernels -> D2H copy of the records -> numpy recarray, every step (SiftPlan.keypoints_many, three
+          images in flight); `one_at_a_time` is the reference's own call, SiftPlan.keypoints(host image).
+  roofline : the Gaussian pyramid convolution = ALL blur launches of a step (normalise + first blur, 8*W*H
+          bytes; five blur+DoG launches per octave, 12*W_o*H_o bytes each).  achieved =
+          algorithmic bytes of the average launch / its average duration (CUDA events on the plan's stream
+          in a K-step region with profiling on) against MEASURED_PEAKS.json hbm_gbs; the octave-0 launches
+          and the first blur are broken out; `traffic` = DRAM bytes of the average launch from the committed
+          ncu --set full capture (profiles/).
+  cpu_baseline : the oracle (CPU port of the reference kernels, OpenMP) on the same image, all host
+          threads and one thread.
+For N > 1 (torchrun) every rank runs the same per-GPU work on different images (weak scaling) and every
+step's keypoint records are all-gathered over NCCL (dist.RecordExchange: one collective per step on a
+side stream, completed one pipeline step later).
 """
 import argparse
 import json
@@ -35,10 +43,12 @@ if ROOT not in sys.path:
 SIZE = 4096
 OCTAVES = 3
 N_IMAGES = 2  # distinct images cycled per rank (working set per image ~1.2 GB >> 126 MB L2)
-# dram__bytes_read.sum + dram__bytes_write.sum of all blur launches of one step, summed from the committed
-# ncu --set full capture of the final kernels of the round (profiles/, see TRAFFIC_NOTE); None until measured
-TRAFFIC_PER_STEP = None
-TRAFFIC_NOTE = "not captured yet for this kernel revision"
+# dram__bytes_read.sum + dram__bytes_write.sum of all 16 blur launches of one step, summed from the committed
+# ncu --set full capture of the final kernels of the round (see TRAFFIC_NOTE); bytes per step
+TRAFFIC_PER_STEP = 1021.28e6
+TRAFFIC_NOTE = ("sum over the 16 blur launches of one step in profiles/r02_ncu_full_step_4096_3oct.csv (ncu --set full of "
+                "the round's final kernels), divided by 16; below the algorithmic 1455 MB because the planes of "
+                "octaves 1 and 2 are still dirty in the 126 MB L2 when their launches end")
 
 
 def _peaks():
@@ -362,10 +372,11 @@ def main():
                                % (n_blur, " / ".join("%dx%d" % (int(w), int(h)) for w, h in plan.scales)),
                      "achieved": achieved_all, "peak": peak, "unit": "GB/s",
                      "frac": (achieved_all / peak) if achieved_all else None,
-                     "traffic": TRAFFIC_PER_STEP, "traffic_note": TRAFFIC_NOTE,
+                     "traffic": (TRAFFIC_PER_STEP / n_blur) if TRAFFIC_PER_STEP else None, "traffic_note": TRAFFIC_NOTE,
                      "peak_source": peak_src + " (burst copy figure)",
-                     "algorithmic_bytes_per_step": bbytes, "launches_per_step": n_blur,
-                     "avg_launch_ms": blur_ms / args.steps / n_blur, "ms_per_step": blur_ms / args.steps,
+                     "algorithmic_bytes_per_launch": bbytes / n_blur, "launches_per_step": n_blur,
+                     "avg_launch_ms": blur_ms / args.steps / n_blur,
+                     "algorithmic_bytes_per_step": bbytes, "ms_per_step": blur_ms / args.steps,
                      "octave0_launches": {"note": "the 5 blur+DoG launches on the 4096x4096 planes, 12*W*H bytes each",
                                           "achieved": achieved0, "frac": (achieved0 / peak) if achieved0 else None,
                                           "avg_launch_ms": blur0_ms / args.steps / 5},

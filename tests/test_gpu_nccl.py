@@ -37,9 +37,15 @@ def _worker(rank, world, port, q):
         plan = sift.SiftPlan(shape=imgs[0].shape, dtype=np.float32, device=rank)
         solo = [plan.keypoints(im) for im in imgs]                 # single-GPU records of every image
         ok = True
+        failed = []
+
+        def check(name, cond):
+            if not cond:
+                failed.append(name)
+            return bool(cond)
         # (a) the sharded batch with the NCCL gather: every rank ends up with every image's records
         out = sdist.keypoints_batch(plan, imgs)
-        ok = ok and len(out) == len(imgs) and all(same_records(a, b) for a, b in zip(out, solo))
+        ok = check("keypoints_batch", len(out) == len(imgs) and all(same_records(a, b) for a, b in zip(out, solo))) and ok
         # (b) the pipelined per-step exchange on device-resident records (what bench.py does at N > 1), with a
         # capacity small enough that one step takes the overflow path
         mine = sdist.shard_indices(len(imgs), rank, world)
@@ -61,8 +67,8 @@ def _worker(rank, world, port, q):
         for step, (per_rank, counts) in enumerate(got):
             for r in range(world):
                 idx = sdist.shard_indices(len(imgs), r, world)[step]
-                ok = ok and int(counts[r]) == solo[idx].size
-                ok = ok and same_records(sdist.records_to_numpy(per_rank[r]), solo[idx])
+                ok = check("exchange count step %d rank %d" % (step, r), int(counts[r]) == solo[idx].size) and ok
+                ok = check("exchange records step %d rank %d" % (step, r), same_records(sdist.records_to_numpy(per_rank[r]), solo[idx])) and ok
         # (c) the C-ABI communicator: unique id from rank 0, all-gather of this rank's first image
         lib = _lib.load()
         uid = torch.zeros(128, dtype=torch.uint8)
@@ -85,19 +91,20 @@ def _worker(rank, world, port, q):
         _lib.check(lib.siftb_allgather_kp(comm, ctypes.c_void_p(recs), n, counts.ctypes.data_as(_lib.c_int_p),
                                           _lib.ptr(host), cap_out, ctypes.byref(total)))
         first = [sdist.shard_indices(len(imgs), r, world)[0] for r in range(world)]
-        ok = ok and counts.tolist() == [solo[i].size for i in first] and total.value == counts.sum()
+        ok = check("c-abi counts", counts.tolist() == [solo[i].size for i in first] and total.value == counts.sum()) and ok
         start = 0
         for r in range(world):
-            ok = ok and same_records(host[start:start + counts[r]].view(np.recarray), solo[first[r]])
+            ok = check("c-abi records rank %d" % r, same_records(host[start:start + counts[r]].view(np.recarray), solo[first[r]])) and ok
             start += counts[r]
         _lib.check(lib.siftb_comm_destroy(comm))
         # (d) MatchPlan with the rows of list 1 sharded over the ranks, index pairs all-gathered over NCCL
         mp = sift.MatchPlan(device=rank)
-        whole = mp.match(solo[0], solo[1], raw_results=True)
+        other = np.concatenate([solo[1], solo[0][::-1]]).view(np.recarray)   # holds a copy of every keypoint of list 1
+        whole = mp.match(solo[0], other, raw_results=True)
         whole = whole[np.argsort(whole[:, 0], kind="stable")]
-        sharded = sdist.match_sharded(mp, solo[0], solo[1])
-        ok = ok and np.array_equal(sharded, whole) and len(whole) > 0
-        q.put((rank, bool(ok), ""))
+        sharded = sdist.match_sharded(mp, solo[0], other)
+        ok = check("match_sharded (%d vs %d pairs)" % (len(sharded), len(whole)), np.array_equal(sharded, whole) and len(whole) > 0) and ok
+        q.put((rank, bool(ok), "; ".join(failed)))
         dist.destroy_process_group()
     except Exception as exc:  # report instead of hanging the parent
         import traceback

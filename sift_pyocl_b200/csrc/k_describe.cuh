@@ -25,17 +25,14 @@
 
 #define DESC_WARPS 4  // warps per CTA -> 16 keypoints per CTA
 
-#define DESC_MAXROWS 104  // window rows per keypoint handled by the interval table (default sigmas: 97, GPU variant 101)
+#define DESC_MAXROWS 101  // window rows per keypoint handled by the interval table (default sigmas: 97, GPU variant 101)
 
-// Per-octet table of the non-empty window rows: only the j-interval that can be valid.  One packed word per row:
-// byte 0 = window row i (-iradius..iradius; |.| <= 49 for tabled windows), byte 1 = first candidate j, byte 2 = last
-// candidate j (signed bytes).
+// Per-octet table of the non-empty window rows: only the j-interval that can be valid.  Three signed bytes per row
+// (window row i, -66..63 for tabled windows; first and last candidate j): 306 bytes per octet -- together with the
+// swizzled stage below this lets SEVEN CTAs share an SM's shared memory.
 struct DescRows {
-    int w[DESC_MAXROWS];
+    signed char i[DESC_MAXROWS], jlo[DESC_MAXROWS], jhi[DESC_MAXROWS];
 };
-__device__ __forceinline__ int desc_pack_row(int i, int jlo, int jhi) {
-    return (i & 0xff) | ((jlo & 0xff) << 8) | ((jhi & 0xff) << 16);
-}
 
 // Staging area of one octet for one pass (8 samples): the evaluating lane s writes, for each of the 8 parity
 // classes p = (row&1)<<2 | (col&1)<<1 | (ori&1), the ONE contribution of sample s to a bin of that class as
@@ -43,12 +40,26 @@ __device__ __forceinline__ int desc_pack_row(int i, int jlo, int jhi) {
 // the trilinear interpolation) and those always differ in all three parities, so every class receives exactly one
 // term per sample.  Rejected samples stage value +-0.0 (every histogram term is >= +0, so adding a zero of either
 // sign is an exact no-op).
-// Rows are 10 float2 apart (80 B) and octets 704 B apart: the 8 lanes of an octet then store their 16-byte
-// chunks to 8 different bank quads, and the per-class 8-byte loads of two neighbouring octets do not collide.
+// Layout: row s = 64 bytes = four 16-byte chunks (chunk c = classes 2c, 2c + 1), stored at chunk position
+// c ^ ((s >> 1) & 3): the 8 lanes of an octet then write their chunk c to 8 different bank quads (one wavefront per
+// octet) although the rows are only 64 bytes apart.  The four stages of a warp sit at byte offsets 0, 576, 1088, 1664
+// of a 2176-byte block: octets 0 / 1 and 2 / 3 -- the pairs that share a half-warp, the unit of a 64-bit shared load
+// -- are 64 bytes apart modulo 128, so the 64-byte rows they read together cover 32 different banks.
 struct __align__(16) DescStage {
-    float2 e[8][10];
-    float2 pad[8];
+    float2 e[8][8];
 };
+#define DESC_STAGE_WARP_BYTES 2176
+__device__ __forceinline__ int desc_stage_offset(int octet_in_warp) {  // 0, 576, 1088, 1664
+    return 544 * octet_in_warp + 32 * (octet_in_warp & 1);
+}
+// one raw shared buffer per CTA, carved by hand (no alignment padding between the arrays: with 32 288 bytes seven
+// CTAs fit into an SM's 228 KB, each CTA also reserving 1 KB)
+#define DESC_SMEM_HIST (DESC_WARPS * DESC_HROWS * 32 * 4)
+#define DESC_SMEM_STAGE (DESC_WARPS * DESC_STAGE_WARP_BYTES)
+#define DESC_SMEM_EXP 256
+#define DESC_SMEM_ROWS (DESC_WARPS * 4 * 3 * DESC_MAXROWS)
+#define DESC_SMEM_BYTES (DESC_SMEM_HIST + DESC_SMEM_STAGE + DESC_SMEM_EXP + DESC_SMEM_ROWS)
+__device__ __forceinline__ int desc_stage_chunk(int s, int c) { return 4 * s + (c ^ ((s >> 1) & 3)); }  // float4 index
 
 // Histogram storage of one warp: the 4 x 4 x 8 bins of the reference plus a GUARD RING -- cells r, c in -1..4,
 // stored as r0 = r + 1, c0 = c + 1 in 0..5 -- so that the trilinear neighbours of a sample never need a range test
@@ -157,7 +168,9 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
             jlo = max(jlo, max(wlo, -icol));
             jhi = min(jhi, min(whi, grad_width - 1 - icol));
             if (jhi < jlo) { jlo = 1; jhi = 0; }  // empty (the real-valued bounds may not fit the table's type)
-            rows.w[r] = desc_pack_row(i, jlo, jhi);
+            rows.i[r] = (signed char)i;
+            rows.jlo[r] = (signed char)jlo;
+            rows.jhi[r] = (signed char)jhi;
         }
     }
     // (the warp-level barriers sit outside the per-octet branches: the four octets of a warp may take different ones)
@@ -166,10 +179,12 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
         if (l8 == 0) {  // drop the empty rows (in place: the write index never overtakes the read index)
             int n = 0, acc = 0;
             for (int r = 0; r < nrows; r++) {
-                const int w = rows.w[r];
-                const int jlo = (int)(signed char)(w >> 8), jhi = (int)(signed char)(w >> 16);
+                const int jlo = rows.jlo[r], jhi = rows.jhi[r];
                 if (jhi >= jlo) {
-                    rows.w[n++] = w;
+                    rows.i[n] = rows.i[r];
+                    rows.jlo[n] = (signed char)jlo;
+                    rows.jhi[n] = (signed char)jhi;
+                    n++;
                     acc += jhi - jlo + 1;
                 }
             }
@@ -199,10 +214,9 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
             rcur++;
             if (rcur < nrc) {
                 if (tabled) {
-                    const int w = rows.w[rcur];
-                    n_i = (int)(signed char)w;
-                    jcur = (int)(signed char)(w >> 8) + over;
-                    jend = (int)(signed char)(w >> 16);
+                    n_i = rows.i[rcur];
+                    jcur = rows.jlo[rcur] + over;
+                    jend = rows.jhi[rcur];
                 } else {
                     n_i = u_r0 + rcur + wlo;
                     jcur = u_jlo + over;
@@ -279,21 +293,22 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
             // GPU variant: the term enters the histogram as (uint)(100000 * term) (keypoints_gpu2.cl:189-191); its
             // bit pattern travels through the stage in place of the float
             auto term = [](float t) { return GPUVAR ? __uint_as_float((unsigned)(100000.0f * t)) : t; };
-            float4 *dst = reinterpret_cast<float4 *>(&stage.e[l8][0]);
-            dst[0] = make_float4(__uint_as_float(ra_e + ca_e + oa_e), term(cw_ee * ow_e),
+            float4 *dst = reinterpret_cast<float4 *>(&stage.e[0][0]);
+            dst[desc_stage_chunk(l8, 0)] = make_float4(__uint_as_float(ra_e + ca_e + oa_e), term(cw_ee * ow_e),
                                  __uint_as_float(ra_e + ca_e + oa_o), term(cw_ee * ow_o));
-            dst[1] = make_float4(__uint_as_float(ra_e + ca_o + oa_e), term(cw_eo * ow_e),
+            dst[desc_stage_chunk(l8, 1)] = make_float4(__uint_as_float(ra_e + ca_o + oa_e), term(cw_eo * ow_e),
                                  __uint_as_float(ra_e + ca_o + oa_o), term(cw_eo * ow_o));
-            dst[2] = make_float4(__uint_as_float(ra_o + ca_e + oa_e), term(cw_oe * ow_e),
+            dst[desc_stage_chunk(l8, 2)] = make_float4(__uint_as_float(ra_o + ca_e + oa_e), term(cw_oe * ow_e),
                                  __uint_as_float(ra_o + ca_e + oa_o), term(cw_oe * ow_o));
-            dst[3] = make_float4(__uint_as_float(ra_o + ca_o + oa_e), term(cw_oo * ow_e),
+            dst[desc_stage_chunk(l8, 3)] = make_float4(__uint_as_float(ra_o + ca_o + oa_e), term(cw_oo * ow_e),
                                  __uint_as_float(ra_o + ca_o + oa_o), term(cw_oo * ow_o));
         }
         __syncwarp();
         // commit the 8 samples of the pass in sample order: lane (pr, pc, po) adds the one term of its class
         float2 term[8];
 #pragma unroll
-        for (int sidx = 0; sidx < 8; sidx++) term[sidx] = stage.e[sidx][l8];
+        for (int sidx = 0; sidx < 8; sidx++)  // class l8 of sample sidx: chunk l8 >> 1 (swizzled), half l8 & 1
+            term[sidx] = reinterpret_cast<const float2 *>(&stage.e[0][0])[2 * desc_stage_chunk(sidx, l8 >> 1) + (l8 & 1)];
 #pragma unroll
         for (int sidx = 0; sidx < 8; sidx++) {
             const unsigned sa = __float_as_uint(term[sidx].x);
@@ -469,21 +484,22 @@ __global__ void __launch_bounds__(256) k_size_order(const float4 *__restrict__ k
 // (plan.py:546-550); the survivors of octave o go to out[oct_offset[o] + ...], i.e. the output is grouped by
 // octave in octave order like the reference's concatenation (plan.py:555-565).
 template <bool GPUVAR>
-__global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe(OctTable T, const float4 *__restrict__ kp,
+__global__ void __launch_bounds__(DESC_WARPS * 32, 7) k_describe(OctTable T, const float4 *__restrict__ kp,
                                                                const int *__restrict__ kp_tag,
                                                                const int *__restrict__ n_order_p, int cap,
                                                                KpRecord *__restrict__ out, int out_cap,
                                                                const int *__restrict__ oct_offset,
                                                                int *__restrict__ oct_fill, int *__restrict__ queue,
                                                                const int *__restrict__ order) {
-    __shared__ float s_hist[DESC_WARPS][DESC_HROWS * 32];
-    __shared__ DescRows s_rows[DESC_WARPS * 4];
-    __shared__ DescStage s_stage[DESC_WARPS * 4];
-    __shared__ double s_exp[32];
+    __shared__ __align__(16) unsigned char s_raw[DESC_SMEM_BYTES];
+    float *hist = reinterpret_cast<float *>(s_raw) + (threadIdx.x >> 5) * (DESC_HROWS * 32);
+    DescStage &my_stage = *reinterpret_cast<DescStage *>(s_raw + DESC_SMEM_HIST + (threadIdx.x >> 5) * DESC_STAGE_WARP_BYTES +
+                                                         desc_stage_offset((threadIdx.x >> 3) & 3));
+    double *s_exp = reinterpret_cast<double *>(s_raw + DESC_SMEM_HIST + DESC_SMEM_STAGE);
+    DescRows &my_rows = reinterpret_cast<DescRows *>(s_raw + DESC_SMEM_HIST + DESC_SMEM_STAGE + DESC_SMEM_EXP)[threadIdx.x >> 3];
     if (threadIdx.x < 32) s_exp[threadIdx.x] = c_exp_t32[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31, l8 = lane & 7, obase = lane & 24;
-    float *hist = s_hist[threadIdx.x >> 5];
     const int n = min(*n_order_p, cap);
     // dynamic work queue: every warp fetches 4 keypoints at a time, so warps with small windows simply fetch
     // more often and the last wave is not quantised to the grid size
@@ -510,23 +526,25 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe(OctTable T, con
         if (slot >= out_cap) act = false;
         KpRecord *o = out + (act ? slot : 0);
         if (act && l8 == 0) { o->x = k.x; o->y = k.y; o->scale = k.z; o->angle = k.w; }
-        describe_octets<false, GPUVAR>(hist, s_rows[threadIdx.x >> 3], s_stage[threadIdx.x >> 3], s_exp, act, k, T.go[oct][sc - 1],
+        describe_octets<false, GPUVAR>(hist, my_rows, my_stage, s_exp, act, k, T.go[oct][sc - 1],
                         T.pitch[oct], T.w[oct], T.h[oct], T.octsize[oct], o->desc);
     }
 }
 
 // Stage-hook form: desc[i] for every input row (no filtering), single gradient plane
 template <bool GPUVAR>
-__global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe_rows(const float2 *__restrict__ go, int pitch, int w,
+__global__ void __launch_bounds__(DESC_WARPS * 32, 7) k_describe_rows(const float2 *__restrict__ go, int pitch, int w,
                                                                     int h, const float4 *__restrict__ kp, int n,
                                                                     int octsize, uint8_t *__restrict__ desc) {
-    __shared__ float s_hist[DESC_WARPS][DESC_HROWS * 32];
-    __shared__ DescRows s_rows[DESC_WARPS * 4];
-    __shared__ DescStage s_stage[DESC_WARPS * 4];
-    __shared__ double s_exp[32];
+    __shared__ __align__(16) unsigned char s_raw[DESC_SMEM_BYTES];
+    float *hist = reinterpret_cast<float *>(s_raw) + (threadIdx.x >> 5) * (DESC_HROWS * 32);
+    DescStage &my_stage = *reinterpret_cast<DescStage *>(s_raw + DESC_SMEM_HIST + (threadIdx.x >> 5) * DESC_STAGE_WARP_BYTES +
+                                                         desc_stage_offset((threadIdx.x >> 3) & 3));
+    double *s_exp = reinterpret_cast<double *>(s_raw + DESC_SMEM_HIST + DESC_SMEM_STAGE);
+    DescRows &my_rows = reinterpret_cast<DescRows *>(s_raw + DESC_SMEM_HIST + DESC_SMEM_STAGE + DESC_SMEM_EXP)[threadIdx.x >> 3];
     if (threadIdx.x < 32) s_exp[threadIdx.x] = c_exp_t32[threadIdx.x];
     __syncthreads();
-    float *hist = s_hist[threadIdx.x >> 5];
+
     const int noct = (gridDim.x * blockDim.x) >> 3;
     const int rounds = (n + noct - 1) / noct;
     int gid0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
@@ -537,7 +555,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32, 6) k_describe_rows(const floa
             k = kp[gid0];
             act = k.y >= 0.0f;
         }
-        describe_octets<true, GPUVAR>(hist, s_rows[threadIdx.x >> 3], s_stage[threadIdx.x >> 3], s_exp, act, k, go, pitch, w, h, octsize,
+        describe_octets<true, GPUVAR>(hist, my_rows, my_stage, s_exp, act, k, go, pitch, w, h, octsize,
                         desc + 128L * (act ? gid0 : 0));
     }
 }

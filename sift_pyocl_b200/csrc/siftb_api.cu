@@ -669,11 +669,11 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
                                           n_order, oct_valid, p->n_oct, oct_offset, p->c_nout(slot),
                                           p->c_oct(slot, 0) + 3);
         if (p->variant)
-            k_describe<true><<<148 * 6, DESC_WARPS * 32, 0, st>>>(p->table, p->kp, p->kp_tag, n_order, p->kp_cap,
+            k_describe<true><<<148 * 7, DESC_WARPS * 32, 0, st>>>(p->table, p->kp, p->kp_tag, n_order, p->kp_cap,
                                                                   p->outs[slot], p->out_cap, oct_offset, oct_fill,
                                                                   q_head, p->kp_order);
         else
-            k_describe<false><<<148 * 6, DESC_WARPS * 32, 0, st>>>(p->table, p->kp, p->kp_tag, n_order, p->kp_cap,
+            k_describe<false><<<148 * 7, DESC_WARPS * 32, 0, st>>>(p->table, p->kp, p->kp_tag, n_order, p->kp_cap,
                                                                    p->outs[slot], p->out_cap, oct_offset, oct_fill,
                                                                    q_head, p->kp_order);
         CKL();

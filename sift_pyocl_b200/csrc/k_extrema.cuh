@@ -224,7 +224,7 @@ struct PyrTable {
     int ext_bx[SIFTB_KOCT], ext_start[SIFTB_KOCT + 1];   // k_extrema_all: blocks per row of octave o, first block of octave o
     int n_oct;
 };
-__global__ void __launch_bounds__(128, 6) k_extrema_all(const PyrTable *__restrict__ T, int border, float gate) {
+__global__ void __launch_bounds__(128, 5) k_extrema_all(const PyrTable *__restrict__ T, int border, float gate) {
     int o = 0;
     const int n_oct = T->n_oct;
     while (o + 1 < n_oct && (int)blockIdx.x >= T->ext_start[o + 1]) o++;

@@ -8,16 +8,20 @@
 //   * candidates: per window row, the j-interval that can pass the reference's (rx, cx) test is computed in
 //     double with a rigorous bound on the fp32 evaluation error folded in; the candidates of all rows are
 //     packed back to back and lane l of the octet takes candidates l, l + 8, ... (8 per pass);
-//   * evaluation: each lane evaluates its candidate with the reference's exact fp32 expressions and stages, for
-//     each of the 8 parity classes (row&1, col&1, ori&1), ONE (bin address, value) term: a sample feeds up to 8
-//     bins (2 rows x 2 columns x 2 orientations of the trilinear interpolation) and those always differ in all
-//     three parities.  Missing terms are +0.0 on the class's home bin (an exact no-op: every term is >= +0);
+//   * evaluation: each lane evaluates its candidate with the reference's exact fp32 expressions -- straight-line
+//     code: a rejected sample is carried along with magnitude zero, and the histogram has a guard ring of cells so
+//     that the trilinear neighbours need no range test -- and stages, for each of the 8 parity classes (row&1,
+//     col&1, ori&1), ONE (bin address, value) term: a sample feeds 8 bins (2 rows x 2 columns x 2 orientations of
+//     the trilinear interpolation) and those always differ in all three parities.  Terms of rejected samples are
+//     +-0.0 (an exact no-op: every histogram term is >= +0);
 //   * commit: lane p owns parity class p and performs 8 unconditional `hist[addr] += value` steps per pass, in
 //     sample order: all lanes busy, bins of one sample never collide, and each bin receives its contributions
 //     in the reference's order.  (ori == 2*pi exactly puts both orientation terms into bin 0; the second one is
 //     cweight * 0 = +0 there, so one add suffices.)
 //   * finish: L2 normalisation / 0.2 clamp / renormalisation / x512 -> uint8; the two
 //     sums of squares are accumulated sequentially by one lane of the octet (order matters).
+// The same code, compiled with GPUVAR, reproduces keypoints_gpu2.cl instead (fixed [-64, 64)^2 window, integer
+// accumulation of (uint)(100000 * term), halving-tree norms, uchar wrap): see describe_octets.
 // Also performs the host-side NaN filtering and record assembly of plan.py:546-565.
 #pragma once
 #include "common.cuh"

@@ -1,13 +1,14 @@
-// siftb_api.cu -- C ABI of libsiftb200.so (see include/siftb.h) and the host-side orchestration
-// that replaces sift-src/plan.py:432-756 (keypoints / _one_octave), match.py:200-272 and the
-// transform launch of alignment.py:329-349.
+// siftb_api.cu -- C ABI of libsiftb200.so (see include/siftb.h), first translation unit: the SiftPlan path --
+// the host-side orchestration that replaces sift-src/plan.py:432-756 (keypoints / _one_octave) -- the warp of the
+// frame a plan holds (alignment.py:329-349) and the stage-level test hooks.  (siftb_match.cu: MatchPlan, the
+// stateless warps, the NCCL helpers.)
 //
 // Differences from the reference's control flow (results identical):
 //   * no host round trips inside an image: every count stays on the device and drives the next
 //     kernel through grid-stride loops; one D->H copy of the counters and one of the records at the end;
-//   * the three scales of an octave are processed by single launches (extrema, gradient, orientation,
-//     descriptor), so records of one octave are not grouped by scale (the reference's order inside a
-//     scale group is already nondeterministic: atomic_inc);
+//   * the whole pyramid (every octave keeps its own planes) is built first; extrema, refinement, gradient planes,
+//     orientation and descriptors then run ONCE per image over all octaves and scales, so records of one octave are
+//     not grouped by scale (the reference's order inside a scale group is already nondeterministic: atomic_inc);
 //   * blur + DoG + decimation are one kernel per scale instead of four.
 #include <cuda_runtime.h>
 #include <math.h>

@@ -4,13 +4,25 @@
 #include <stdint.h>
 #include <string.h>
 // CPU check of the fast atan2 used by k_gradient (sift_pyocl_b200/csrc/common.cuh: cr_atan2f_fast) against glibc:
-// gcc -O2 -mfma -ffp-contract=off -o tools/atan2_check tools/atan2_check.c -lm && tools/atan2_check 200000000 [t-perturbation, e.g. 1.000001]
+// gcc -O2 -mfma -ffp-contract=off -o tools/atan2_check tools/atan2_check.c -lm && tools/atan2_check 200000000 [t-perturbation, e.g. 1.000001] [seed-perturbation, e.g. 1.0000005]
+// The division r = num / den is the device's sequence: reciprocal seed, two Newton steps, quotient, one residual
+// correction.  The hardware seed (MUFU.RCP64H, ~20 good bits) is not reproducible on the host: SEEDPERT scales a
+// 24-bit seed so that runs with 1 - 2^-21, 1 and 1 + 2^-21 bracket whatever the hardware returns; the corrected
+// quotient is the same for all of them except on near-ties of the division (last argument).
 static const int NI = 16;
 // build with -ffp-contract=off (the device code is compiled with -fmad=false)
 static double C[17], ATC[17], TB[17];
 static void init(void){ for(int k=0;k<=NI;k++){ double a = (M_PI/4)*k/NI; C[k]=tan(a); ATC[k]=a; }
   for(int k=0;k<NI;k++){ TB[k]=tan((M_PI/4)*(k+0.5)/NI);} }
 static float TPERT = 1.0f;
+static double SEEDPERT = 1.0;
+static inline double dev_div(double num, double den){
+  double y = (double)(float)(1.0/den) * SEEDPERT;            /* seed: ~2^-21 relative error at worst */
+  y = fma(y, fma(-den, y, 1.0), y);
+  y = fma(y, fma(-den, y, 1.0), y);
+  double r = num * y;
+  return fma(fma(-den, r, num), y, r);
+}
 static inline double fast_atan2(float yf, float xf){
   double x=xf,y=yf; double ax=fabs(x), ay=fabs(y);
   double hi = ax>ay?ax:ay, lo = ax>ay?ay:ax;
@@ -22,7 +34,7 @@ static inline double fast_atan2(float yf, float xf){
        (2 ulp), so a neighbouring k may be picked next to a boundary: KSHIFT = -1/0/+1 forces that here */
     int k; { float lof=(float)lo, hif=(float)hi; float t = lof/hif; t = t*TPERT; k = (int)(t*(21.5615f + -5.5615f*t) + 0.5f); if(k>16)k=16; if(k<0)k=0; }
     double c=C[k];
-    double r = fma(-c,hi,lo)/fma(c,lo,hi);
+    double r = dev_div(fma(-c,hi,lo), fma(c,lo,hi));
     double r2=r*r;
     double p = fma(r2,-1.0/11.0,1.0/9.0); p=fma(r2,p,-1.0/7.0); p=fma(r2,p,1.0/5.0); p=fma(r2,p,-1.0/3.0); p=p*r2;
     a = ATC[k] + fma(r,p,r);
@@ -31,7 +43,7 @@ static inline double fast_atan2(float yf, float xf){
   if (signbit(x)) a = M_PI - a;
   return copysign(a, y);
 }
-int main(int argc,char**argv){ init(); if(argc>2) TPERT=(float)atof(argv[2]); long n = argc>1?atol(argv[1]):100000000; uint64_t s=88172645463325252ULL; long mism=0; double maxulp=0;
+int main(int argc,char**argv){ init(); if(argc>2) TPERT=(float)atof(argv[2]); if(argc>3) SEEDPERT=atof(argv[3]); long n = argc>1?atol(argv[1]):100000000; uint64_t s=88172645463325252ULL; long mism=0; double maxulp=0;
   for(long i=0;i<n;i++){ s^=s<<13; s^=s>>7; s^=s<<17; uint32_t a=(uint32_t)s, b=(uint32_t)(s>>32);
     float x,y; // mix of scales: gradients are differences of floats in [0,255]
     int mode = i&3;

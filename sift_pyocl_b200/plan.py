@@ -176,14 +176,54 @@ class SiftPlan(object):
             image = numpy.ascontiguousarray(image)
         return _lib.ptr(image), flags, image
 
-    def _records(self):
-        if self._out is None:
-            try:  # page-locked: the D->H copy of the records runs at full PCIe speed
-                self._out = _lib.pinned_empty((self._capacity,), self.dtype_kp)
+    def _records(self, n):
+        """Page-locked staging buffer for the D->H copy of ``n`` records (full PCIe speed).  It grows on demand: a
+        buffer for the plan's whole capacity (2 * kpsize records = 483 MB of pinned memory at 4096 x 4096, 1.9 GB at
+        8192 x 8192) would be two orders of magnitude more than images produce."""
+        if self._out is None or self._out.shape[0] < n:
+            if getattr(self, "_out_pinned", False):
+                _lib.pinned_free(self._out)
+            want = min(self._capacity, max(16384, int(1.5 * n)))
+            try:
+                self._out = _lib.pinned_empty((want,), self.dtype_kp)
                 self._out_pinned = True
             except Exception:
-                self._out = numpy.empty(self._capacity, dtype=self.dtype_kp)
+                self._out = numpy.empty(want, dtype=self.dtype_kp)
+                self._out_pinned = False
         return self._out
+
+    def _collect_locked(self, records):
+        """Wait for the oldest image in flight; returns its keypoints (or their number when ``records`` is false)."""
+        lib = _lib.load()
+        n = ctypes.c_int()
+        mm = numpy.zeros(2, numpy.float32)
+        rc = lib.siftb_plan_collect(self._plan, None, 0, ctypes.byref(n), self.last_counts.ctypes.data_as(_lib.c_int_p),
+                                    mm.ctypes.data_as(_lib.c_float_p))
+        if rc == _lib.SIFTB_EOVERFLOW:
+            logger.warning("Keypoint counter overflow risk: counted %s / %s" % (n.value, self.kpsize))  # plan.py:771
+        else:
+            _lib.check(rc)
+        self.buffers["min"].value[0], self.buffers["max"].value[0] = mm[0], mm[1]
+        self._last_n = min(n.value, self._capacity)
+        if not records:
+            return self._last_n
+        for octave, cnt in enumerate(self.last_counts):
+            logger.info("in octave %i found %i kp" % (octave, cnt))  # plan.py:543
+        if self.profile:
+            self._fetch_events()
+        return self._fetch_locked()
+
+    def _fetch_locked(self):
+        """Host recarray of the records of the most recently collected image."""
+        n = self._last_n
+        out = self._records(n)
+        got = ctypes.c_int()
+        _lib.check(_lib.load().siftb_plan_fetch_records(self._plan, _lib.ptr(out), n, ctypes.byref(got)))
+        # fresh host array for the caller; copied as raw bytes (numpy copies a structured array field by field,
+        # 4x slower than the memcpy this is)
+        res = numpy.empty(got.value, dtype=self.dtype_kp)
+        numpy.copyto(res.view(numpy.uint8), out[:got.value].view(numpy.uint8))
+        return res.view(numpy.recarray)
 
     def keypoints(self, image):
         """Calculates the keypoints of the image (reference plan.py:432-567).
@@ -197,37 +237,13 @@ class SiftPlan(object):
             t0 = time.time()
             assert self._pending == 0, "images are in flight: collect() them first"
             pointer, flags, keep = self._image_args(image)
-            lib = _lib.load()
-            out = self._records()
-            n = ctypes.c_int()
-            mm = numpy.zeros(2, numpy.float32)
-            rc = lib.siftb_plan_keypoints(self._plan, pointer, flags, _lib.ptr(out), self._capacity, ctypes.byref(n),
-                                          self.last_counts.ctypes.data_as(_lib.c_int_p),
-                                          mm.ctypes.data_as(_lib.c_float_p))
+            _lib.check(_lib.load().siftb_plan_submit(self._plan, pointer, flags))
+            output = self._collect_locked(True)
             del keep
-            output = self._finish(rc, n.value, mm)
             logger.info("Execution time: %.3fms" % (1000 * (time.time() - t0)))
         return output
 
     __call__ = keypoints
-
-    def _finish(self, rc, n, mm):
-        if rc == _lib.SIFTB_EOVERFLOW:
-            logger.warning("Keypoint counter overflow risk: counted %s / %s" % (n, self.kpsize))  # plan.py:771
-        else:
-            _lib.check(rc)
-        self.buffers["min"].value[0], self.buffers["max"].value[0] = mm[0], mm[1]
-        for octave, cnt in enumerate(self.last_counts):
-            logger.info("in octave %i found %i kp" % (octave, cnt))  # plan.py:543
-        n = min(n, self._capacity)
-        self._last_n = n
-        if self.profile:
-            self._fetch_events()
-        # fresh host array for the caller; copied as raw bytes (numpy copies a structured array field by field,
-        # 4x slower than the memcpy this is)
-        res = numpy.empty(n, dtype=self.dtype_kp)
-        numpy.copyto(res.view(numpy.uint8), self._out[:n].view(numpy.uint8))
-        return res.view(numpy.recarray)
 
     # -- split form, for callers that overlap copies with compute (no reference equivalent) -----
     def submit(self, image):
@@ -250,20 +266,7 @@ class SiftPlan(object):
         with self._sem:
             assert self._pending > 0, "collect() without submit()"
             try:
-                lib = _lib.load()
-                n = ctypes.c_int()
-                mm = numpy.zeros(2, numpy.float32)
-                out = _lib.ptr(self._records()) if records else None
-                rc = lib.siftb_plan_collect(self._plan, out, self._capacity, ctypes.byref(n),
-                                            self.last_counts.ctypes.data_as(_lib.c_int_p),
-                                            mm.ctypes.data_as(_lib.c_float_p))
-                if not records:
-                    if rc != _lib.SIFTB_EOVERFLOW:
-                        _lib.check(rc)
-                    self.buffers["min"].value[0], self.buffers["max"].value[0] = mm[0], mm[1]
-                    self._last_n = min(n.value, self._capacity)
-                    return self._last_n
-                return self._finish(rc, n.value, mm)
+                return self._collect_locked(records)
             finally:
                 self._pending -= 1
                 self._keep.pop(0)
@@ -313,12 +316,7 @@ class SiftPlan(object):
     def fetch_keypoints(self):
         """Host recarray of the keypoints of the last run (for callers that used ``collect(records=False)``)."""
         with self._sem:
-            out = self._records()
-            n = ctypes.c_int()
-            _lib.check(_lib.load().siftb_plan_fetch_records(self._plan, _lib.ptr(out), self._capacity, ctypes.byref(n)))
-            res = numpy.empty(n.value, dtype=self.dtype_kp)
-            numpy.copyto(res.view(numpy.uint8), out[:n.value].view(numpy.uint8))
-        return res.view(numpy.recarray)
+            return self._fetch_locked()
 
     def warp_last(self, matrix, offset, fill, out_shape=None, mode=1, out=None):
         """Affine warp (transform.cl:22 / :116) of the image of the last run, which is still on the device: the

@@ -228,9 +228,13 @@ def main():
         torch.cuda.synchronize()
 
     # warm-up; at N > 1 the ranks also agree on the slab size of the per-step record exchange
+    # (pipelined like the timed steps: the plan allocates the planes of its second compute lane the first time two
+    # images are in flight together)
     n_max = 0
+    plan.submit(dev_imgs[0])
     for i in range(args.warmup):
-        plan.submit(dev_imgs[i % N_IMAGES])
+        if i + 1 < args.warmup:
+            plan.submit(dev_imgs[(i + 1) % N_IMAGES])
         n_max = max(n_max, plan.collect(records=False))
     exchange = None
     if world > 1:

@@ -213,9 +213,10 @@ template <bool GPUVAR>
 __global__ void __launch_bounds__(256) k_orient(OctTable T, float4 *__restrict__ kp, int *__restrict__ kp_tag,
                                                  const int *__restrict__ n_base_p, int *__restrict__ n_extra, int cap,
                                                  float OriSigma, int *__restrict__ stage, int *__restrict__ oct_valid,
-                                                 int *__restrict__ size_hist) {
+                                                 int *__restrict__ size_hist, int *__restrict__ q_head) {
     __shared__ float s_hist[8][36];
-    __shared__ int s_clo[8][ORI_MAXROWS], s_chi[8][ORI_MAXROWS];
+    // per window row: x = packed index of the row's first candidate, y = (first column) - x; two sentinel rows
+    __shared__ int2 s_rows[8][ORI_MAXROWS + 3];
     // per-CTA partial counters, added to the global ones once at the end (one keypoint = three increments on a handful
     // of hot addresses otherwise: ~2e5 same-address atomics per image)
     __shared__ int s_stage[SIFTB_KOCT * 9], s_valid[SIFTB_KOCT], s_size[DESC_CLASSES];
@@ -224,11 +225,19 @@ __global__ void __launch_bounds__(256) k_orient(OctTable T, float4 *__restrict__
     for (int i = threadIdx.x; i < DESC_CLASSES; i += blockDim.x) s_size[i] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    int *clo = s_clo[wib], *chi = s_chi[wib];
+    int2 *rows = s_rows[wib];
     const int n_base = min(*n_base_p, cap);
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
     float *hist = s_hist[wib];
-    for (int gid0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; gid0 < n_base; gid0 += nwarps) {
+    // Keypoints are handed out one at a time from a queue (*q_head, zero at launch): window sizes differ by 4x, and with
+    // a fixed keypoint -> warp assignment the warps finished spread over the last quarter of the kernel (ncu: 14 % of
+    // the warp samples sat at the final barrier).  The next index is requested before the current keypoint is processed.
+    auto fetch = [&]() {
+        int v = 0;
+        if (lane == 0) v = atomicAdd(q_head, 1);
+        return __shfl_sync(0xffffffffu, v, 0);
+    };
+    for (int gid0 = fetch(), gid_next; gid0 < n_base; gid0 = gid_next) {
+        gid_next = fetch();
         float4 k = kp[gid0];
         const int tag = kp_tag[gid0];
         const int sc = tag & 0xff, oct = tag >> 8;
@@ -257,49 +266,70 @@ __global__ void __launch_bounds__(256) k_orient(OctTable T, float4 *__restrict__
         const bool chord = nrows <= ORI_MAXROWS;  // warp-uniform
         int total = (ncols > 0 && nrows > 0) ? ncols * nrows : 0;
         if (chord && total > 0) {
-            int mine = 0;
-            for (int rr = lane; rr < nrows; rr += 32) {
-                const double drd = (double)(rmin + rr) - (double)k.y;
-                const double hw2 = (double)rad2 * 1.00001 - drd * drd * 0.99999 + 1e-3;
-                int lo = 1, hi = 0;  // empty
-                if (hw2 > 0.0) {
-                    const double hw = sqrt(hw2);
-                    lo = max(cmin, (int)ceil((double)k.z - hw));
-                    hi = min(cmax, (int)floor((double)k.z + hw));
-                    if (hi < lo) { lo = 1; hi = 0; }
+            int base = 0;
+            for (int r0 = 0; r0 < nrows; r0 += 32) {  // warp-uniform trip count
+                const int rr = r0 + lane;
+                int lo = 0, len = 0;
+                if (rr < nrows) {
+                    const double drd = (double)(rmin + rr) - (double)k.y;
+                    const double hw2 = (double)rad2 * 1.00001 - drd * drd * 0.99999 + 1e-3;
+                    if (hw2 > 0.0) {
+                        const double hw = sqrt(hw2);
+                        lo = max(cmin, (int)ceil((double)k.z - hw));
+                        len = max(0, min(cmax, (int)floor((double)k.z + hw)) - lo + 1);
+                    }
                 }
-                clo[rr] = lo;
-                chi[rr] = hi;
-                mine += hi - lo + 1;
+                int incl = len;  // inclusive prefix sum over the 32 rows of this chunk
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int up = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += up;
+                }
+                const int start = base + incl - len;
+                if (rr < nrows) rows[rr] = make_int2(start, lo - start);
+                base += __shfl_sync(0xffffffffu, incl, 31);
             }
-            total = __reduce_add_sync(0xffffffffu, mine);
+            total = base;
+            if (lane < 3) rows[nrows + lane] = make_int2(lane == 0 ? total : 0x7fffffff, 0);
         }
         __syncwarp();
-        // Per-lane cursor over the candidates in row-major order: lane l takes candidates l, l + 32, ...  The
-        // gradient / orientation values of chunk c+1 are requested before chunk c is evaluated and committed
-        // (L2 / DRAM gathers: ncu showed the warps mostly waiting on these loads).
+        // Per-lane cursor over the candidates in row-major order: lane l takes candidates l, l + 32, ... (packed index
+        // `cand`); its row is found by walking the row table forward, two rows per probe.  The gradient / orientation
+        // values of chunk c+1 are requested before chunk c is evaluated and committed (L2 / DRAM gathers: ncu showed
+        // the warps mostly waiting on these loads).
         float n_gval = 0.0f, n_ang = 0.0f;
-        int rcur = -1, ccur = lane, cend = -1, n_r = 0, n_c = 0;
+        int rcur = 0, cur_off = 0, cand = lane, n_r = 0, n_c = 0;
         bool n_ok = false;
+        if (chord && total > 0) cur_off = rows[0].y;
         auto locate = [&]() {
-            while (ccur > cend && rcur < nrows) {  // into the next row(s); empty rows are stepped over
-                const int over = ccur - cend - 1;
-                rcur++;
-                if (rcur < nrows) {
-                    const int lo = chord ? clo[rcur] : cmin;
-                    cend = chord ? chi[rcur] : cmax;
-                    ccur = lo + over;
+            n_ok = cand < total;
+            if (chord) {
+                if (total > 0) {
+                    int2 e1 = rows[rcur + 1], e2 = rows[rcur + 2];
+                    while (cand >= e2.x) {
+                        rcur += 2;
+                        cur_off = e2.y;
+                        e1 = rows[rcur + 1];
+                        e2 = rows[rcur + 2];
+                    }
+                    if (cand >= e1.x) {
+                        rcur++;
+                        cur_off = e1.y;
+                    }
                 }
+                n_r = rmin + rcur;
+                n_c = cand + cur_off;
+            } else if (n_ok) {
+                const int rr = cand / ncols;
+                n_r = rmin + rr;
+                n_c = cmin + (cand - rr * ncols);
             }
-            n_ok = rcur < nrows && total > 0;
-            n_r = rmin + rcur;
-            n_c = ccur;
             if (n_ok) {
                 const float2 v = __ldg(go + ((long)n_r * Gpitch + n_c));
                 n_gval = v.x;
                 n_ang = v.y;
             }
-            ccur += 32;
+            cand += 32;
         };
         locate();
         for (int base = 0; base < total; base += 32) {

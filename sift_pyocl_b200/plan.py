@@ -118,7 +118,6 @@ class SiftPlan(object):
             w, h = ctypes.c_int(), ctypes.c_int()
             lib.siftb_plan_octave_shape(handle, o, ctypes.byref(w), ctypes.byref(h))
             self.scales.append((numpy.int32(w.value), numpy.int32(h.value)))
-        self.memory = int(lib.siftb_plan_device_bytes(handle))
         self.queue = lib.siftb_plan_stream(handle)
         if self.profile:
             lib.siftb_plan_set_profile(handle, 1)
@@ -129,6 +128,12 @@ class SiftPlan(object):
         self._keep = []
         logger.info("SiftPlan %s %s on CUDA device %d: %d octaves, kpsize %d, %.1f MB", self.shape, self.dtype,
                     self.device, self.octave_max, self.kpsize, self.memory / 1e6)
+
+    @property
+    def memory(self):
+        """Device memory held by the plan, bytes (reference plan.py:226 _calc_memory).  Grows once, by the planes
+        of a second image, the first time two images are in flight together (submit() / keypoints_many())."""
+        return int(_lib.load().siftb_plan_device_bytes(self._plan)) if self._plan else 0
 
     def __del__(self):
         """Destructor: release all buffers (reference plan.py:203-211)."""

@@ -269,6 +269,30 @@ def test_keypoints_many_drains_when_abandoned(sift, oracle):
     assert same_records(plan.keypoints(imgs[4]), oracle.keypoints(imgs[4]))
 
 
+def test_two_lanes_images_processed_concurrently(sift, oracle, monkeypatch):
+    """Images in flight together alternate between the plan's two compute streams (each with its own planes and
+    lists); every result must equal the one-image-at-a-time result, for converted (uint8) input too."""
+    rng = np.random.default_rng(5)
+    imgs = [ms(1024, 90 + i) for i in range(6)]
+    lo, hi = min(i.min() for i in imgs), max(i.max() for i in imgs)
+    imgs8 = [((i - lo) / (hi - lo) * 255).astype(np.uint8) for i in imgs]
+    want = [oracle.keypoints(i) for i in imgs8]
+    plan = sift.SiftPlan(shape=imgs8[0].shape, dtype=np.uint8)
+    one_lane_bytes = plan.memory
+    for _ in range(2):       # second round: both lanes exist already
+        got = list(plan.keypoints_many(imgs8))
+        assert all(same_records(g, w) for g, w in zip(got, want))
+    assert plan.memory > 1.5 * one_lane_bytes            # the second lane was allocated on demand
+    assert same_records(plan.keypoints(imgs8[2]), want[2])       # and the one-image path still works
+    del rng
+    # SIFTB_LANES=1: every image on one compute stream, no second set of planes
+    monkeypatch.setenv("SIFTB_LANES", "1")
+    single = sift.SiftPlan(shape=imgs8[0].shape, dtype=np.uint8)
+    got = list(single.keypoints_many(imgs8[:4]))
+    assert all(same_records(g, w) for g, w in zip(got, want))
+    assert single.memory == one_lane_bytes
+
+
 # ---- keypoint buffer overflow: clean truncation (reference only warns, plan.py:771) ------------------------
 def test_overflow_truncates_cleanly(sift, oracle):
     img = ms(512, 81)

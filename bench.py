@@ -246,26 +246,35 @@ def main():
             n = plan.collect(records=False)
             exchange.begin(sdist.device_records_tensor(plan, n), plan).finish()
 
-    def device_region(profile):
-        """K steps, device-resident input, records left on the device; software-pipelined: step i+1 is enqueued
-        before step i is collected, the exchange of step i (N > 1) is completed one step later."""
+    host_x = [0.0]
+
+    def device_region(profile, gather=True):
+        """K steps, device-resident input, records left on the device; software-pipelined: three images are in
+        flight (the plan's two compute lanes + one queued), the exchange of step i (N > 1) is completed one step
+        later."""
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         nkp, blur_ms, blur0_ms, first_ms, stage_ms = 0, 0.0, 0.0, 0.0, {}
         barrier()
         ev0.record(stream)
         t0 = time.perf_counter()
         pending = None
-        plan.submit(dev_imgs[0])
+        # images in flight (3 = what SiftPlan.keypoints_many keeps; with the all-gather's host work in the loop, 2 left
+        # a lane idle now and then: 1.89 instead of 1.82 ms per step at 2 GPUs)
+        depth = int(os.environ.get("SIFTB_BENCH_DEPTH", "3"))
+        for j in range(min(depth, args.steps)):
+            plan.submit(dev_imgs[j % N_IMAGES])
         for i in range(args.steps):
-            if i + 1 < args.steps:
-                plan.submit(dev_imgs[(i + 1) % N_IMAGES])
             n = plan.collect(records=False)
+            if i + depth < args.steps:
+                plan.submit(dev_imgs[(i + depth) % N_IMAGES])
             nkp += n
-            if exchange is not None:
+            if exchange is not None and gather:
+                th = time.perf_counter()
                 started = exchange.begin(sdist.device_records_tensor(plan, n), plan)
                 if pending is not None:
                     pending.finish()
                 pending = started
+                host_x[0] += time.perf_counter() - th
             if profile:
                 for name, ms in plan.fetch_events():
                     key = name.split(" octave")[0]
@@ -320,6 +329,8 @@ def main():
     launches0 = plan.launches
     regions = [device_region(False) for _ in range(max(args.repeats, 1))]
     launches = (plan.launches - launches0) // max(args.repeats, 1)
+    # throughput with and without the gather (the images are independent: the exchange is the only collective)
+    nogather = [device_region(False, gather=False) for _ in range(3)] if world > 1 else None
     plan.set_profile(True)   # stage breakdown + roofline launches: a separate region (event pairs cost ~1 %)
     prof = device_region(True)
     plan.set_profile(False)
@@ -335,13 +346,14 @@ def main():
     dev_s, nkp, wall = median_by(regions, lambda r: r[0])[:3]
     e2e_s, e2e_kp, d2h = median_by(e2e_regions, lambda r: r[0])
     all_dev_s = [r[0] for r in regions]
+    ng_s = median_by(nogather, lambda r: r[0])[0] if nogather else 0.0
     if world > 1:
-        t = torch.tensor([dev_s, e2e_s, sync_s, float(nkp), float(e2e_kp), float(launches), float(sync_kp)],
+        t = torch.tensor([dev_s, e2e_s, sync_s, float(nkp), float(e2e_kp), float(launches), float(sync_kp), ng_s],
                          dtype=torch.float64, device="cuda")
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        dev_s, e2e_s, sync_s = float(tmax[0]), float(tmax[1]), float(tmax[2])
+        dev_s, e2e_s, sync_s, ng_s = float(tmax[0]), float(tmax[1]), float(tmax[2]), float(tmax[7])
         nkp, e2e_kp, launches, sync_kp = float(t[3]), float(t[4]), int(t[5]), float(t[6])
     if rank != 0:
         if world > 1:
@@ -392,6 +404,11 @@ def main():
         "wall_ms_per_step": 1e3 * wall / args.steps,
         "clocks": sampler.summary(),
     }
+    if world > 1:
+        line["exchange_host_ms_per_step"] = 1e3 * host_x[0] / (args.steps * (len(regions) + 1))
+        line["without_gather"] = {"value": nkp / ng_s, "ms_per_step": 1e3 * ng_s / args.steps,
+                                  "note": "the same device-resident region without the per-step all-gather of the "
+                                          "records (every rank keeps its own keypoints)"}
     if not args.no_cpu_baseline and world == 1:
         from oracle import siftref
         img = np.array(host_imgs[0])

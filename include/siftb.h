@@ -92,6 +92,10 @@ SIFTB_API int siftb_plan_device(const siftb_plan *plan);               /* CUDA o
  * external stream has been asked to read siftb_plan_result_dev() memory.  Replaces the implicit ordering of the
  * reference's single in-order command queue shared with its pyopencl.array inputs (plan.py:185-188,451). */
 SIFTB_API int siftb_plan_wait_stream(siftb_plan *plan, void *stream);
+/* Narrower form for readers of siftb_plan_result_dev() memory: the record buffer of the most recently collected
+ * image is not rewritten before the work enqueued so far on `stream` has finished.  Only the submit that recycles
+ * that buffer (the third from now) waits; images already queued, and the next ones, are not held up. */
+SIFTB_API int siftb_plan_hold_records(siftb_plan *plan, void *stream);
 /* number of CUDA kernels this plan has launched since it was created (bench.py's gpu_launches) */
 SIFTB_API uint64_t siftb_plan_launches(const siftb_plan *plan);
 

@@ -50,6 +50,7 @@ SIGNATURES = {
     "siftb_plan_set_variant": (c_int, [c_void_p, c_int]),
     "siftb_plan_launches": (c_u64, [c_void_p]),
     "siftb_plan_device": (c_int, [c_void_p]),
+    "siftb_plan_hold_records": (c_int, [c_void_p, c_void_p]),
     "siftb_plan_wait_stream": (c_int, [c_void_p, c_void_p]),
     "siftb_plan_keypoints": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int_p, c_int_p, c_float_p]),
     "siftb_plan_submit": (c_int, [c_void_p, c_void_p, c_int]),

@@ -158,6 +158,8 @@ struct siftb_plan {
     cudaStream_t d2h_stream = nullptr;   // device -> host record copies (PCIe is full duplex: never queued behind an upload)
     cudaEvent_t ev_h2d[NSLOT] = {}, ev_done[NSLOT] = {}, ev_d2h[NSLOT] = {};
     cudaEvent_t ev_ext = nullptr;  // siftb_plan_wait_stream
+    cudaEvent_t ev_hold[NSLOT] = {};  // siftb_plan_hold_records: readers of outs[slot] on other streams
+    bool held[NSLOT] = {};
     const void *src_ptr[NSLOT] = {};  // device pointer of the image submitted to each slot, and its pixel type
     int src_dtype[NSLOT] = {};
     GrowBuf d_warp;                   // output of siftb_plan_warp_last
@@ -255,6 +257,7 @@ extern "C" int siftb_plan_destroy(siftb_plan *p) {
         if (p->ev_h2d[s]) cudaEventDestroy(p->ev_h2d[s]);
         if (p->ev_done[s]) cudaEventDestroy(p->ev_done[s]);
         if (p->ev_d2h[s]) cudaEventDestroy(p->ev_d2h[s]);
+        if (p->ev_hold[s]) cudaEventDestroy(p->ev_hold[s]);
     }
     if (p->ev_ext) cudaEventDestroy(p->ev_ext);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
@@ -358,6 +361,7 @@ static int plan_create_impl(siftb_plan *p) {
         CK(cudaEventCreateWithFlags(&p->ev_h2d[s], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&p->ev_done[s], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&p->ev_d2h[s], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&p->ev_hold[s], cudaEventDisableTiming));
     }
     CK(cudaEventCreateWithFlags(&p->ev_ext, cudaEventDisableTiming));
     // plan.py:213-224 _calc_scales
@@ -632,6 +636,10 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
     p->src_dtype[slot] = dtype;
     // the records of this slot's previous image must have left the device before they are overwritten
     CK(cudaStreamWaitEvent(st, p->ev_d2h[slot], 0));
+    if (p->held[slot]) {  // ... and external readers of that buffer must be done (siftb_plan_hold_records)
+        CK(cudaStreamWaitEvent(st, p->ev_hold[slot], 0));
+        p->held[slot] = false;
+    }
     CK(cudaMemsetAsync(p->d_cnts[slot], 0, p->cnt_ints * sizeof(int), st));
     int *aux = p->d_queue + slot * AUX_INTS;
     CK(cudaMemsetAsync(aux, 0, AUX_INTS * sizeof(int), st));
@@ -823,6 +831,14 @@ extern "C" int siftb_plan_wait_stream(siftb_plan *p, void *stream) {
     CK(cudaEventRecord(p->ev_ext, (cudaStream_t)stream));
     CK(cudaStreamWaitEvent(p->stream, p->ev_ext, 0));
     for (auto &L : p->lanes) CK(cudaStreamWaitEvent(L.stream, p->ev_ext, 0));
+    return 0;
+}
+extern "C" int siftb_plan_hold_records(siftb_plan *p, void *stream) {
+    if (!p) return fail(SIFTB_EINVAL, "null plan");
+    std::lock_guard<std::mutex> lk(p->mtx);
+    DeviceGuard dg_(p->device);
+    CK(cudaEventRecord(p->ev_hold[p->last], (cudaStream_t)stream));
+    p->held[p->last] = true;
     return 0;
 }
 extern "C" int siftb_plan_device(const siftb_plan *p) { return p ? p->device : SIFTB_EINVAL; }

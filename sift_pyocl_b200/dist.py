@@ -70,9 +70,10 @@ class _Pending(object):
     """One exchange in flight; owns references to the slabs it was started with (the exchange may enlarge its
     buffers while an older step is still pending)."""
 
-    def __init__(self, ex, send, recv, capacity, work, event, n_local, spill):
+    def __init__(self, ex, send, recv, capacity, work, event, n_local, spill, counts_host=None):
         self.ex, self.send, self.recv, self.capacity = ex, send, recv, capacity
         self.work, self.event, self.n_local, self.spill = work, event, n_local, spill
+        self.counts_host = counts_host
 
     def finish(self):
         """(list of per-rank uint8 tensors [n_r, 144], int64 counts).  The tensors alias the exchange's receive
@@ -83,7 +84,10 @@ class _Pending(object):
         if self.event is not None:
             self.event.synchronize()
         recv = self.recv
-        counts = recv[:, 0, :8].contiguous().view(torch.int64).reshape(-1).cpu()
+        if self.counts_host is not None:
+            counts = self.counts_host.view(torch.int64).reshape(-1).clone()
+        else:
+            counts = recv[:, 0, :8].contiguous().view(torch.int64).reshape(-1).cpu()
         if int(counts.max()) > self.capacity:
             # a rank produced more records than a slab holds (every rank sees the same counts, so all take this
             # branch together): exact-size blocking exchange of the full local arrays, and larger slabs from now on
@@ -120,6 +124,7 @@ class RecordExchange(object):
         self.send = [torch.zeros((rows, REC), dtype=torch.uint8, device=self.device) for _ in range(2)]
         self.recv = [torch.empty((self.world, rows, REC), dtype=torch.uint8, device=self.device) for _ in range(2)]
         self.header = [torch.zeros(1, dtype=torch.int64, pin_memory=self.cuda) for _ in range(2)]
+        self.counts_host = [torch.zeros((self.world, 8), dtype=torch.uint8, pin_memory=self.cuda) for _ in range(2)]
 
     def begin(self, local, plan=None):
         """Start the exchange of ``local`` (uint8 [n, 144]; may alias a plan's record buffer: pass ``plan`` so that
@@ -145,11 +150,20 @@ class RecordExchange(object):
             if n > self.capacity:
                 spill = local.clone()
             if plan is not None:  # the plan's next writer of this record buffer waits for the copies above
-                plan.wait_stream(self.stream.cuda_stream)
+                if hasattr(plan, "hold_records"):
+                    plan.hold_records(self.stream.cuda_stream)
+                else:
+                    plan.wait_stream(self.stream.cuda_stream)
             dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=self.group)
+            # the gathered counts travel to page-locked host memory by the copy engine: reading them in finish()
+            # then needs no kernel (a kernel, however small, queues behind the plan's persistent CTAs for SM space
+            # and stalled the host thread by up to a kernel's duration)
+            counts_host = self.counts_host[b]
+            for r in range(self.world):
+                counts_host[r].copy_(recv[r, 0, :8], non_blocking=True)
             event = torch.cuda.Event()
             event.record(self.stream)
-        return _Pending(self, send, recv, self.capacity, None, event, n, spill)
+        return _Pending(self, send, recv, self.capacity, None, event, n, spill, counts_host)
 
 
 def allgather_records_begin(local, group=None, exchange=None, plan=None):

@@ -310,6 +310,12 @@ class SiftPlan(object):
         input image, or still reads the plan's device-resident records (device_records())."""
         _lib.check(_lib.load().siftb_plan_wait_stream(self._plan, ctypes.c_void_p(int(stream))))
 
+    def hold_records(self, stream):
+        """The device-resident records of the last collected image (device_records()) are not overwritten before
+        the work enqueued so far on ``stream`` has finished.  Unlike wait_stream() this does not hold up the images
+        already queued or the next ones: only the submit() that recycles the buffer (the third from now) waits."""
+        _lib.check(_lib.load().siftb_plan_hold_records(self._plan, ctypes.c_void_p(int(stream))))
+
     def device_keypoints(self, n=None):
         """The keypoints of the last run as a device-resident array (``match.DeviceRecords``) -- what the reference
         gets by keeping results in a ``pyopencl.array`` (alignment.py:246-249); valid until the third submit()

@@ -265,18 +265,24 @@ def main():
             plan.submit(dev_imgs[j % N_IMAGES])
         for i in range(args.steps):
             n = plan.collect(records=False)
-            if i + depth < args.steps:
-                plan.submit(dev_imgs[(i + depth) % N_IMAGES])
             nkp += n
+            started = None
             if exchange is not None and gather:
                 th = time.perf_counter()
                 started = exchange.begin(sdist.device_records_tensor(plan, n), plan)
+                host_x[0] += time.perf_counter() - th
+            events = plan.fetch_events() if profile else ()
+            # (the next submit recycles the slot of the image just collected: its records and events are taken first)
+            if i + depth < args.steps:
+                plan.submit(dev_imgs[(i + depth) % N_IMAGES])
+            if started is not None:
+                th = time.perf_counter()
                 if pending is not None:
                     pending.finish()
                 pending = started
                 host_x[0] += time.perf_counter() - th
             if profile:
-                for name, ms in plan.fetch_events():
+                for name, ms in events:
                     key = name.split(" octave")[0]
                     stage_ms[key] = stage_ms.get(key, 0.0) + ms
                     if "blur" in name:

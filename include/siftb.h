@@ -94,7 +94,7 @@ SIFTB_API int siftb_plan_device(const siftb_plan *plan);               /* CUDA o
 SIFTB_API int siftb_plan_wait_stream(siftb_plan *plan, void *stream);
 /* Narrower form for readers of siftb_plan_result_dev() memory: the record buffer of the most recently collected
  * image is not rewritten before the work enqueued so far on `stream` has finished.  Only the submit that recycles
- * that buffer (the third from now) waits; images already queued, and the next ones, are not held up. */
+ * that buffer (the third after the one that produced these records) waits; images already queued, and the next ones, are not held up. */
 SIFTB_API int siftb_plan_hold_records(siftb_plan *plan, void *stream);
 /* number of CUDA kernels this plan has launched since it was created (bench.py's gpu_launches) */
 SIFTB_API uint64_t siftb_plan_launches(const siftb_plan *plan);
@@ -119,7 +119,9 @@ SIFTB_API int siftb_plan_keypoints(siftb_plan *plan, const void *image, int flag
 SIFTB_API int siftb_plan_submit(siftb_plan *plan, const void *image, int flags);
 SIFTB_API int siftb_plan_collect(siftb_plan *plan, siftb_kp *out, int cap, int *n_out, int *n_per_octave,
                        float *minmax);   /* out == NULL: wait and return the counts only (records stay on the device) */
-/* results left on the device (valid until the next submit): records, count */
+/* results of the most recently collected image, left on the device: records, count.  The plan cycles through three
+ * record buffers: this one is rewritten by the third submit after the one that produced it (see
+ * siftb_plan_hold_records for readers on other streams) */
 SIFTB_API int siftb_plan_result_dev(const siftb_plan *plan, const siftb_kp **dev_records, const int **dev_count);
 
 /* host copy of the records of the most recently collected run (for callers that collected with out == NULL) */

@@ -117,6 +117,17 @@ __device__ __forceinline__ float cr_atan2f_fast(float yf, float xf, const AtanCo
     return copysignf((float)a, yf);
 }
 
+// Read-only 8-byte load that stays where it is written: the software-pipelined gathers of k_orient / k_describe
+// request the values of step n+1 BEFORE step n is evaluated.  With a plain __ldg the compiler is free to sink the
+// load down to its first use, i.e. into the next iteration (it did, in one build of k_orient: 24 % of the warp samples
+// then sat on the first use of the value, 0.25 instead of 0.21 ms); a volatile asm is not moved across the
+// shuffles and shared-memory traffic of the step.
+__device__ __forceinline__ float2 ldg_f2_here(const float2 *p) {
+    float2 v;
+    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+
 // ---- correctly rounded fp32 division by a loop-invariant divisor -------------------------------------------
 // a / b == (float)((double)a * inv) with inv = 1.0 / (double)b: the double product is within 2^-52 (relative) of
 // the exact quotient, while a quotient of two 24-bit significands is either at least 2^-49 (relative) away from

@@ -210,9 +210,14 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
     // (keypoints_cpu.cl:63-65 evaluates them per sample; same operands, same fp32 products).  The gradient /
     // orientation values of the lane's sample of pass p+1 are requested before pass p is evaluated and committed,
     // so the L2 / DRAM gather latency overlaps the commit loop.
-    int rcur = -1, jcur = l8, jend = -1, n_i = 0, n_j = 0, rowoff = 0;
-    float n_g = 0.0f, n_o = 0.0f;
-    auto fetch = [&]() {
+    // (two sets of "next sample" values, A and B, used alternately by the pass loop unrolled twice by hand: with one
+    // set the compiler copies next -> current at the end of the iteration and that copy waits for the load)
+    struct Sample {
+        int i, j;
+        float g, o;
+    };
+    int rcur = -1, jcur = l8, jend = -1, n_i = 0, rowoff = 0;
+    auto fetch = [&](Sample &n) {
         while (jcur > jend && rcur < nrc) {  // into the next table row(s)
             const int over = jcur - jend - 1;
             rcur++;
@@ -228,24 +233,23 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
                 }
             }
         }
-        n_j = jcur;
-        n_g = 0.0f;  // past the end of the window: a sample of zero gradient, i.e. eight +-0 terms
-        n_o = 0.0f;
+        n.i = n_i;
+        n.j = jcur;
+        n.g = 0.0f;  // past the end of the window: a sample of zero gradient, i.e. eight +-0 terms
+        n.o = 0.0f;
         if (rcur < nrc) {
             rowoff = (irow + n_i) * pitch + icol;
-            const float2 v = __ldg(go + (rowoff + n_j));
-            n_g = v.x;
-            n_o = v.y;
+            const float2 v = ldg_f2_here(go + (rowoff + n.j));
+            n.g = v.x;
+            n.o = v.y;
         }
         jcur += 8;
     };
     // shared-memory byte address of bin (0, 0, 0) of my octet: the stage carries absolute addresses
     const unsigned hist_sa = (unsigned)__cvta_generic_to_shared(hist);
-    fetch();
-    for (int p = 0; p < passes_max; p++) {
-        const float fi = (float)n_i, fj = (float)n_j;
-        const float g_val = n_g, o_val = n_o;
-        fetch();
+    auto pass = [&](const Sample &cur) {
+        const float fi = (float)cur.i, fj = (float)cur.j;
+        const float g_val = cur.g, o_val = cur.o;
         // ---- evaluate (straight-line code: a rejected sample is carried along with magnitude zero) -------------
         // keypoints_cpu.cl:63-67
         const float rx = div_by((cosine * fi - sine * fj) - drow, inv_spacing) + 1.5f;
@@ -329,6 +333,15 @@ __device__ __forceinline__ void describe_octets(float *__restrict__ whist, DescR
             }
         }
         __syncwarp();
+    };
+    Sample sa, sb;
+    fetch(sa);
+    for (int p = 0; p < passes_max; p += 2) {
+        fetch(sb);
+        pass(sa);
+        if (p + 1 >= passes_max) break;  // warp-uniform
+        fetch(sa);
+        pass(sb);
     }
     __syncwarp();
     // finish, keypoints_cpu.cl:127-160: each lane of the octet owns 16 consecutive descriptor entries

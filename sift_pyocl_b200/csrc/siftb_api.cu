@@ -710,10 +710,10 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
     {
         ProfScope ps(p, "orientation_assignment");
         if (p->variant)
-            k_orient<true><<<148 * 4, 256, 0, st>>>(L.table, L.kp, L.kp_tag, n_kp, n_extra, p->kp_cap, kOriSigma,
+            k_orient<true><<<148 * 5, 256, 0, st>>>(L.table, L.kp, L.kp_tag, n_kp, n_extra, p->kp_cap, kOriSigma,
                                                     p->c_stage(slot, 0), oct_valid, size_hist, aux + 4);
         else
-            k_orient<false><<<148 * 4, 256, 0, st>>>(L.table, L.kp, L.kp_tag, n_kp, n_extra, p->kp_cap, kOriSigma,
+            k_orient<false><<<148 * 5, 256, 0, st>>>(L.table, L.kp, L.kp_tag, n_kp, n_extra, p->kp_cap, kOriSigma,
                                                      p->c_stage(slot, 0), oct_valid, size_hist, aux + 4);
         CKL();
         p->launches += 1;
@@ -1114,10 +1114,10 @@ extern "C" int siftb_orientation_v(const float *kp4_in, int n, const float *grad
     for (int i = 0; i < 3; i++) tb.go[0][i] = GO.as<float2>();
     tb.pitch[0] = width; tb.w[0] = width; tb.h[0] = height; tb.octsize[0] = octsize;
     if (variant)
-        k_orient<true><<<148 * 4, 256>>>(tb, K.as<float4>(), S.as<int>(), C.as<int>(), C.as<int>() + 1, cap, kOriSigma,
+        k_orient<true><<<148 * 5, 256>>>(tb, K.as<float4>(), S.as<int>(), C.as<int>(), C.as<int>() + 1, cap, kOriSigma,
                                          nullptr, nullptr, nullptr, C.as<int>() + 2);
     else
-        k_orient<false><<<148 * 4, 256>>>(tb, K.as<float4>(), S.as<int>(), C.as<int>(), C.as<int>() + 1, cap, kOriSigma,
+        k_orient<false><<<148 * 5, 256>>>(tb, K.as<float4>(), S.as<int>(), C.as<int>(), C.as<int>() + 1, cap, kOriSigma,
                                           nullptr, nullptr, nullptr, C.as<int>() + 2);
     CKL();
     CK(cudaMemcpy(cnt, C.p, 8, cudaMemcpyDeviceToHost));

@@ -313,13 +313,14 @@ class SiftPlan(object):
     def hold_records(self, stream):
         """The device-resident records of the last collected image (device_records()) are not overwritten before
         the work enqueued so far on ``stream`` has finished.  Unlike wait_stream() this does not hold up the images
-        already queued or the next ones: only the submit() that recycles the buffer (the third from now) waits."""
+        already queued or the next ones: only the submit() that recycles the buffer (the third after the one that produced these records) waits."""
         _lib.check(_lib.load().siftb_plan_hold_records(self._plan, ctypes.c_void_p(int(stream))))
 
     def device_keypoints(self, n=None):
         """The keypoints of the last run as a device-resident array (``match.DeviceRecords``) -- what the reference
         gets by keeping results in a ``pyopencl.array`` (alignment.py:246-249); valid until the third submit()
-        from now.  MatchPlan.match() accepts it directly, so the records never visit the host."""
+        after the one that produced them (the plan cycles through three record buffers).  MatchPlan.match() accepts it
+        directly, so the records never visit the host."""
         from .match import DeviceRecords
         recs, _ = self.device_records()
         return DeviceRecords(recs or 0, self._last_n if n is None else n, self.device, owner=self)

@@ -45,7 +45,7 @@ OCTAVES = 3
 N_IMAGES = 2  # distinct images cycled per rank (working set per image ~1.2 GB >> 126 MB L2)
 # dram__bytes_read.sum + dram__bytes_write.sum of all 16 blur launches of one step, summed from the committed
 # ncu --set full capture of the final kernels of the round (see TRAFFIC_NOTE); bytes per step
-TRAFFIC_PER_STEP = 1029.26e6
+TRAFFIC_PER_STEP = 1028.72e6
 TRAFFIC_NOTE = ("sum over the 16 blur launches of one step in profiles/r02_ncu_full_step_4096_3oct.csv (ncu --set full of "
                 "the round's final kernels), divided by 16; below the algorithmic 1455 MB because the planes of "
                 "octaves 1 and 2 are still dirty in the 126 MB L2 when their launches end")

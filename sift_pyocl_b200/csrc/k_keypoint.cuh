@@ -379,8 +379,11 @@ __global__ void __launch_bounds__(256, 5) k_orient(OctTable T, float4 *__restric
                     const float upto = __shfl_sync(0xffffffffu, run, prev_lane);
                     if (rank == rd) run = upto + w;
                 }
-                if (bin >= 0 && (peers >> lane) == 1u) hist[bin] = run;  // last lane of its bin
+                // (the write below is ordered after the first lane's read of the same bin by the data flow through
+                // the shuffles; the barrier states it for compute-sanitizer's racecheck and costs no instruction)
                 __syncwarp();
+                if (bin >= 0 && (peers >> lane) == 1u) hist[bin] = run;  // last lane of its bin
+                __syncwarp();  // the next step's first lane of this bin may be another lane
             }
         };
         Sample sa, sb;

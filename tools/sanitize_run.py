@@ -1,5 +1,6 @@
 """Small run of every kernel family for compute-sanitizer (memcheck / racecheck / initcheck): whole path in both
-kernel-family variants, windows beyond the descriptor row table, buffer overflow, matcher (short list, segmented
+kernel-family variants, windows beyond the descriptor row table, buffer overflow, pipelined images on the plan's two
+compute lanes, matcher (short list, segmented
 long list, two queries per thread, L2 metric, device-side gathers), LinearAlign (warp of the resident frame)."""
 import sys
 import numpy as np
@@ -19,6 +20,9 @@ for shape in ((300, 420), (513, 257)):
 img = multiscale_image(0, 6, (256, 320))
 print("init_sigma 3.0", sift.SiftPlan(template=img, init_sigma=3.0).keypoints(img).size)
 print("overflow", sift.SiftPlan(template=img, PIX_PER_KP=300).keypoints(img).size)
+plan = sift.SiftPlan(template=img)   # images in flight together: the plan's two compute lanes
+imgs = [multiscale_image(0, 7 + i, (256, 320)) for i in range(5)]
+print("two lanes", [k.size for k in plan.keypoints_many(imgs)], plan.memory)
 mp = sift.MatchPlan()
 print("matches", len(mp.match(kp, kp, raw_results=True)), mp.match(kp, kp).shape, mp.match_coords(kp, kp).shape)
 rng = np.random.default_rng(0)

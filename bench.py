@@ -22,9 +22,10 @@ BASELINE.json configs[1]: SiftPlan 4096x4096 float32, 3 octaves x 3 scales (par.
           ncu --set full capture (profiles/).
   cpu_baseline : the oracle (CPU port of the reference kernels, OpenMP) on the same image, all host
           threads and one thread.
-For N > 1 (torchrun) every rank runs the same per-GPU work on different images (weak scaling) and every
-step's keypoint records are all-gathered over NCCL (dist.RecordExchange: one collective per step on a
-side stream, completed one pipeline step later).
+For N > 1 (torchrun) every rank runs the same per-GPU work on different images (weak scaling).  The images are
+independent, so the data path has no collective and `value` / `e2e` have none; `with_gather` reports the same
+regions with every step's keypoint records all-gathered to every rank over NCCL (dist.RecordExchange: one
+collective per step on a side stream, completed one pipeline step later) -- SURVEY 8e asks for both.
 """
 import argparse
 import json
@@ -124,7 +125,8 @@ def _config(world):
             "image": "multiscale noise (sift_pyocl_b200.utils.multiscale_image), seeds 1234+",
             "l2": "inputs larger than L2: %d distinct 67 MB images cycled per GPU, ~1.2 GB of planes rewritten per step"
                   % N_IMAGES,
-            "gather": "NCCL all-gather of the keypoint records every step" if world > 1 else "none (1 GPU)"}
+            "gather": "none on the data path (independent images, one per GPU and step); the all-gather of the "
+                      "records is timed separately: with_gather" if world > 1 else "none (1 GPU)"}
 
 
 def _cpu_leg(siftref, img, threads, reps):
@@ -240,7 +242,7 @@ def main():
     if world > 1:
         cap = torch.tensor([n_max], dtype=torch.int64, device="cuda")
         dist.all_reduce(cap, op=dist.ReduceOp.MAX)
-        exchange = sdist.RecordExchange(int(int(cap.item()) * 1.3) + 1024, "cuda:%d" % local_rank)
+        exchange = sdist.RecordExchange(int(int(cap.item()) * 1.12) + 1024, "cuda:%d" % local_rank)
         for i in range(2):  # NCCL warm-up of the exchange itself
             plan.submit(dev_imgs[i % N_IMAGES])
             n = plan.collect(records=False)
@@ -248,7 +250,7 @@ def main():
 
     host_x = [0.0]
 
-    def device_region(profile, gather=True):
+    def device_region(profile, gather=False):
         """K steps, device-resident input, records left on the device; software-pipelined: three images are in
         flight (the plan's two compute lanes + one queued), the exchange of step i (N > 1) is completed one step
         later."""
@@ -293,7 +295,7 @@ def main():
                         first_ms += ms
         cur = torch.cuda.current_stream()
         cur.wait_stream(stream)
-        if exchange is not None:
+        if exchange is not None and gather:
             cur.wait_stream(exchange.stream)  # the last exchange belongs to the timed region
         ev1.record(cur)
         if pending is not None:
@@ -302,7 +304,7 @@ def main():
         wall = time.perf_counter() - t0
         return ev0.elapsed_time(ev1) / 1e3, nkp, wall, blur_ms, blur0_ms, first_ms, stage_ms
 
-    def e2e_region():
+    def e2e_region(gather=False):
         """K steps through the public API with HOST buffers: pinned image -> H2D -> kernels -> D2H records ->
         numpy recarray every step (SiftPlan.keypoints_many keeps three images in flight)."""
         barrier()
@@ -311,7 +313,7 @@ def main():
         for kp in plan.keypoints_many(host_imgs[i % N_IMAGES] for i in range(args.steps)):
             e2e_kp += kp.size
             d2h += kp.size * 144 + 4 * (1 + 13 * plan.octave_max + 4)
-            if exchange is not None:
+            if exchange is not None and gather:
                 started = exchange.begin(sdist.device_records_tensor(plan, kp.size), plan)
                 if pending is not None:
                     pending.finish()
@@ -335,14 +337,16 @@ def main():
     launches0 = plan.launches
     regions = [device_region(False) for _ in range(max(args.repeats, 1))]
     launches = (plan.launches - launches0) // max(args.repeats, 1)
-    # throughput with and without the gather (the images are independent: the exchange is the only collective)
-    nogather = [device_region(False, gather=False) for _ in range(3)] if world > 1 else None
+    # throughput without and with the gather.  The images are independent, so the data path has no
+    # collective (`value`); the all-gather of every step's records to every rank is an extra, timed separately
+    withgather = [device_region(False, gather=True) for _ in range(3)] if world > 1 else None
     plan.set_profile(True)   # stage breakdown + roofline launches: a separate region (event pairs cost ~1 %)
     prof = device_region(True)
     plan.set_profile(False)
     for kp in plan.keypoints_many(host_imgs[i % N_IMAGES] for i in range(3)):
         pass
     e2e_regions = [e2e_region() for _ in range(max(min(args.repeats, 3), 1))]
+    e2e_gather = [e2e_region(gather=True) for _ in range(2)] if world > 1 else None
     sync_s, sync_kp = sync_region()
     sampler.stop_flag = True
 
@@ -352,14 +356,16 @@ def main():
     dev_s, nkp, wall = median_by(regions, lambda r: r[0])[:3]
     e2e_s, e2e_kp, d2h = median_by(e2e_regions, lambda r: r[0])
     all_dev_s = [r[0] for r in regions]
-    ng_s = median_by(nogather, lambda r: r[0])[0] if nogather else 0.0
+    wg_s = median_by(withgather, lambda r: r[0])[0] if withgather else 0.0
+    wg_e2e_s = median_by(e2e_gather, lambda r: r[0])[0] if e2e_gather else 0.0
     if world > 1:
-        t = torch.tensor([dev_s, e2e_s, sync_s, float(nkp), float(e2e_kp), float(launches), float(sync_kp), ng_s],
+        t = torch.tensor([dev_s, e2e_s, sync_s, float(nkp), float(e2e_kp), float(launches), float(sync_kp), wg_s, wg_e2e_s],
                          dtype=torch.float64, device="cuda")
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        dev_s, e2e_s, sync_s, ng_s = float(tmax[0]), float(tmax[1]), float(tmax[2]), float(tmax[7])
+        dev_s, e2e_s, sync_s, wg_s, wg_e2e_s = (float(tmax[0]), float(tmax[1]), float(tmax[2]), float(tmax[7]),
+                                                float(tmax[8]))
         nkp, e2e_kp, launches, sync_kp = float(t[3]), float(t[4]), int(t[5]), float(t[6])
     if rank != 0:
         if world > 1:
@@ -411,10 +417,13 @@ def main():
         "clocks": sampler.summary(),
     }
     if world > 1:
-        line["exchange_host_ms_per_step"] = 1e3 * host_x[0] / (args.steps * (len(regions) + 1))
-        line["without_gather"] = {"value": nkp / ng_s, "ms_per_step": 1e3 * ng_s / args.steps,
-                                  "note": "the same device-resident region without the per-step all-gather of the "
-                                          "records (every rank keeps its own keypoints)"}
+        line["with_gather"] = {
+            "value": nkp / wg_s, "ms_per_step": 1e3 * wg_s / args.steps,
+            "e2e_value": e2e_kp / wg_e2e_s, "e2e_ms_per_step": 1e3 * wg_e2e_s / args.steps,
+            "exchange_host_ms_per_step": 1e3 * host_x[0] / (args.steps * len(withgather)),
+            "note": "the same regions with every step's keypoint records all-gathered to every rank over NCCL "
+                    "(dist.RecordExchange: one collective per step on a side stream, completed one pipeline step "
+                    "later); not part of `value`: the images are independent, the path itself has no exchange step"}
     if not args.no_cpu_baseline and world == 1:
         from oracle import siftref
         img = np.array(host_imgs[0])

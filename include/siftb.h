@@ -78,8 +78,13 @@ SIFTB_API int siftb_plan_octaves(const siftb_plan *plan);
 SIFTB_API int siftb_plan_kpsize(const siftb_plan *plan);      /* per-octave keypoint slots, plan.py:243 */
 SIFTB_API int siftb_plan_capacity(const siftb_plan *plan);    /* records the plan can return for one image (all octaves) */
 SIFTB_API int siftb_plan_octave_shape(const siftb_plan *plan, int octave, int *width, int *height);
-SIFTB_API uint64_t siftb_plan_device_bytes(const siftb_plan *plan);   /* plan.py:226 _calc_memory */
-SIFTB_API void *siftb_plan_stream(const siftb_plan *plan);            /* cudaStream_t of the plan's queue */
+SIFTB_API uint64_t siftb_plan_device_bytes(const siftb_plan *plan);   /* plan.py:226 _calc_memory; grows once, when the
+                                                                        * second lane is first needed */
+/* cudaStream_t of the plan's queue: it is ordered after every image submitted so far (work enqueued on it, or an event
+ * recorded on it, runs after their kernels).  The kernels themselves run on two private streams ("lanes", each with
+ * its own planes: images that are in flight together are computed two at a time); to order a submit after your own
+ * producer use siftb_plan_wait_stream, not this stream. */
+SIFTB_API void *siftb_plan_stream(const siftb_plan *plan);
 SIFTB_API int siftb_plan_set_profile(siftb_plan *plan, int enable);   /* plan.py:185-186 PROFILING_ENABLE */
 /* Which of the reference's two kernel families the orientation / descriptor stages reproduce (plan.py:667-725 picks
  * by device type; they give different numbers): 0 = orientation_cpu.cl + keypoints_cpu.cl
@@ -113,7 +118,8 @@ SIFTB_API int siftb_plan_keypoints(siftb_plan *plan, const void *image, int flag
                          int *n_out, int *n_per_octave, float *minmax);
 
 /* The same path split in two so that callers can overlap the copy of image k+1 with the kernels of
- * image k: submit() enqueues copy + all kernels on the plan's stream and returns immediately;
+ * image k: submit() enqueues copy + all kernels (on one of the plan's two compute lanes: an image submitted while
+ * another is in flight takes the other lane and the two are computed concurrently) and returns immediately;
  * collect() waits for the oldest submitted image and copies its records to the host.  Up to three submits may be
  * in flight per plan (results come back in submission order). */
 SIFTB_API int siftb_plan_submit(siftb_plan *plan, const void *image, int flags);

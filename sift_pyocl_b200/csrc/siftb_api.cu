@@ -228,6 +228,34 @@ extern "C" int siftb_host_free(void *ptr) {
     return 0;
 }
 
+// frees what lane_alloc() allocated (also a partly allocated lane); the lane's stream stays
+static void lane_release(siftb_plan *p, siftb_plan::Lane &L) {
+    auto drop = [&](auto *&ptr, size_t bytes) {
+        if (!ptr) return;
+        cudaFree(ptr);
+        ptr = nullptr;
+        p->dev_bytes -= bytes < p->dev_bytes ? bytes : p->dev_bytes;
+    };
+    const size_t N = (size_t)p->h * p->w;
+    drop(L.d_img, N * sizeof(float));
+    for (int o = 0; o < MAX_OCT; o++) {
+        const size_t pl = o < p->n_oct ? (size_t)p->opitch[o] * p->oh[o] * sizeof(float) : 0;
+        for (auto &q : L.G[o]) drop(q, pl);
+        for (auto &q : L.D[o]) drop(q, pl);
+        drop(L.cands[o], (size_t)p->cand_cap[o] * sizeof(float4));
+    }
+    for (int s = 0; s < NSLOT; s++) drop(L.d_pyr[s], sizeof(PyrTable));
+    drop(L.d_grad, sizeof(GradTable));
+    for (int o = 0; o < SIFTB_KOCT; o++) {
+        const size_t pl = o < p->n_oct ? (size_t)p->opitch[o] * p->oh[o] * sizeof(float) : 0;
+        for (int i = 0; i < 3; i++) drop(L.gop[o][i], 2 * pl);
+    }
+    drop(L.kp, (size_t)p->kp_cap * sizeof(float4));
+    drop(L.kp_tag, (size_t)p->kp_cap * sizeof(int));
+    drop(L.kp_order, (size_t)p->kp_cap * sizeof(int));
+    L.ready = false;
+}
+
 extern "C" int siftb_plan_destroy(siftb_plan *p) {
     if (!p) return 0;
     DeviceGuard dg_(p->device);
@@ -238,17 +266,7 @@ extern "C" int siftb_plan_destroy(siftb_plan *p) {
     for (int s = 0; s < NSLOT; s++) { cudaFree(p->d_raws[s]); cudaFree(p->outs[s]); cudaFree(p->d_cnts[s]); }
     p->d_warp.release();
     for (auto &L : p->lanes) {
-        cudaFree(L.d_img);
-        for (int o = 0; o < MAX_OCT; o++) {
-            for (auto q : L.G[o]) cudaFree(q);
-            for (auto q : L.D[o]) cudaFree(q);
-            cudaFree(L.cands[o]);
-        }
-        for (int s = 0; s < NSLOT; s++) cudaFree(L.d_pyr[s]);
-        cudaFree(L.d_grad);
-        for (int o = 0; o < SIFTB_KOCT; o++)
-            for (int i = 0; i < 3; i++) cudaFree(L.gop[o][i]);
-        cudaFree(L.kp); cudaFree(L.kp_tag); cudaFree(L.kp_order);
+        lane_release(p, L);
         if (L.stream) cudaStreamDestroy(L.stream);
     }
     cudaFree(p->d_queue);
@@ -612,7 +630,8 @@ static int submit_impl(siftb_plan *p, const void *image, int flags) {
     if (p->n_flight > 0 && p->max_lanes > 1 && !p->profile) {
         li = (p->last_lane + 1) % p->max_lanes;
         if (!p->lanes[li].ready && lane_alloc(p, p->lanes[li])) {
-            // no memory for a second set of planes: stay on one lane (what was allocated is released with the plan)
+            // no memory for a second set of planes: give back what was allocated and stay on one lane
+            lane_release(p, p->lanes[li]);
             cudaGetLastError();
             p->max_lanes = 1;
             li = 0;

@@ -104,7 +104,8 @@ class RecordExchange(object):
 
     Every rank contributes a slab of ``capacity + 1`` rows of 144 bytes: row 0 carries the count (int64), rows
     1.. the records.  ``begin()`` copies the local records into the send slab and starts ONE all-gather on a side
-    stream; ``finish()`` -- typically one pipeline step later -- reads the counts out of the gathered slabs.  All
+    stream; ``finish()`` -- typically one pipeline step later -- reads the gathered counts, which the copy engine has
+    placed in page-locked host memory right after the collective (no kernel, no host wait beyond the event).  All
     buffers are allocated once (``capacity`` must be the same on every rank); a step whose count exceeds the
     capacity falls back to the exact-size exchange and enlarges the slabs.
     """
